@@ -1,0 +1,163 @@
+/*
+ * fot.h -- C ABI of the B200-native Frenet optimal-trajectory candidate sweep.
+ *
+ * This is the drop-in boundary for ONE hot path of mnhrk15/integrated_path_planning:
+ * everything `FrenetPlanner.plan()` does between "ego state already in the Frenet
+ * frame" and "best FrenetPath selected"  (reference src/planning/frenet_planner.py:271-294,
+ * i.e. _generate_frenet_paths :376, _generate_brake_candidates :453, _calc_global_paths :736,
+ * _check_paths :891, _apply_stop_distance_filter :307, _select_best_path :1235).
+ * The reference has no FFI of its own (it is pure Python); these entry points are what a
+ * ctypes binding of that path binds.  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - all floating point is IEEE binary64 ("double"), as in the reference;
+ *   - "device" pointers are CUDA device pointers on the handle's device (e.g. torch
+ *     tensor .data_ptr()); "host" pointers are ordinary process memory;
+ *   - every function returns FOT_OK (0) or a negative FOT_ERR_* code; "no valid path"
+ *     is NOT an error: best_idx = -1 (reference returns None, frenet_planner.py:298-299).
+ *   - candidate index = generation order of the reference (:398-449):
+ *     ((j_T * n_v + k_v) * n_d + i_d), brake-ladder candidates appended after the grid.
+ */
+#ifndef FOT_H_
+#define FOT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOT_ABI_VERSION 1
+#define FOT_MAX_CIRCLES 8
+#define FOT_N_STATS 8    /* ok, max_speed, max_accel, max_curvature, max_lat_accel, road_bound, collision, stop_distance */
+#define FOT_N_SERIES 15  /* t s s_d s_dd s_ddd d d_d d_dd d_ddd x y yaw c v a  (data_structures.py:149-181) */
+
+/* candidate categories (frenet_planner.py:910-918, :324; DROP = silently discarded :933-956) */
+enum {
+  FOT_CAT_OK = 0, FOT_CAT_SPEED = 1, FOT_CAT_ACCEL = 2, FOT_CAT_CURV = 3, FOT_CAT_LAT = 4,
+  FOT_CAT_ROAD = 5, FOT_CAT_COLL = 6, FOT_CAT_STOP = 7, FOT_CAT_DROP = 8
+};
+
+enum {
+  FOT_OK = 0,
+  FOT_ERR_ARG = -1,        /* bad argument / unsupported size */
+  FOT_ERR_CUDA = -2,       /* CUDA runtime error (see fot_last_error) */
+  FOT_ERR_NO_DEVICE = -3,  /* no CUDA device: there is no CPU fallback */
+  FOT_ERR_TOO_LARGE = -4   /* time grid does not fit shared memory */
+};
+
+/* dynamic-obstacle modes (frenet_planner.py:1043-1047) */
+enum { FOT_DYN_NONE = 0, FOT_DYN_SINGLE = 1, FOT_DYN_DISTRIBUTION = 2 };
+
+/* Planner-constant knobs: FrenetPlanner.__init__ (frenet_planner.py:149-210). */
+typedef struct fot_config {
+  double dt;               /* :171 */
+  double max_speed;        /* constructor value; teleport guard uses max(override, this) (:955) */
+  double max_road_width;   /* road-bound check (:982) */
+  double k_j, k_t, k_d, k_s_dot, k_lat, k_lon;   /* :187-192 */
+  double collide_r2;       /* sq_rubicon     = max(ego_radius + obstacle_radius, 1e-6) ** 2            (:1172-1174) */
+  double collide_r2_single;/* sq_rubicon_dyn = (that radius * collision_margin_inflation) ** 2; used by the
+                              single-sample dynamic test only (:1173-1175, :1072).  Both are evaluated by the
+                              host with the reference's own expression so the thresholds are bit-identical. */
+  double chance_epsilon;   /* :197 */
+  double circle_offsets[FOT_MAX_CIRCLES]; /* EgoFootprint.offsets (footprint.py:66-81) */
+  int32_t n_circles;       /* 0 = single circle at the path point (footprint None, :1152) */
+  int32_t n_T;             /* horizon grid size (:397-398) */
+  int32_t n_d;             /* lateral grid size (:419-420) */
+  int32_t n_B;             /* brake-ladder horizons that fit max_t (:475-485) */
+  int32_t n_total;         /* brake-candidate samples: round(max_t/dt)+1 (:473) */
+  int32_t nx;              /* spline knots */
+} fot_config_t;
+
+/* Planner-constant tables, all HOST pointers (copied at create).
+ * The horizon tables are built by the host exactly as the reference builds its TimeCache
+ * (:586-617): n_steps = int(round(T/dt)); inv4/inv5 = numpy.linalg.inv of the quartic/quintic
+ * boundary matrices (row-major 2x2 / 3x3).  The kernel applies them in the same accumulation
+ * order as the reference's `b @ A_inv.T` (:640, :683). */
+typedef struct fot_tables {
+  const double*  T;        /* [n_T]   T_j = min_t + j*dt */
+  const int32_t* n_steps;  /* [n_T]   */
+  const double*  inv4;     /* [n_T][4] */
+  const double*  inv5;     /* [n_T][9] */
+  const double*  Tb;       /* [n_B]   brake horizons */
+  const int32_t* n_steps_b;/* [n_B]   */
+  const double*  inv4b;    /* [n_B][4] */
+  const double*  inv5b;    /* [n_B][9] */
+  const double*  d_grid;   /* [n_d]   lateral targets (:420) */
+  /* natural cubic spline, CubicSpline1D coefficients (cubic_spline.py:23-45) */
+  const double*  knots;    /* [nx] */
+  const double*  xa; const double* xb; const double* xc; const double* xd; /* [nx],[nx-1],[nx],[nx-1] */
+  const double*  ya; const double* yb; const double* yc; const double* yd;
+} fot_tables_t;
+
+/* One batch of independent planning queries (one reference plan() call each). */
+typedef struct fot_batch {
+  int32_t n_q;
+  int32_t n_v_max;            /* row stride of v_grid */
+  const double*  frenet;      /* [n_q][6]  s, s_d, s_dd, d, d_d, d_dd   (:371) */
+  const double*  target_speed;/* [n_q]     (:232) */
+  const double*  limits;      /* [n_q][4]  max_speed, max_accel, max_curvature, max_lat_accel after overrides (:921-930) */
+  const double*  stop_dist;   /* [n_q]     max_stop_distance, NaN = None (:285) */
+  const double*  v_grid;      /* [n_q][n_v_max] terminal-speed grid (:410-413) */
+  const int32_t* n_v;         /* [n_q]     entries used in each v_grid row */
+  const double*  static_obs;  /* [n_q or 1][n_static][2]  (:1181-1198); may be NULL when n_static == 0 */
+  int32_t n_static;
+  int32_t static_per_query;   /* 0: one set shared by all queries */
+  const double*  dyn;         /* [n_q][S][P][T_obs][2] reference layout (:242, :246); NULL when dyn_mode == NONE */
+  int32_t S, P, T_obs;
+  int32_t dyn_mode;           /* FOT_DYN_* */
+} fot_batch_t;
+
+/* Results.  cand_cat / cand_cost are optional diagnostics (may be NULL). */
+typedef struct fot_result {
+  int32_t* best_idx;    /* [n_q]  generation-order index of the winner, -1 = none */
+  double*  best_cost;   /* [n_q]  +inf when none */
+  int32_t* stats;       /* [n_q][FOT_N_STATS]  last_check_stats counts (:291) */
+  int32_t* winner_len;  /* [n_q]  samples kept after NaN-prefix truncation (:866) */
+  double*  winner;      /* [n_q][FOT_N_SERIES][n_t_max]  winner sequences */
+  uint8_t* cand_cat;    /* [n_q][cand_stride] or NULL */
+  double*  cand_cost;   /* [n_q][cand_stride] or NULL */
+  int32_t  cand_stride;
+  int32_t  reserved;
+} fot_result_t;
+
+typedef struct fot_handle fot_handle_t;
+
+/* ABI version of the loaded library. */
+int fot_abi_version(void);
+/* Human-readable text of the last error on this thread. */
+const char* fot_last_error(void);
+
+/* Replaces FrenetPlanner.__init__ for the sweep (frenet_planner.py:149-225): copies knobs,
+ * horizon tables and spline coefficients to `device`, creates the stream and scratch. */
+int fot_create(const fot_config_t* cfg, const fot_tables_t* tables, int device, fot_handle_t** out);
+int fot_destroy(fot_handle_t* h);
+
+/* Longest candidate (samples); the row length of fot_result_t.winner. */
+int fot_n_t_max(const fot_handle_t* h);
+/* Candidates of a query with n_v terminal speeds; brake ladder counted when has_brake != 0. */
+int fot_candidate_count(const fot_handle_t* h, int n_v, int has_brake);
+
+/* Replaces frenet_planner.py:271-294 for n_q queries.  All pointers in `batch` and `res` are
+ * DEVICE pointers.  Asynchronous on `stream` (a cudaStream_t, NULL = the handle's own stream,
+ * which is then synchronised before returning). */
+int fot_plan_batch_device(fot_handle_t* h, const fot_batch_t* batch, const fot_result_t* res, void* stream);
+
+/* Same call with HOST pointers everywhere: stages inputs through the handle's pinned buffers,
+ * runs the kernels, copies the results back, and returns when they are in `res`. This is the
+ * entry point FrenetPlanner.plan() binds. */
+int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* batch, const fot_result_t* res);
+
+/* Device-side time of the kernels of the last fot_plan_batch_* call on this handle, in ms
+ * (CUDA events on the launching stream); negative if unavailable. */
+float fot_last_kernel_ms(const fot_handle_t* h);
+
+/* Pipe-throughput probes used to anchor the roofline denominator (MEASURED_PEAKS.json holds no
+ * FP64/FP32 figure).  kind: 0 = FP64 FMA, 1 = FP32 FMA, 2 = packed FP32x2 FMA.
+ * Writes achieved TFLOP/s (2 flops per FMA). */
+int fot_probe_fma_tflops(int device, int kind, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOT_H_ */

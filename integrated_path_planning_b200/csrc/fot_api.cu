@@ -1,0 +1,369 @@
+// fot_api.cu -- C ABI (include/fot.h) over the sweep kernels.  Host side only: argument
+// checks, device tables, scratch, launches.  There is no CPU fallback anywhere in this file:
+// without a CUDA device every entry point that computes returns FOT_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "fot_kernels.cuh"
+
+using namespace fot;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess)
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+  else
+    snprintf(buf, sizeof buf, "%s", what);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return fail(FOT_ERR_CUDA, #call, e__);      \
+  } while (0)
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Growable device / pinned-host buffer.
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool host = false;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    release();
+    size_t want = n + n / 4 + 256;
+    cudaError_t e = host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want; else p = nullptr;
+    return e;
+  }
+  void release() {
+    if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
+    p = nullptr; cap = 0;
+  }
+};
+
+}  // namespace
+
+struct fot_handle {
+  int device = 0;
+  Plan plan{};
+  void* tables_dev = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int smem_optin = 0;
+  Buf obs_tm, part_cost, part_idx;   // device scratch
+  Buf stage_h, stage_d, out_h, out_d, dyn_d, stat_d;   // host-API staging
+  fot_handle() { stage_h.host = true; out_h.host = true; }
+};
+
+extern "C" int fot_abi_version(void) { return FOT_ABI_VERSION; }
+extern "C" const char* fot_last_error(void) { return g_err.c_str(); }
+
+extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int device, fot_handle_t** out) {
+  if (!cfg || !tb || !out) return fail(FOT_ERR_ARG, "fot_create: null argument");
+  *out = nullptr;
+  if (cfg->n_T < 1 || cfg->n_d < 1 || cfg->n_B < 0 || cfg->nx < 2 || cfg->n_total < 1 ||
+      cfg->n_circles < 0 || cfg->n_circles > FOT_MAX_CIRCLES || !(cfg->dt > 0.0))
+    return fail(FOT_ERR_ARG, "fot_create: bad grid sizes");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(FOT_ERR_NO_DEVICE, "fot_create: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= n_dev) return fail(FOT_ERR_ARG, "fot_create: bad device ordinal");
+  CK(cudaSetDevice(device));
+
+  fot_handle* h = new fot_handle();
+  h->device = device;
+  h->plan.cfg = *cfg;
+  const int nT = cfg->n_T, nB = cfg->n_B, nd = cfg->n_d, nx = cfg->nx;
+  int n_t_max = nB > 0 ? cfg->n_total : 0;
+  for (int j = 0; j < nT; ++j) {
+    if (tb->n_steps[j] < 1) { delete h; return fail(FOT_ERR_ARG, "fot_create: horizon shorter than 2 samples"); }
+    n_t_max = std::max(n_t_max, tb->n_steps[j] + 1);
+  }
+  for (int j = 0; j < nB; ++j)
+    if (tb->n_steps_b[j] + 1 > cfg->n_total) { delete h; return fail(FOT_ERR_ARG, "fot_create: brake horizon longer than max_t"); }
+  h->plan.n_t_max = n_t_max;
+
+  // one device blob: doubles first, then the int tables
+  std::vector<double> dbl;
+  auto push = [&](const double* p, size_t n) { size_t o = dbl.size(); dbl.insert(dbl.end(), p, p + n); return o; };
+  const size_t oT = push(tb->T, nT), oI4 = push(tb->inv4, 4 * (size_t)nT), oI5 = push(tb->inv5, 9 * (size_t)nT);
+  const size_t oTb = nB ? push(tb->Tb, nB) : 0, oI4b = nB ? push(tb->inv4b, 4 * (size_t)nB) : 0,
+               oI5b = nB ? push(tb->inv5b, 9 * (size_t)nB) : 0;
+  const size_t oD = push(tb->d_grid, nd), oK = push(tb->knots, nx);
+  const size_t oxa = push(tb->xa, nx), oxb = push(tb->xb, nx - 1), oxc = push(tb->xc, nx), oxd = push(tb->xd, nx - 1);
+  const size_t oya = push(tb->ya, nx), oyb = push(tb->yb, nx - 1), oyc = push(tb->yc, nx), oyd = push(tb->yd, nx - 1);
+  std::vector<int32_t> ints(tb->n_steps, tb->n_steps + nT);
+  if (nB) ints.insert(ints.end(), tb->n_steps_b, tb->n_steps_b + nB);
+  const size_t dbytes = dbl.size() * sizeof(double), ibytes = ints.size() * sizeof(int32_t);
+  cudaError_t e = cudaMalloc(&h->tables_dev, dbytes + ibytes);
+  if (e != cudaSuccess) { delete h; return fail(FOT_ERR_CUDA, "cudaMalloc(tables)", e); }
+  e = cudaMemcpy(h->tables_dev, dbl.data(), dbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy((char*)h->tables_dev + dbytes, ints.data(), ibytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(h->tables_dev); delete h; return fail(FOT_ERR_CUDA, "cudaMemcpy(tables)", e); }
+  const double* D = (const double*)h->tables_dev;
+  const int32_t* I = (const int32_t*)((char*)h->tables_dev + dbytes);
+  Plan& P = h->plan;
+  P.T = D + oT; P.inv4 = D + oI4; P.inv5 = D + oI5;
+  P.Tb = D + oTb; P.inv4b = D + oI4b; P.inv5b = D + oI5b;
+  P.d_grid = D + oD; P.knots = D + oK;
+  P.xa = D + oxa; P.xb = D + oxb; P.xc = D + oxc; P.xd = D + oxd;
+  P.ya = D + oya; P.yb = D + oyb; P.yc = D + oyc; P.yd = D + oyd;
+  P.n_steps = I; P.n_steps_b = I + nT;
+
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  CK(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  h->smem_optin -= 2048;   // leave room for the kernels' static shared memory
+  CK(cudaFuncSetAttribute(fot_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  *out = h;
+  return FOT_OK;
+}
+
+extern "C" int fot_destroy(fot_handle_t* h) {
+  if (!h) return FOT_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (Buf* b : {&h->obs_tm, &h->part_cost, &h->part_idx, &h->stage_h, &h->stage_d, &h->out_h, &h->out_d,
+                 &h->dyn_d, &h->stat_d})
+    b->release();
+  if (h->tables_dev) cudaFree(h->tables_dev);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return FOT_OK;
+}
+
+extern "C" int fot_n_t_max(const fot_handle_t* h) { return h ? h->plan.n_t_max : FOT_ERR_ARG; }
+
+extern "C" int fot_candidate_count(const fot_handle_t* h, int n_v, int has_brake) {
+  if (!h || n_v < 0) return FOT_ERR_ARG;
+  return h->plan.cfg.n_T * n_v * h->plan.cfg.n_d + (has_brake ? h->plan.cfg.n_B : 0);
+}
+
+// Block geometry: how many (speed, lateral) candidates one block takes, bounded by the shared
+// memory its per-speed reference samples need.
+static int sweep_geometry(const fot_handle* h, int n_v_max, SweepGeom* g, size_t* smem_bytes) {
+  const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B;
+  const size_t budget = std::min<size_t>((size_t)h->smem_optin, 200 * 1024);
+  auto bytes = [&](int kv) {
+    return ((size_t)5 * NT + (size_t)kRefFields * kv * NT + 6 * (size_t)kv) * sizeof(double) + (size_t)kv * sizeof(int32_t) + 16;
+  };
+  int ch = std::min(kSweepThreads, n_v_max * nd);
+  ch = std::max(ch, 1);
+  int kv;
+  for (;;) {
+    kv = std::min(n_v_max, (ch - 1) / nd + 2);
+    if (bytes(kv) <= std::min<size_t>(budget, 72 * 1024) || ch <= nd || ch == 1) break;   // keep >= 3 blocks/SM when possible
+    ch = std::max(nd, ch / 2);
+  }
+  while (bytes(kv) > budget && ch > 1) { ch = std::max(1, ch / 2); kv = std::min(n_v_max, (ch - 1) / nd + 2); }
+  if (bytes(kv) > budget) return fail(FOT_ERR_TOO_LARGE, "time grid too long for shared memory");
+  g->ch_eff = ch;
+  g->kv_cap = std::max(kv, 1);
+  g->chunks_per_T = (n_v_max * nd + ch - 1) / ch;
+  g->brake_blocks = nB > 0 ? (nB + g->kv_cap - 1) / g->kv_cap : 0;
+  g->blocks_per_query = h->plan.cfg.n_T * g->chunks_per_T + g->brake_blocks;
+  *smem_bytes = bytes(g->kv_cap);
+  return FOT_OK;
+}
+
+static int check_batch(const fot_handle* h, const fot_batch_t* b, const fot_result_t* r) {
+  if (!h || !b || !r) return fail(FOT_ERR_ARG, "null argument");
+  if (b->n_q < 1 || b->n_v_max < 1) return fail(FOT_ERR_ARG, "n_q and n_v_max must be >= 1");
+  if (!b->frenet || !b->target_speed || !b->limits || !b->stop_dist || !b->v_grid || !b->n_v)
+    return fail(FOT_ERR_ARG, "null query array");
+  if (b->n_static < 0 || (b->n_static > 0 && !b->static_obs)) return fail(FOT_ERR_ARG, "static obstacles missing");
+  if (b->dyn_mode != FOT_DYN_NONE) {
+    if (b->dyn_mode != FOT_DYN_SINGLE && b->dyn_mode != FOT_DYN_DISTRIBUTION) return fail(FOT_ERR_ARG, "bad dyn_mode");
+    if (!b->dyn || b->S < 1 || b->P < 1 || b->T_obs < 1) return fail(FOT_ERR_ARG, "dynamic obstacle shape");
+    if (b->dyn_mode == FOT_DYN_SINGLE && b->S != 1) return fail(FOT_ERR_ARG, "single-sample mode needs S == 1");
+    if (b->dyn_mode == FOT_DYN_DISTRIBUTION && b->S > 64 &&
+        std::floor(h->plan.cfg.chance_epsilon * (double)b->S) > 0.0)
+      return fail(FOT_ERR_ARG, "chance_epsilon > 0 supports at most 64 samples");
+  }
+  if (!r->best_idx || !r->best_cost || !r->stats || !r->winner_len || !r->winner)
+    return fail(FOT_ERR_ARG, "null result array");
+  if ((r->cand_cat || r->cand_cost) && r->cand_stride < fot_candidate_count(h, b->n_v_max, 1))
+    return fail(FOT_ERR_ARG, "cand_stride too small");
+  return FOT_OK;
+}
+
+static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r, cudaStream_t st) {
+  SweepGeom g;
+  size_t smem = 0;
+  int rc = sweep_geometry(h, b->n_v_max, &g, &smem);
+  if (rc != FOT_OK) return rc;
+  const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
+  const size_t n_part = (size_t)b->n_q * g.blocks_per_query;
+  if ((size_t)b->n_q * (size_t)g.blocks_per_query > 0x7fffffffull) return fail(FOT_ERR_ARG, "batch too large for one launch");
+  CK(h->part_cost.reserve(n_part * sizeof(double)));
+  CK(h->part_idx.reserve(n_part * sizeof(int32_t)));
+  const int SP = has_dyn ? b->S * b->P : 0;
+  if (has_dyn) CK(h->obs_tm.reserve((size_t)b->n_q * b->T_obs * SP * sizeof(double2)));
+
+  Batch B{};
+  B.n_q = b->n_q; B.n_v_max = b->n_v_max;
+  B.frenet = b->frenet; B.target = b->target_speed; B.limits = b->limits; B.stop_dist = b->stop_dist;
+  B.v_grid = b->v_grid; B.n_v = b->n_v;
+  B.static_obs = b->n_static > 0 ? (const double2*)b->static_obs : nullptr;
+  B.n_static = b->n_static; B.static_per_query = b->static_per_query;
+  B.obs_tm = has_dyn ? (const double2*)h->obs_tm.p : nullptr;
+  B.S = has_dyn ? b->S : 0; B.P = has_dyn ? b->P : 0; B.T_obs = has_dyn ? b->T_obs : 0; B.dyn_mode = b->dyn_mode;
+  Out O{};
+  O.best_idx = r->best_idx; O.best_cost = r->best_cost; O.stats = r->stats; O.winner_len = r->winner_len;
+  O.winner = r->winner; O.cand_cat = r->cand_cat; O.cand_cost = r->cand_cost; O.cand_stride = r->cand_stride;
+  O.part_cost = (double*)h->part_cost.p; O.part_idx = (int32_t*)h->part_idx.p;
+
+  CK(cudaEventRecord(h->ev0, st));
+  CK(cudaMemsetAsync(r->stats, 0, (size_t)b->n_q * FOT_N_STATS * sizeof(int32_t), st));
+  if (r->cand_cat) CK(cudaMemsetAsync(r->cand_cat, FOT_CAT_DROP + 1, (size_t)b->n_q * r->cand_stride, st));
+  if (has_dyn) {
+    const long long warps = (long long)b->n_q * SP;
+    const int blocks = (int)((warps * 32 + 255) / 256);
+    fot_obstacle_prepass<<<blocks, 256, 0, st>>>((const double2*)b->dyn, (double2*)h->obs_tm.p, b->n_q, SP, b->T_obs);
+  }
+  fot_sweep<<<(unsigned)n_part, kSweepThreads, smem, st>>>(h->plan, B, O, g);
+  fot_winner<<<b->n_q, 128, (size_t)5 * h->plan.n_t_max * sizeof(double), st>>>(h->plan, B, O, g);
+  CK(cudaEventRecord(h->ev1, st));
+  CK(cudaGetLastError());
+  h->timed = true;
+  return FOT_OK;
+}
+
+extern "C" int fot_plan_batch_device(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r, void* stream) {
+  int rc = check_batch(h, b, r);
+  if (rc != FOT_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  rc = launch_all(h, b, r, st);
+  if (rc != FOT_OK) return rc;
+  if (!stream) CK(cudaStreamSynchronize(st));
+  return FOT_OK;
+}
+
+extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r) {
+  int rc = check_batch(h, b, r);
+  if (rc != FOT_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int nq = b->n_q, NT = h->plan.n_t_max;
+  // ---- small per-query arrays: one pinned blob, one H2D -------------------------------
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  const size_t o_fr = take((size_t)nq * 6 * 8), o_tg = take((size_t)nq * 8), o_lm = take((size_t)nq * 4 * 8),
+               o_sd = take((size_t)nq * 8), o_vg = take((size_t)nq * b->n_v_max * 8), o_nv = take((size_t)nq * 4);
+  CK(h->stage_h.reserve(off));
+  CK(h->stage_d.reserve(off));
+  char* sh = (char*)h->stage_h.p;
+  memcpy(sh + o_fr, b->frenet, (size_t)nq * 6 * 8);
+  memcpy(sh + o_tg, b->target_speed, (size_t)nq * 8);
+  memcpy(sh + o_lm, b->limits, (size_t)nq * 4 * 8);
+  memcpy(sh + o_sd, b->stop_dist, (size_t)nq * 8);
+  memcpy(sh + o_vg, b->v_grid, (size_t)nq * b->n_v_max * 8);
+  memcpy(sh + o_nv, b->n_v, (size_t)nq * 4);
+  CK(cudaMemcpyAsync(h->stage_d.p, sh, off, cudaMemcpyHostToDevice, st));
+  // ---- obstacle arrays straight from the caller's memory (pinned or pageable) ------------
+  fot_batch_t db = *b;
+  char* sd = (char*)h->stage_d.p;
+  db.frenet = (const double*)(sd + o_fr); db.target_speed = (const double*)(sd + o_tg);
+  db.limits = (const double*)(sd + o_lm); db.stop_dist = (const double*)(sd + o_sd);
+  db.v_grid = (const double*)(sd + o_vg); db.n_v = (const int32_t*)(sd + o_nv);
+  if (b->dyn_mode != FOT_DYN_NONE) {
+    const size_t bytes = (size_t)nq * b->S * b->P * b->T_obs * 16;
+    CK(h->dyn_d.reserve(bytes));
+    CK(cudaMemcpyAsync(h->dyn_d.p, b->dyn, bytes, cudaMemcpyHostToDevice, st));
+    db.dyn = (const double*)h->dyn_d.p;
+  }
+  if (b->n_static > 0) {
+    const size_t bytes = (size_t)(b->static_per_query ? nq : 1) * b->n_static * 16;
+    CK(h->stat_d.reserve(bytes));
+    CK(cudaMemcpyAsync(h->stat_d.p, b->static_obs, bytes, cudaMemcpyHostToDevice, st));
+    db.static_obs = (const double*)h->stat_d.p;
+  }
+  // ---- results: one device blob, one D2H ----------------------------------------------
+  size_t ro = 0;
+  auto rtake = [&](size_t bytes) { size_t o = ro; ro = align_up(ro + bytes); return o; };
+  const size_t r_bi = rtake((size_t)nq * 4), r_bc = rtake((size_t)nq * 8), r_st = rtake((size_t)nq * FOT_N_STATS * 4),
+               r_wl = rtake((size_t)nq * 4), r_w = rtake((size_t)nq * FOT_N_SERIES * NT * 8);
+  const size_t r_cc = r->cand_cat ? rtake((size_t)nq * r->cand_stride) : 0;
+  const size_t r_cs = r->cand_cost ? rtake((size_t)nq * r->cand_stride * 8) : 0;
+  CK(h->out_d.reserve(ro));
+  CK(h->out_h.reserve(ro));
+  char* od = (char*)h->out_d.p;
+  fot_result_t dr = *r;
+  dr.best_idx = (int32_t*)(od + r_bi); dr.best_cost = (double*)(od + r_bc); dr.stats = (int32_t*)(od + r_st);
+  dr.winner_len = (int32_t*)(od + r_wl); dr.winner = (double*)(od + r_w);
+  dr.cand_cat = r->cand_cat ? (uint8_t*)(od + r_cc) : nullptr;
+  dr.cand_cost = r->cand_cost ? (double*)(od + r_cs) : nullptr;
+  rc = launch_all(h, &db, &dr, st);
+  if (rc != FOT_OK) return rc;
+  CK(cudaMemcpyAsync(h->out_h.p, od, ro, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const char* oh = (const char*)h->out_h.p;
+  memcpy(r->best_idx, oh + r_bi, (size_t)nq * 4);
+  memcpy(r->best_cost, oh + r_bc, (size_t)nq * 8);
+  memcpy(r->stats, oh + r_st, (size_t)nq * FOT_N_STATS * 4);
+  memcpy(r->winner_len, oh + r_wl, (size_t)nq * 4);
+  memcpy(r->winner, oh + r_w, (size_t)nq * FOT_N_SERIES * NT * 8);
+  if (r->cand_cat) memcpy(r->cand_cat, oh + r_cc, (size_t)nq * r->cand_stride);
+  if (r->cand_cost) memcpy(r->cand_cost, oh + r_cs, (size_t)nq * r->cand_stride * 8);
+  return FOT_OK;
+}
+
+extern "C" float fot_last_kernel_ms(const fot_handle_t* h) {
+  if (!h || !h->timed) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+extern "C" int fot_probe_fma_tflops(int device, int kind, double* tflops_out) {
+  if (!tflops_out || kind < 0 || kind > 2) return fail(FOT_ERR_ARG, "fot_probe_fma_tflops: bad argument");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(FOT_ERR_NO_DEVICE, "no CUDA device");
+  CK(cudaSetDevice(device));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float* sink = nullptr;
+  CK(cudaMalloc(&sink, 4));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256, iters = kind == 0 ? 4096 : 8192;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0));
+    if (kind == 0) fot_probe_kernel<0><<<blocks, threads>>>(sink, iters);
+    else if (kind == 1) fot_probe_kernel<1><<<blocks, threads>>>(sink, iters);
+    else fot_probe_kernel<2><<<blocks, threads>>>(sink, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fmas = (double)blocks * threads * iters * 64.0 * (kind == 2 ? 2.0 : 1.0);
+    const double tf = 2.0 * fmas / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  CK(cudaGetLastError());
+  *tflops_out = best;
+  return FOT_OK;
+}

@@ -1,0 +1,255 @@
+// fot_device.cuh -- device-side numerics of the Frenet candidate sweep (sm_100a).
+//
+// Compiled with -fmad=false: every expression below keeps the reference's NumPy
+// association order and rounding (one rounding per * and +); fused multiply-adds
+// appear only where written explicitly as fma().  Reference citations are to
+// /root/reference/src/planning/frenet_planner.py ("fp.py"),
+// src/planning/cubic_spline.py ("cs.py") and src/core/coordinate_converter.py ("cc.py").
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "fot.h"
+
+namespace fot {
+
+// Planner constants resident on the device (pointers into one device blob).
+struct Plan {
+  fot_config_t cfg;
+  const double *T, *inv4, *inv5, *Tb, *inv4b, *inv5b, *d_grid;
+  const int32_t *n_steps, *n_steps_b;
+  const double *knots, *xa, *xb, *xc, *xd, *ya, *yb, *yc, *yd;
+  int32_t n_t_max;
+};
+
+// One batch, device pointers.
+struct Batch {
+  int32_t n_q, n_v_max;
+  const double *frenet, *target, *limits, *stop_dist, *v_grid;
+  const int32_t* n_v;
+  const double2* static_obs;
+  int32_t n_static, static_per_query;
+  const double2* obs_tm;   // time-major copy of the dynamic obstacles [n_q][T_obs][S*P]
+  int32_t S, P, T_obs, dyn_mode;
+};
+
+struct Out {
+  int32_t* best_idx; double* best_cost; int32_t* stats; int32_t* winner_len; double* winner;
+  uint8_t* cand_cat; double* cand_cost; int32_t cand_stride;
+  double* part_cost; int32_t* part_idx;   // [n_q][blocks_per_query] partial arg-min
+};
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ---- coefficient solve: `b @ A_inv.T` (fp.py:640, :683) -------------------------------
+// NumPy hands this product to BLAS; on the x86-64 builds in this image the accumulation
+// is a left-to-right FMA chain for >= 2 rows and (k = 1, 0, 2) for a single row (brake
+// candidates, target_speed = 0).  `single` selects the latter.
+__device__ __forceinline__ void apply_inv2(const double* __restrict__ A, double r0, double r1,
+                                           bool single, double& o0, double& o1) {
+  if (!single) {
+    o0 = fma(r1, A[1], r0 * A[0]);
+    o1 = fma(r1, A[3], r0 * A[2]);
+  } else {
+    o0 = fma(r0, A[0], r1 * A[1]);
+    o1 = fma(r0, A[2], r1 * A[3]);
+  }
+}
+__device__ __forceinline__ void apply_inv3(const double* __restrict__ A, double r0, double r1, double r2,
+                                           bool single, double& o0, double& o1, double& o2) {
+  if (!single) {
+    o0 = fma(r2, A[2], fma(r1, A[1], r0 * A[0]));
+    o1 = fma(r2, A[5], fma(r1, A[4], r0 * A[3]));
+    o2 = fma(r2, A[8], fma(r1, A[7], r0 * A[6]));
+  } else {
+    o0 = fma(r2, A[2], fma(r0, A[0], r1 * A[1]));
+    o1 = fma(r2, A[5], fma(r0, A[3], r1 * A[4]));
+    o2 = fma(r2, A[8], fma(r0, A[6], r1 * A[7]));
+  }
+}
+
+// Quartic longitudinal profile (fp.py:619-647).  `hold`: last polynomial sample; beyond it the
+// brake-ladder padding applies (position held, derivatives zero; fp.py:487-499).
+struct Lon {
+  double a0, a1, a2, a3, a4;
+  int hold;
+};
+__device__ __forceinline__ Lon lon_solve(const double* __restrict__ fs, double tv, double T,
+                                         const double* __restrict__ inv4, bool single, int hold) {
+  Lon L;
+  L.a0 = fs[0];
+  L.a1 = fs[1];
+  L.a2 = fs[2] / 2.0;
+  const double r0 = tv - L.a1 - 2.0 * L.a2 * T;
+  const double r1 = -2.0 * L.a2;
+  apply_inv2(inv4, r0, r1, single, L.a3, L.a4);
+  L.hold = hold;
+  return L;
+}
+// tt = shared table [5][NT] of t, t^2, t^3, t^4, t^5 built as fp.py:594-598.
+__device__ __forceinline__ double lon_p0(const Lon& L, const double* tt, int NT, int n) {
+  const int m = n > L.hold ? L.hold : n;
+  return L.a0 + L.a1 * tt[m] + L.a2 * tt[NT + m] + L.a3 * tt[2 * NT + m] + L.a4 * tt[3 * NT + m];
+}
+__device__ __forceinline__ double lon_p1(const Lon& L, const double* tt, int NT, int n) {
+  if (n > L.hold) return 0.0;
+  return L.a1 + 2.0 * L.a2 * tt[n] + 3.0 * L.a3 * tt[NT + n] + 4.0 * L.a4 * tt[2 * NT + n];
+}
+__device__ __forceinline__ double lon_p2(const Lon& L, const double* tt, int NT, int n) {
+  if (n > L.hold) return 0.0;
+  return 2.0 * L.a2 + 6.0 * L.a3 * tt[n] + 12.0 * L.a4 * tt[NT + n];
+}
+__device__ __forceinline__ double lon_p3(const Lon& L, const double* tt, int NT, int n) {
+  if (n > L.hold) return 0.0;
+  return 6.0 * L.a3 + 24.0 * L.a4 * tt[n];
+}
+
+// Quintic lateral profile (fp.py:660-691).
+struct Lat {
+  double a0, a1, a2, a3, a4, a5;
+  int hold;
+};
+__device__ __forceinline__ Lat lat_solve(const double* __restrict__ fs, double di, double T,
+                                         const double* __restrict__ inv5, bool single, int hold) {
+  Lat L;
+  L.a0 = fs[3];
+  L.a1 = fs[4];
+  L.a2 = fs[5] / 2.0;
+  const double r0 = di - L.a0 - L.a1 * T - L.a2 * T * T;
+  const double r1 = -L.a1 - 2.0 * L.a2 * T;
+  const double r2 = -2.0 * L.a2;
+  apply_inv3(inv5, r0, r1, r2, single, L.a3, L.a4, L.a5);
+  L.hold = hold;
+  return L;
+}
+__device__ __forceinline__ double lat_p0(const Lat& L, const double* tt, int NT, int n) {
+  const int m = n > L.hold ? L.hold : n;
+  return L.a0 + L.a1 * tt[m] + L.a2 * tt[NT + m] + L.a3 * tt[2 * NT + m] + L.a4 * tt[3 * NT + m] +
+         L.a5 * tt[4 * NT + m];
+}
+__device__ __forceinline__ double lat_p1(const Lat& L, const double* tt, int NT, int n) {
+  if (n > L.hold) return 0.0;
+  return L.a1 + 2.0 * L.a2 * tt[n] + 3.0 * L.a3 * tt[NT + n] + 4.0 * L.a4 * tt[2 * NT + n] +
+         5.0 * L.a5 * tt[3 * NT + n];
+}
+__device__ __forceinline__ double lat_p2(const Lat& L, const double* tt, int NT, int n) {
+  if (n > L.hold) return 0.0;
+  return 2.0 * L.a2 + 6.0 * L.a3 * tt[n] + 12.0 * L.a4 * tt[NT + n] + 20.0 * L.a5 * tt[2 * NT + n];
+}
+__device__ __forceinline__ double lat_p3(const Lat& L, const double* tt, int NT, int n) {
+  if (n > L.hold) return 0.0;
+  return 6.0 * L.a3 + 24.0 * L.a4 * tt[n] + 60.0 * L.a5 * tt[NT + n];
+}
+
+// np.sum over a contiguous float64 vector: NumPy's pairwise summation (8 interleaved
+// accumulators per <=128-element block, halving above that).  The jerk costs fp.py:718,:722
+// go through it, so the cost -- and with it the arg-min -- only reproduces with this order.
+template <class F>
+__device__ double np_pairwise_sum(const F& f, int lo, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r += f(lo + i);
+    return r;
+  }
+  if (n <= 128) {
+    double r0 = f(lo), r1 = f(lo + 1), r2 = f(lo + 2), r3 = f(lo + 3);
+    double r4 = f(lo + 4), r5 = f(lo + 5), r6 = f(lo + 6), r7 = f(lo + 7);
+    int i = 8;
+    const int stop = n - (n % 8);
+    for (; i < stop; i += 8) {
+      r0 += f(lo + i);     r1 += f(lo + i + 1); r2 += f(lo + i + 2); r3 += f(lo + i + 3);
+      r4 += f(lo + i + 4); r5 += f(lo + i + 5); r6 += f(lo + i + 6); r7 += f(lo + i + 7);
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += f(lo + i);
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return np_pairwise_sum(f, lo, n2) + np_pairwise_sum(f, lo + n2, n - n2);
+}
+
+// Reference-line sample at arc length s (cs.py:47-166, :215-288).  NaN outside the knot range.
+struct RefPt {
+  double rx, ry, rth, rk, rdk;
+};
+__device__ __forceinline__ RefPt spline_ref(const Plan& P, double s) {
+  RefPt o;
+  const int nx = P.cfg.nx;
+  if (!(s >= P.knots[0] && s <= P.knots[nx - 1])) {   // cs.py:62 (inclusive; NaN s fails both)
+    o.rx = o.ry = o.rth = o.rk = o.rdk = qnan();
+    return o;
+  }
+  int lo = 0, hi = nx;                                 // searchsorted(side='right') (cs.py:162)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (P.knots[mid] <= s) lo = mid + 1; else hi = mid;
+  }
+  int seg = lo - 1;
+  seg = seg < 0 ? 0 : (seg > nx - 2 ? nx - 2 : seg);   // cs.py:165
+  const double dx = s - P.knots[seg];
+  const double dx2 = dx * dx;
+  const double dx3 = dx2 * dx;
+  const double xa = P.xa[seg], xb = P.xb[seg], xc = P.xc[seg], xd = P.xd[seg];
+  const double ya = P.ya[seg], yb = P.yb[seg], yc = P.yc[seg], yd = P.yd[seg];
+  o.rx = xa + xb * dx + xc * dx2 + xd * dx3;           // cs.py:73-74
+  o.ry = ya + yb * dx + yc * dx2 + yd * dx3;
+  const double x1 = xb + 2.0 * xc * dx + 3.0 * xd * dx2;   // cs.py:100
+  const double y1 = yb + 2.0 * yc * dx + 3.0 * yd * dx2;
+  const double x2 = 2.0 * xc + 6.0 * xd * dx;              // cs.py:125
+  const double y2 = 2.0 * yc + 6.0 * yd * dx;
+  const double x3 = 6.0 * xd, y3 = 6.0 * yd;               // cs.py:149
+  o.rth = atan2(y1, x1);                                   // cs.py:287
+  const double D = x1 * x1 + y1 * y1;
+  const double rD = sqrt(D);
+  const double D15 = D * rD;                               // D ** 1.5
+  const double D25 = D * D * rD;                           // D ** 2.5
+  o.rk = (y2 * x1 - x2 * y1) / D15;                        // cs.py:246
+  const double a = x1 * y2 - y1 * x2;
+  const double b = x1 * y3 - y1 * x3;
+  const double c = x1 * x2 + y1 * y2;
+  o.rdk = b / D15 - 3.0 * a * c / D25;                     // cs.py:273
+  return o;
+}
+
+// Frenet -> Cartesian at one sample (fp.py:792-799 then cc.py:128-158).
+struct CartPt {
+  double x, y, kappa, v, a, ang;   // ang = delta_theta + rtheta, yaw = wrap(ang)
+};
+__device__ __forceinline__ CartPt to_cartesian(double rx, double ry, double cth, double sth, double rth,
+                                               double rk, double rdk, double sd, double sdd,
+                                               double d, double dd_t, double ddd_t) {
+  CartPt c;
+  double d_p = 0.0, d_pp = 0.0;
+  if (fabs(sd) > 1e-3) {                                   // fp.py:792 EPS_S_DOT
+    d_p = dd_t / sd;
+    d_pp = (ddd_t - d_p * sdd) / (sd * sd);
+  }
+  c.x = rx - sth * d;
+  c.y = ry + cth * d;
+  const double q = 1.0 - rk * d;
+  const double tan_d = d_p / q;
+  const double dth = atan2(d_p, q);
+  const double cos_d = cos(dth);
+  c.ang = dth + rth;
+  const double m = rdk * d + rk * d_p;
+  c.kappa = (((d_pp + m * tan_d) * cos_d * cos_d) / q + rk) * cos_d / q;
+  const double d_dot = d_p * sd;
+  c.v = sqrt(q * q * sd * sd + d_dot * d_dot);
+  const double dth_p = q / cos_d * c.kappa - rk;
+  c.a = sdd * q / cos_d + sd * sd / cos_d * (d_p * dth_p - m);
+  return c;
+}
+// normalize_angle (cc.py:173-182): np.angle(np.exp(1j*a)) = atan2(sin a, cos a).
+__device__ __forceinline__ double wrap_angle(double a) {
+  double s, c;
+  sincos(a, &s, &c);
+  return atan2(s, c);
+}
+
+// Lexicographic (cost, index) minimum: first strict minimum in generation order (fp.py:1254-1257).
+__device__ __forceinline__ void argmin_merge(double& c, int& i, double oc, int oi) {
+  if (oc < c || (oc == c && oi < i)) { c = oc; i = oi; }
+}
+
+}  // namespace fot

@@ -1,0 +1,132 @@
+"""Ego state -> Frenet initial conditions, on the host (O(1) per query, stateful).
+
+Restates reference `src/core/coordinate_converter.py:26-88` (Cartesian->Frenet formulas) and
+`:202-339` (nearest point on the path with the `_prev_s` window cache), plus the spatial->time
+derivative conversion of `frenet_planner.py:362-371`.  These produce the six numbers that seed
+every candidate polynomial, so they follow the reference's arithmetic literally.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def _f(v):
+    """numpy 0-d / 1-element result -> scalar."""
+    v = np.asarray(v)
+    return v.reshape(-1)[0] if v.size == 1 else v
+
+
+class CoordinateConverter:
+    """Nearest-point search with the reference's cache semantics (coordinate_converter.py:185-339)."""
+
+    WINDOW = 10.0        # half width of the cached local window [m]      (:223-224)
+    WINDOW_SAMPLES = 100  # (:225)
+    GLOBAL_STEP = 0.1    # (:322)
+
+    def __init__(self, reference_path):
+        self.reference_path = reference_path
+
+    # -- search --------------------------------------------------------------------------
+    def _xy(self, s):
+        px, py = self.reference_path.calc_position(s)
+        return _f(px), _f(py)
+
+    def _global_search(self, x, y):
+        length = self.reference_path.s[-1]
+        n = max(100, int(length / self.GLOBAL_STEP))
+        grid = np.linspace(0, length, n)
+        px, py = self.reference_path.calc_position(grid)
+        return grid[np.argmin(np.hypot(x - px, y - py))]
+
+    def find_nearest_point_on_path(self, x, y):
+        path_end = self.reference_path.s[-1]
+        best_s = 0.0
+        if hasattr(self, "_prev_s"):
+            lo = max(0.0, self._prev_s - self.WINDOW)
+            hi = min(path_end, self._prev_s + self.WINDOW)
+            nearest = float("inf")
+            for s in np.linspace(lo, hi, self.WINDOW_SAMPLES):
+                px, py = self._xy(s)
+                gap = math.hypot(x - px, y - py)
+                if gap < nearest:
+                    nearest, best_s = gap, s
+            # a minimum on the window edge (not the path end) means the cache is stale (:241-248)
+            stale = (abs(best_s - lo) < 1e-3 and lo > 0) or (abs(best_s - hi) < 1e-3 and hi < path_end)
+            if stale:
+                best_s = self._global_search(x, y)
+        else:
+            best_s = self._global_search(x, y)
+
+        step = 0.2                                   # 20 three-point refinements (:253-280)
+        for _ in range(20):
+            s_lo = max(0, best_s - step)
+            s_hi = min(path_end, best_s + step)
+            x_lo, y_lo = self._xy(s_lo)
+            x_hi, y_hi = self._xy(s_hi)
+            gap_lo = math.hypot(x - x_lo, y - y_lo)
+            gap_hi = math.hypot(x - x_hi, y - y_hi)
+            x_c, y_c = self._xy(best_s)
+            gap_c = math.hypot(x - x_c, y - y_c)
+            if gap_lo < gap_c and gap_lo < gap_hi:
+                best_s = s_lo
+            elif gap_hi < gap_c and gap_hi < gap_lo:
+                best_s = s_hi
+            else:
+                step *= 0.5
+        self._prev_s = best_s
+
+        rs = best_s
+        rx, ry = self._xy(rs)
+        if np.any(np.isnan([rx, ry])):
+            rs = self._global_search(x, y)
+            rx, ry = self._xy(rs)
+            if np.any(np.isnan([rx, ry])):
+                raise ValueError(f"Failed to find valid reference point for position ({x:.2f}, {y:.2f})")
+        rtheta = _f(self.reference_path.calc_yaw(rs))
+        rkappa = _f(self.reference_path.calc_curvature(rs))
+        rdkappa = _f(self.reference_path.calc_curvature_rate(rs))
+        if np.any(np.isnan([rtheta, rkappa, rdkappa])):
+            raise ValueError(f"Failed to calculate reference path properties at s={rs:.2f}")
+        return rs, rx, ry, rtheta, rkappa, rdkappa
+
+    # -- formulas ------------------------------------------------------------------------
+    @staticmethod
+    def cartesian_to_frenet(rs, rx, ry, rtheta, rkappa, rdkappa, x, y, v, a, theta, kappa
+                            ) -> Tuple[Tuple[float, float, float], Tuple[float, float, float]]:
+        """Apollo-style conversion; returns (s, s', s''), (d, d', d'') with d', d'' SPATIAL
+        derivatives (coordinate_converter.py:58-88)."""
+        off_x = x - rx
+        off_y = y - ry
+        cos_r = np.cos(rtheta)
+        sin_r = np.sin(rtheta)
+        side = cos_r * off_y - sin_r * off_x
+        d = np.copysign(np.hypot(off_x, off_y), side)
+        delta = theta - rtheta
+        tan_delta = np.tan(delta)
+        cos_delta = np.cos(delta)
+        one_minus_kd = 1 - rkappa * d
+        d_prime = one_minus_kd * tan_delta
+        kd_prime = rdkappa * d + rkappa * d_prime
+        d_pprime = (-kd_prime * tan_delta +
+                    one_minus_kd / (cos_delta * cos_delta) * (kappa * one_minus_kd / cos_delta - rkappa))
+        s_dot = v * cos_delta / one_minus_kd
+        delta_prime = one_minus_kd / cos_delta * kappa - rkappa
+        s_ddot = (a * cos_delta - s_dot * s_dot * (d_prime * delta_prime - kd_prime)) / one_minus_kd
+        return (rs, s_dot, s_ddot), (d, d_prime, d_pprime)
+
+
+def ego_to_frenet(converter: CoordinateConverter, ego_state, last_kappa: float) -> Optional[np.ndarray]:
+    """frenet_planner.py:334-374.  Returns [s, s_d, s_dd, d, d_d, d_dd] (time derivatives) or
+    None when the conversion fails (the reference logs and returns None)."""
+    try:
+        ref = converter.find_nearest_point_on_path(ego_state.x, ego_state.y)
+        (s, s_d, s_dd), (d, d_p, d_pp) = converter.cartesian_to_frenet(
+            *ref, ego_state.x, ego_state.y, ego_state.v, ego_state.a, ego_state.yaw, last_kappa)
+        d_d = d_p * s_d
+        d_dd = d_pp * s_d ** 2 + d_p * s_dd
+        return np.array([s, s_d, s_dd, d, d_d, d_dd], dtype=np.float64)
+    except Exception:
+        return None
