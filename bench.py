@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- Frenet candidate evals/s of the batched sweep (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch: Q independent planning queries per GPU
+(scenario_01 grid, 1261 candidates x 50 pedestrians x 1 sample,
+51 obstacle steps), queries sharded over ranks with no data-path collective (weak scaling: Q per
+GPU is fixed) and one small all_gather of the winners' (index, cost, stats) per step when N > 1.
+
+  value      dense evaluations/s with every input already resident in HBM (CUDA events, max over ranks)
+  e2e        the same through the host-pointer C-ABI call `fot_plan_batch_host` (what
+             FrenetPlanner.plan() binds): pinned host inputs -> H2D -> kernels -> D2H of the winners
+  roofline   the sweep kernel: algorithmic 5 FLOP x evaluations / its own CUDA-event time, against the
+             FP64 FMA peak measured on this GPU by fot_probe_fma_tflops (MEASURED_PEAKS.json holds no
+             FP64 figure)
+  cpu_baseline  the NumPy oracle (a port of the reference planner) on a bounded sample of the same
+             queries on this box's host cores (rank 0, N = 1 only)
+
+`--impl reference` times only that CPU leg (all host cores) and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import scenarios  # noqa: E402  (seeded synthetic fields; no reference access)
+
+METRIC = "frenet_candidate_evals_per_s"
+UNIT = "evals/s"
+FLOP_PER_EVAL = 5.0      # 2 SUB + 1 MUL + 1 FMA
+N_PEDS, T_OBS = 50, 51
+TARGET_SPEED = 6.0
+
+
+# ------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------
+def make_queries(first: int, count: int):
+    """Queries first..first+count-1 of config 4 (seed = global query id): ego state -> Frenet
+    state on the host exactly as plan() does it, plus that query's pedestrian field."""
+    from integrated_path_planning_b200 import CubicSpline2D
+    from integrated_path_planning_b200.frenet_host import CoordinateConverter, ego_to_frenet
+    from integrated_path_planning_b200.types import EgoVehicleState
+    spline = CubicSpline2D(*scenarios.STRAIGHT_60)
+    frenet = np.empty((count, 6))
+    dyn = np.empty((count, 1, N_PEDS, T_OBS, 2))
+    for i in range(count):
+        rng = np.random.default_rng(first + i)
+        dyn[i, 0] = scenarios.pedestrian_field(rng, N_PEDS, T_OBS, scenarios.S1_KNOBS["dt"])
+        ego = EgoVehicleState(x=rng.uniform(2, 20), y=rng.uniform(-1, 1), yaw=rng.normal(0, 0.05),
+                              v=rng.uniform(0, 8), a=rng.uniform(-1, 1))
+        fs = ego_to_frenet(CoordinateConverter(spline), ego, 0.0)
+        frenet[i] = fs
+    return spline, frenet, dyn
+
+
+def _oracle_worker(args):
+    frenet, dyn = args
+    from oracle import frenet_oracle as O
+    pl = O.OraclePlanner(O.Spline2D(*scenarios.STRAIGHT_60), O.Knobs(**scenarios.S1_KNOBS))
+    res = pl.plan_frenet(tuple(frenet), np.empty((0, 2)), dyn, TARGET_SPEED)
+    return int(res.n_points.sum()) * N_PEDS, res.best_index
+
+
+def cpu_leg(frenet, dyn, n_sample, cores, steps, warmup):
+    """Oracle (reference port) on `n_sample` queries per step over a process pool."""
+    import multiprocessing as mp
+    jobs = [(frenet[i], dyn[i, 0]) for i in range(n_sample)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(warmup):
+            pool.map(_oracle_worker, jobs[:cores])
+        times, evals = [], 0
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            out = pool.map(_oracle_worker, jobs)
+            times.append(time.perf_counter() - t0)
+            evals = sum(o[0] for o in out)
+    ms = 1e3 * float(np.mean(times))
+    return evals / (ms * 1e-3), ms, evals
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", type=int, default=4096, help="planning queries per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU sample (0 = 2 x cores)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = len(os.sched_getaffinity(0))
+    config = {"workload": "config4: 4096 independent plan() queries per GPU, scenario_01 grid "
+                          "(19 d x 11 T x 6 v + 7 brake = 1261 candidates, 58041 points), "
+                          "50 pedestrians x 1 sample x 51 steps, seed = query id",
+              "queries_per_gpu": args.queries, "parallelism": f"query-sharded x{world}",
+              "l2": "inputs (167 MB of obstacle tracks per step) exceed the 126 MB L2; no explicit flush"}
+
+    # ---------------- reference arm: CPU only --------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_sample = args.cpu_sample or 2 * cores
+        _, frenet, dyn = make_queries(0, n_sample)
+        val, ms, evals = cpu_leg(frenet, dyn, n_sample, cores, max(1, min(args.steps, 5)), 1)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{n_sample} of the {args.queries} queries per step "
+                                           f"({evals:.3g} dense evals), NumPy oracle over a {cores}-process pool; "
+                                           f"timed steps capped at 5"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- B200 arm -----------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from integrated_path_planning_b200 import BatchFrenetPlanner, DeviceBatch, _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sweep has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    Q = args.queries
+    spline, frenet, dyn = make_queries(rank * Q, Q)
+    planner = BatchFrenetPlanner(spline, device=local_rank, **scenarios.S1_KNOBS)
+    eng = planner.engine
+
+    # resident leg: inputs in HBM, torch tensors as buffers
+    batch = DeviceBatch(planner, frenet, TARGET_SPEED, dyn, _lib.FOT_DYN_SINGLE)
+    evals_step = batch.dense_evals()
+    stream = torch.cuda.Stream(device=local_rank)
+    small = None
+
+    def resident_step():
+        batch.launch(stream.cuda_stream)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                nonlocal small
+                small = [torch.empty_like(batch.out["best_cost"]) for _ in range(world)]
+                dist.all_gather(small, batch.out["best_cost"])
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        resident_step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(args.steps):
+        resident_step()
+    with torch.cuda.stream(stream):
+        e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    n_timed = min(args.steps, 256)
+    stage = np.array([eng.launch_stage_ms(b) for b in range(n_timed)])   # [prepass, sweep, winner]
+    sweep_ms = float(stage[:, 1].mean())
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = evals_step * world / (ms_step * 1e-3)
+
+    # e2e leg: host-pointer C-ABI call, pinned inputs, H2D + kernels + D2H inside the timed region
+    dyn_pinned = torch.from_numpy(dyn).pin_memory()
+    dyn_host = dyn_pinned.numpy()
+    for _ in range(args.warmup):
+        res = planner.plan_batch(frenet, TARGET_SPEED, dynamic_obstacles=dyn_host[:, 0])
+    e2e_steps = max(3, args.steps // 3)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = planner.plan_batch(frenet, TARGET_SPEED, dynamic_obstacles=dyn_host[:, 0])
+    if world > 1:
+        dist.barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = dyn.nbytes + frenet.nbytes + Q * (8 + 32 + 8 + 4) + Q * 6 * 8
+    d2h = res.best_idx.nbytes + res.best_cost.nbytes + res.stats.nbytes + res.winner_len.nbytes + res.winner.nbytes
+    # resident and e2e legs must pick the same winners
+    same = bool(np.array_equal(batch.out["best_idx"].cpu().numpy(), res.best_idx))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # FP64 pipe peak measured here (2 FLOP per FMA)
+    import ctypes as C
+    peak = C.c_double()
+    _lib.check(eng.lib.fot_probe_fma_tflops(local_rank, 0, C.byref(peak)), "probe")
+    achieved_tf = FLOP_PER_EVAL * evals_step / (sweep_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64_pipe", "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak.value, "traffic": None,
+                "kernel": "fot_sweep", "kernel_ms": sweep_ms,
+                "stage_ms": {"prepass": float(stage[:, 0].mean()), "sweep": sweep_ms, "winner": float(stage[:, 2].mean())},
+                "peak_source": "fot_probe_fma_tflops on this GPU (dependent-chain DFMA, 2 FLOP/FMA); "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "note": "algorithmic 5 FLOP per dense evaluation; point generation (about 58041 points per query) "
+                        "is extra work not credited here"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        n_sample = args.cpu_sample or 2 * cores
+        val, ms, ev = cpu_leg(frenet, dyn, n_sample, cores, 2, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_sample} of the {Q} queries ({ev:.3g} dense evals), NumPy oracle over a "
+                         f"{cores}-process pool, mean of 2 passes, {ms:.0f} ms per pass"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": evals_step * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "winners_match_resident": same},
+            "gpu_launches": 3 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "candidates_per_s": float(res.n_cand.sum()) * world / (ms_step * 1e-3),
+            "evals_per_step_per_gpu": evals_step}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -152,6 +152,11 @@ int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* batch, const fot_res
  * (CUDA events on the launching stream); negative if unavailable. */
 float fot_last_kernel_ms(const fot_handle_t* h);
 
+/* Device time of the three stages of the `back`-th most recent launch on this handle (0 = the
+ * last one; the handle keeps the last 256), in ms, from CUDA events on the launching stream:
+ * ms[0] obstacle prepass, ms[1] sweep kernel, ms[2] winner kernel.  Waits for that launch. */
+int fot_launch_stage_ms(const fot_handle_t* h, int back, float ms[3]);
+
 /* Pipe-throughput probes used to anchor the roofline denominator (MEASURED_PEAKS.json holds no
  * FP64/FP32 figure).  kind: 0 = FP64 FMA, 1 = FP32 FMA, 2 = packed FP32x2 FMA.
  * Writes achieved TFLOP/s (2 flops per FMA). */

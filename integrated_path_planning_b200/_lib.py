@@ -78,6 +78,7 @@ SYMBOLS = (
     ("fot_plan_batch_device", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult), C.c_void_p)),
     ("fot_plan_batch_host", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult))),
     ("fot_last_kernel_ms", C.c_float, (C.c_void_p,)),
+    ("fot_launch_stage_ms", C.c_int, (C.c_void_p, C.c_int, C.POINTER(C.c_float * 3))),
     ("fot_probe_fma_tflops", C.c_int, (C.c_int, C.c_int, c_double_p)),
 )
 

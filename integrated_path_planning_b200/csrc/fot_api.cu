@@ -62,8 +62,11 @@ struct fot_handle {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  static constexpr int kRing = 256;
+  std::vector<cudaEvent_t> ring;     // kRing x 4 events: start, after prepass, after sweep, after winner
+  long long n_launch = 0;
   int smem_optin = 0;
-  Buf obs_tm, part_cost, part_idx;   // device scratch
+  Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx;   // device scratch
   Buf stage_h, stage_d, out_h, out_d, dyn_d, stat_d;   // host-API staging
   fot_handle() { stage_h.host = true; out_h.host = true; }
 };
@@ -126,6 +129,8 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
+  h->ring.resize((size_t)fot_handle::kRing * 4);
+  for (auto& ev : h->ring) CK(cudaEventCreate(&ev));
   CK(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   h->smem_optin -= 2048;   // leave room for the kernels' static shared memory
   CK(cudaFuncSetAttribute(fot_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
@@ -137,10 +142,11 @@ extern "C" int fot_destroy(fot_handle_t* h) {
   if (!h) return FOT_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (Buf* b : {&h->obs_tm, &h->part_cost, &h->part_idx, &h->stage_h, &h->stage_d, &h->out_h, &h->out_d,
+  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->stage_h, &h->stage_d, &h->out_h, &h->out_d,
                  &h->dyn_d, &h->stat_d})
     b->release();
   if (h->tables_dev) cudaFree(h->tables_dev);
+  for (auto ev : h->ring) if (ev) cudaEventDestroy(ev);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -161,7 +167,8 @@ static int sweep_geometry(const fot_handle* h, int n_v_max, SweepGeom* g, size_t
   const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B;
   const size_t budget = std::min<size_t>((size_t)h->smem_optin, 200 * 1024);
   auto bytes = [&](int kv) {
-    return ((size_t)5 * NT + (size_t)kRefFields * kv * NT + 6 * (size_t)kv) * sizeof(double) + (size_t)kv * sizeof(int32_t) + 16;
+    return ((size_t)kTT * NT + (size_t)kRef * kv * NT + 6 * (size_t)kv) * sizeof(double) +
+           ((size_t)kv + NT) * sizeof(int32_t) + 16;
   };
   int ch = std::min(kSweepThreads, n_v_max * nd);
   ch = std::max(ch, 1);
@@ -214,32 +221,57 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   CK(h->part_cost.reserve(n_part * sizeof(double)));
   CK(h->part_idx.reserve(n_part * sizeof(int32_t)));
   const int SP = has_dyn ? b->S * b->P : 0;
-  if (has_dyn) CK(h->obs_tm.reserve((size_t)b->n_q * b->T_obs * SP * sizeof(double2)));
+  const int SPp = (SP + 3) & ~3, Mp = (b->n_static + 3) & ~3;
+  const int nq_s = b->static_per_query ? b->n_q : 1;
+  if (has_dyn) {
+    CK(h->obs_tm.reserve((size_t)b->n_q * b->T_obs * 3 * SPp * sizeof(double)));
+    CK(h->obs_max2.reserve((size_t)b->n_q * sizeof(double)));
+  }
+  if (b->n_static > 0) {
+    CK(h->stat_tm.reserve((size_t)nq_s * 3 * Mp * sizeof(double)));
+    CK(h->stat_max2.reserve((size_t)nq_s * sizeof(double)));
+  }
 
   Batch B{};
   B.n_q = b->n_q; B.n_v_max = b->n_v_max;
   B.frenet = b->frenet; B.target = b->target_speed; B.limits = b->limits; B.stop_dist = b->stop_dist;
   B.v_grid = b->v_grid; B.n_v = b->n_v;
-  B.static_obs = b->n_static > 0 ? (const double2*)b->static_obs : nullptr;
+  B.static_tm = b->n_static > 0 ? (const double*)h->stat_tm.p : nullptr;
+  B.static_max2 = b->n_static > 0 ? (const double*)h->stat_max2.p : nullptr;
   B.n_static = b->n_static; B.static_per_query = b->static_per_query;
-  B.obs_tm = has_dyn ? (const double2*)h->obs_tm.p : nullptr;
+  B.obs_tm = has_dyn ? (const double*)h->obs_tm.p : nullptr;
+  B.obs_max2 = has_dyn ? (const double*)h->obs_max2.p : nullptr;
   B.S = has_dyn ? b->S : 0; B.P = has_dyn ? b->P : 0; B.T_obs = has_dyn ? b->T_obs : 0; B.dyn_mode = b->dyn_mode;
   Out O{};
   O.best_idx = r->best_idx; O.best_cost = r->best_cost; O.stats = r->stats; O.winner_len = r->winner_len;
   O.winner = r->winner; O.cand_cat = r->cand_cat; O.cand_cost = r->cand_cost; O.cand_stride = r->cand_stride;
   O.part_cost = (double*)h->part_cost.p; O.part_idx = (int32_t*)h->part_idx.p;
 
+  cudaEvent_t* ring = h->ring.data() + (size_t)(h->n_launch % fot_handle::kRing) * 4;
   CK(cudaEventRecord(h->ev0, st));
   CK(cudaMemsetAsync(r->stats, 0, (size_t)b->n_q * FOT_N_STATS * sizeof(int32_t), st));
   if (r->cand_cat) CK(cudaMemsetAsync(r->cand_cat, FOT_CAT_DROP + 1, (size_t)b->n_q * r->cand_stride, st));
+  CK(cudaEventRecord(ring[0], st));
   if (has_dyn) {
+    CK(cudaMemsetAsync(h->obs_max2.p, 0, (size_t)b->n_q * sizeof(double), st));
     const long long warps = (long long)b->n_q * SP;
     const int blocks = (int)((warps * 32 + 255) / 256);
-    fot_obstacle_prepass<<<blocks, 256, 0, st>>>((const double2*)b->dyn, (double2*)h->obs_tm.p, b->n_q, SP, b->T_obs);
+    fot_obstacle_prepass<<<blocks, 256, 0, st>>>((const double2*)b->dyn, (double*)h->obs_tm.p,
+                                                 (double*)h->obs_max2.p, b->n_q, SP, b->T_obs);
   }
+  if (b->n_static > 0) {
+    CK(cudaMemsetAsync(h->stat_max2.p, 0, (size_t)nq_s * sizeof(double), st));
+    const int total = nq_s * b->n_static;
+    fot_static_prepass<<<(total + 255) / 256, 256, 0, st>>>((const double2*)b->static_obs, (double*)h->stat_tm.p,
+                                                            (double*)h->stat_max2.p, nq_s, b->n_static);
+  }
+  CK(cudaEventRecord(ring[1], st));
   fot_sweep<<<(unsigned)n_part, kSweepThreads, smem, st>>>(h->plan, B, O, g);
-  fot_winner<<<b->n_q, 128, (size_t)5 * h->plan.n_t_max * sizeof(double), st>>>(h->plan, B, O, g);
+  CK(cudaEventRecord(ring[2], st));
+  fot_winner<<<b->n_q, 128, (size_t)kTT * h->plan.n_t_max * sizeof(double), st>>>(h->plan, B, O, g);
+  CK(cudaEventRecord(ring[3], st));
   CK(cudaEventRecord(h->ev1, st));
+  h->n_launch++;
   CK(cudaGetLastError());
   h->timed = true;
   return FOT_OK;
@@ -331,6 +363,15 @@ extern "C" float fot_last_kernel_ms(const fot_handle_t* h) {
   if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
   return ms;
+}
+
+extern "C" int fot_launch_stage_ms(const fot_handle_t* h, int back, float ms[3]) {
+  if (!h || !ms || back < 0 || back >= fot_handle::kRing || back >= h->n_launch)
+    return fail(FOT_ERR_ARG, "fot_launch_stage_ms: no such launch");
+  const cudaEvent_t* ring = h->ring.data() + (size_t)((h->n_launch - 1 - back) % fot_handle::kRing) * 4;
+  CK(cudaEventSynchronize(ring[3]));
+  for (int i = 0; i < 3; ++i) CK(cudaEventElapsedTime(&ms[i], ring[i], ring[i + 1]));
+  return FOT_OK;
 }
 
 extern "C" int fot_probe_fma_tflops(int device, int kind, double* tflops_out) {

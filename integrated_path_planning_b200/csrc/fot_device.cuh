@@ -27,9 +27,11 @@ struct Batch {
   int32_t n_q, n_v_max;
   const double *frenet, *target, *limits, *stop_dist, *v_grid;
   const int32_t* n_v;
-  const double2* static_obs;
+  const double* static_tm;    // static obstacles as planes [n_q or 1][3][pad4(M)] of (-2x, -2y, x^2+y^2)
+  const double* static_max2;  // [n_q or 1] max x^2+y^2 (rounding band of the expanded distance form)
   int32_t n_static, static_per_query;
-  const double2* obs_tm;   // time-major copy of the dynamic obstacles [n_q][T_obs][S*P]
+  const double* obs_tm;       // dynamic obstacles, time-major planes [n_q][T_obs][3][pad4(S*P)]
+  const double* obs_max2;     // [n_q]
   int32_t S, P, T_obs, dyn_mode;
 };
 
@@ -86,22 +88,31 @@ __device__ __forceinline__ Lon lon_solve(const double* __restrict__ fs, double t
   L.hold = hold;
   return L;
 }
-// tt = shared table [5][NT] of t, t^2, t^3, t^4, t^5 built as fp.py:594-598.
-__device__ __forceinline__ double lon_p0(const Lon& L, const double* tt, int NT, int n) {
-  const int m = n > L.hold ? L.hold : n;
-  return L.a0 + L.a1 * tt[m] + L.a2 * tt[NT + m] + L.a3 * tt[2 * NT + m] + L.a4 * tt[3 * NT + m];
+// tt = shared table [NT][kTT] of t, t^2, t^3, t^4, t^5 (one row per sample) built as fp.py:594-598.
+constexpr int kTT = 6;
+__device__ __forceinline__ void tt_fill(double* tt, int n, double dt) {
+  const double t = (double)n * dt;
+  const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
+  double* r = tt + kTT * n;
+  r[0] = t; r[1] = t2; r[2] = t3; r[3] = t4; r[4] = t5; r[5] = 0.0;
 }
-__device__ __forceinline__ double lon_p1(const Lon& L, const double* tt, int NT, int n) {
-  if (n > L.hold) return 0.0;
-  return L.a1 + 2.0 * L.a2 * tt[n] + 3.0 * L.a3 * tt[NT + n] + 4.0 * L.a4 * tt[2 * NT + n];
+__device__ __forceinline__ double lon_p0(const Lon& L, const double* tt, int n) {
+  const double* r = tt + kTT * (n > L.hold ? L.hold : n);
+  return L.a0 + L.a1 * r[0] + L.a2 * r[1] + L.a3 * r[2] + L.a4 * r[3];
 }
-__device__ __forceinline__ double lon_p2(const Lon& L, const double* tt, int NT, int n) {
+__device__ __forceinline__ double lon_p1(const Lon& L, const double* tt, int n) {
   if (n > L.hold) return 0.0;
-  return 2.0 * L.a2 + 6.0 * L.a3 * tt[n] + 12.0 * L.a4 * tt[NT + n];
+  const double* r = tt + kTT * n;
+  return L.a1 + 2.0 * L.a2 * r[0] + 3.0 * L.a3 * r[1] + 4.0 * L.a4 * r[2];
 }
-__device__ __forceinline__ double lon_p3(const Lon& L, const double* tt, int NT, int n) {
+__device__ __forceinline__ double lon_p2(const Lon& L, const double* tt, int n) {
   if (n > L.hold) return 0.0;
-  return 6.0 * L.a3 + 24.0 * L.a4 * tt[n];
+  const double* r = tt + kTT * n;
+  return 2.0 * L.a2 + 6.0 * L.a3 * r[0] + 12.0 * L.a4 * r[1];
+}
+__device__ __forceinline__ double lon_p3(const Lon& L, const double* tt, int n) {
+  if (n > L.hold) return 0.0;
+  return 6.0 * L.a3 + 24.0 * L.a4 * tt[kTT * n];
 }
 
 // Quintic lateral profile (fp.py:660-691).
@@ -122,51 +133,58 @@ __device__ __forceinline__ Lat lat_solve(const double* __restrict__ fs, double d
   L.hold = hold;
   return L;
 }
-__device__ __forceinline__ double lat_p0(const Lat& L, const double* tt, int NT, int n) {
-  const int m = n > L.hold ? L.hold : n;
-  return L.a0 + L.a1 * tt[m] + L.a2 * tt[NT + m] + L.a3 * tt[2 * NT + m] + L.a4 * tt[3 * NT + m] +
-         L.a5 * tt[4 * NT + m];
+__device__ __forceinline__ double lat_p0(const Lat& L, const double* tt, int n) {
+  const double* r = tt + kTT * (n > L.hold ? L.hold : n);
+  return L.a0 + L.a1 * r[0] + L.a2 * r[1] + L.a3 * r[2] + L.a4 * r[3] + L.a5 * r[4];
 }
-__device__ __forceinline__ double lat_p1(const Lat& L, const double* tt, int NT, int n) {
+__device__ __forceinline__ double lat_p1(const Lat& L, const double* tt, int n) {
   if (n > L.hold) return 0.0;
-  return L.a1 + 2.0 * L.a2 * tt[n] + 3.0 * L.a3 * tt[NT + n] + 4.0 * L.a4 * tt[2 * NT + n] +
-         5.0 * L.a5 * tt[3 * NT + n];
+  const double* r = tt + kTT * n;
+  return L.a1 + 2.0 * L.a2 * r[0] + 3.0 * L.a3 * r[1] + 4.0 * L.a4 * r[2] + 5.0 * L.a5 * r[3];
 }
-__device__ __forceinline__ double lat_p2(const Lat& L, const double* tt, int NT, int n) {
+__device__ __forceinline__ double lat_p2(const Lat& L, const double* tt, int n) {
   if (n > L.hold) return 0.0;
-  return 2.0 * L.a2 + 6.0 * L.a3 * tt[n] + 12.0 * L.a4 * tt[NT + n] + 20.0 * L.a5 * tt[2 * NT + n];
+  const double* r = tt + kTT * n;
+  return 2.0 * L.a2 + 6.0 * L.a3 * r[0] + 12.0 * L.a4 * r[1] + 20.0 * L.a5 * r[2];
 }
-__device__ __forceinline__ double lat_p3(const Lat& L, const double* tt, int NT, int n) {
+__device__ __forceinline__ double lat_p3(const Lat& L, const double* tt, int n) {
   if (n > L.hold) return 0.0;
-  return 6.0 * L.a3 + 24.0 * L.a4 * tt[n] + 60.0 * L.a5 * tt[NT + n];
+  const double* r = tt + kTT * n;
+  return 6.0 * L.a3 + 24.0 * L.a4 * r[0] + 60.0 * L.a5 * r[1];
 }
 
 // np.sum over a contiguous float64 vector: NumPy's pairwise summation (8 interleaved
 // accumulators per <=128-element block, halving above that).  The jerk costs fp.py:718,:722
 // go through it, so the cost -- and with it the arg-min -- only reproduces with this order.
 template <class F>
-__device__ double np_pairwise_sum(const F& f, int lo, int n) {
+__device__ __forceinline__ double np_block_sum(const F& f, int lo, int n) {   // n <= 128
   if (n < 8) {
     double r = 0.0;
     for (int i = 0; i < n; ++i) r += f(lo + i);
     return r;
   }
-  if (n <= 128) {
-    double r0 = f(lo), r1 = f(lo + 1), r2 = f(lo + 2), r3 = f(lo + 3);
-    double r4 = f(lo + 4), r5 = f(lo + 5), r6 = f(lo + 6), r7 = f(lo + 7);
-    int i = 8;
-    const int stop = n - (n % 8);
-    for (; i < stop; i += 8) {
-      r0 += f(lo + i);     r1 += f(lo + i + 1); r2 += f(lo + i + 2); r3 += f(lo + i + 3);
-      r4 += f(lo + i + 4); r5 += f(lo + i + 5); r6 += f(lo + i + 6); r7 += f(lo + i + 7);
-    }
-    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-    for (; i < n; ++i) res += f(lo + i);
-    return res;
+  double r0 = f(lo), r1 = f(lo + 1), r2 = f(lo + 2), r3 = f(lo + 3);
+  double r4 = f(lo + 4), r5 = f(lo + 5), r6 = f(lo + 6), r7 = f(lo + 7);
+  int i = 8;
+  const int stop = n - (n % 8);
+  for (; i < stop; i += 8) {
+    r0 += f(lo + i);     r1 += f(lo + i + 1); r2 += f(lo + i + 2); r3 += f(lo + i + 3);
+    r4 += f(lo + i + 4); r5 += f(lo + i + 5); r6 += f(lo + i + 6); r7 += f(lo + i + 7);
   }
+  double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+  for (; i < n; ++i) res += f(lo + i);
+  return res;
+}
+template <class F>
+__device__ __noinline__ double np_split_sum(const F& f, int lo, int n) {      // n > 128: halve, 8-aligned
+  if (n <= 128) return np_block_sum(f, lo, n);
   int n2 = n / 2;
   n2 -= n2 % 8;
-  return np_pairwise_sum(f, lo, n2) + np_pairwise_sum(f, lo + n2, n - n2);
+  return np_split_sum(f, lo, n2) + np_split_sum(f, lo + n2, n - n2);
+}
+template <class F>
+__device__ __forceinline__ double np_pairwise_sum(const F& f, int lo, int n) {
+  return n <= 128 ? np_block_sum(f, lo, n) : np_split_sum(f, lo, n);
 }
 
 // Reference-line sample at arc length s (cs.py:47-166, :215-288).  NaN outside the knot range.
@@ -240,6 +258,37 @@ __device__ __forceinline__ CartPt to_cartesian(double rx, double ry, double cth,
   c.a = sdd * q / cos_d + sd * sd / cos_d * (d_p * dth_p - m);
   return c;
 }
+// Same conversion for the sweep's validity chain, with the transcendentals removed:
+//   cos(atan2(d', q)) = q / hypot(q, d'),  v = |s_dot| * hypot(q, d'),  divisions by s_dot, q and
+//   cos(delta) replaced by multiplication with one reciprocal each.
+// Values differ from to_cartesian() by a few ulp (<= 1e-14 relative), far inside the 1e-9 parity
+// bound; the winner's returned sequences are regenerated with the reference-order to_cartesian().
+// inv_sd / inv_sd2 = 1/s_dot and its square, or 0 when |s_dot| <= EPS_S_DOT (fp.py:792-799).
+struct KinPt {
+  double kappa, v, a, d_p, q;
+};
+__device__ __forceinline__ KinPt kinematics_fast(double rk, double rdk, double sd, double sdd, double inv_sd,
+                                                 double inv_sd2, double d, double dd_t, double ddd_t) {
+  KinPt c;
+  c.d_p = dd_t * inv_sd;
+  const double d_pp = (ddd_t - c.d_p * sdd) * inv_sd2;
+  c.q = 1.0 - rk * d;
+  const double h2 = fma(c.q, c.q, c.d_p * c.d_p);
+  const double rh = rsqrt(h2);
+  const double h = h2 * rh;
+  const double rq = 1.0 / c.q;
+  const double cos_d = c.q * rh;
+  const double tan_d = c.d_p * rq;
+  const double m = fma(rdk, d, rk * c.d_p);
+  const double cq = cos_d * rq;
+  c.kappa = fma(fma(m, tan_d, d_pp) * cos_d, cq, rk) * cq;
+  c.v = fabs(sd) * h;
+  const double rc = h * rq;                       // 1 / cos(delta)
+  const double dth_p = fma(c.q * rc, c.kappa, -rk);
+  c.a = fma(sdd * c.q, rc, sd * sd * rc * fma(c.d_p, dth_p, -m));
+  return c;
+}
+
 // normalize_angle (cc.py:173-182): np.angle(np.exp(1j*a)) = atan2(sin a, cos a).
 __device__ __forceinline__ double wrap_angle(double a) {
   double s, c;

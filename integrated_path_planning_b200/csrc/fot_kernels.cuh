@@ -1,22 +1,23 @@
 // fot_kernels.cuh -- the kernels of the Frenet candidate sweep (sm_100a, fp64).
 //
-//   fot_obstacle_prepass : [q][S][P][T][2] reference layout -> time-major [q][T][S*P] (+ NaN-pedestrian rule)
-//   fot_sweep            : ONE fused kernel for the whole candidate sweep of every query:
-//                          coefficient solve -> time-grid evaluation -> spline Frenet->global ->
-//                          validity chain -> same-time collision test -> cost -> block arg-min.
-//                          No trajectory is written to HBM.
-//   fot_winner           : per query, reduce the block partials and regenerate the 15 sequences
-//                          of the winning candidate only.
+//   fot_obstacle_prepass / fot_static_prepass :
+//        reference layout [q][S][P][T][2] -> time-major planes [q][T][3][SPp] of (-2x, -2y, x^2+y^2)
+//        (+ the NaN-pedestrian rule, + max |o|^2 per query for the rounding band)
+//   fot_sweep  : ONE fused kernel for the whole candidate sweep of every query:
+//        coefficient solve -> time-grid evaluation -> spline Frenet->global -> validity chain ->
+//        same-time collision test -> cost -> block arg-min.  No trajectory is written to HBM.
+//   fot_winner : per query, reduce the block partials and regenerate the 15 sequences of the
+//        winning candidate only, in the reference's arithmetic order.
 #pragma once
 #include "fot_device.cuh"
 
 namespace fot {
 
 constexpr int kSweepThreads = 128;
-constexpr int kRefFields = 10;  // rx ry cos sin rth rk rdk s sd sdd
+constexpr int kRef = 12;   // doubles per reference-line sample: rx ry cos sin | rk rdk s sd | sdd 1/sd 1/sd^2 rth
 
 // flag bits of the priority chain fp.py:964-991
-enum : unsigned { F_SPEED = 1u, F_ACCEL = 2u, F_CURV = 4u, F_LAT = 8u, F_ROAD = 16u, F_COLL = 32u };
+enum : unsigned { F_SPEED = 1u, F_ACCEL = 2u, F_CURV = 4u, F_LAT = 8u, F_ROAD = 16u };
 
 struct SweepGeom {
   int32_t blocks_per_query;  // n_T * chunks_per_T + brake_blocks
@@ -26,6 +27,12 @@ struct SweepGeom {
   int32_t brake_blocks;
 };
 
+__device__ __forceinline__ int pad4(int n) { return (n + 3) & ~3; }
+
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {   // v >= 0, finite
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
 // ----------------------------------------------------------------------------------------
 // Obstacle prepass.  One warp per predicted pedestrian trajectory (q, sample, ped).
 // The reference drops a pedestrian from a candidate's test when its trajectory AABB misses the
@@ -33,13 +40,15 @@ struct SweepGeom {
 // within r of a path point lies inside both padded boxes), but a NaN anywhere in a trajectory
 // makes np.min/np.max NaN and so removes that pedestrian entirely; the prepass reproduces
 // exactly that by writing NaN for every step of such a trajectory.
+// Output per (q, k): three planes of SPp = pad4(S*P) doubles: -2x, -2y, x^2+y^2 (pad: 0, 0, NaN).
 // ----------------------------------------------------------------------------------------
-__global__ void fot_obstacle_prepass(const double2* __restrict__ dyn, double2* __restrict__ tm,
-                                     int n_q, int SP, int T_obs) {
+__global__ void fot_obstacle_prepass(const double2* __restrict__ dyn, double* __restrict__ tm,
+                                     double* __restrict__ max2, int n_q, int SP, int T_obs) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_q * SP) return;
   const int q = warp / SP, j = warp % SP;
+  const int SPp = pad4(SP);
   const double2* src = dyn + (size_t)warp * T_obs;
   bool bad = false;
   for (int k = lane; k < T_obs; k += 32) {
@@ -47,186 +56,226 @@ __global__ void fot_obstacle_prepass(const double2* __restrict__ dyn, double2* _
     bad |= (o.x != o.x) || (o.y != o.y);
   }
   bad = __any_sync(0xffffffffu, bad);
-  double2* dst = tm + (size_t)q * T_obs * SP + j;
+  double* dst = tm + (size_t)q * T_obs * 3 * SPp + j;
+  double m2 = 0.0;
   for (int k = lane; k < T_obs; k += 32) {
-    double2 o = src[k];
-    if (bad) o.x = o.y = qnan();
-    dst[(size_t)k * SP] = o;
+    const double2 o = src[k];
+    double a = -2.0 * o.x, b = -2.0 * o.y, c = o.x * o.x + o.y * o.y;
+    if (bad) a = b = c = qnan();
+    else if (isfinite(c)) m2 = fmax(m2, c);
+    double* row = dst + (size_t)k * 3 * SPp;
+    row[0] = a; row[SPp] = b; row[2 * SPp] = c;
+    if (j == SP - 1)
+      for (int e = SP; e < SPp; ++e) { row[e - j] = 0.0; row[SPp + e - j] = 0.0; row[2 * SPp + e - j] = qnan(); }
   }
+  for (int off = 16; off > 0; off >>= 1) m2 = fmax(m2, __shfl_down_sync(0xffffffffu, m2, off));
+  if (lane == 0 && m2 > 0.0) atomic_max_pos(max2 + q, m2);
+}
+
+// Static obstacles [nq_s][M][2] -> [nq_s][3][Mp].
+__global__ void fot_static_prepass(const double2* __restrict__ st, double* __restrict__ out,
+                                   double* __restrict__ max2, int nq_s, int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq_s * M) return;
+  const int q = i / M, j = i % M, Mp = pad4(M);
+  const double2 o = st[i];
+  const double c = o.x * o.x + o.y * o.y;
+  double* row = out + (size_t)q * 3 * Mp + j;
+  row[0] = -2.0 * o.x; row[Mp] = -2.0 * o.y; row[2 * Mp] = c;
+  if (j == M - 1)
+    for (int e = M; e < Mp; ++e) { row[e - j] = 0.0; row[Mp + e - j] = 0.0; row[2 * Mp + e - j] = qnan(); }
+  if (isfinite(c) && c > 0.0) atomic_max_pos(max2 + q, c);
 }
 
 // ----------------------------------------------------------------------------------------
-// Point-vs-obstacle test of one trajectory sample against `cnt` obstacle positions.
-// d2 is formed with one FMA; anything within 2^-50 relative of the threshold is re-tested with
-// the reference's un-fused (dx*dx + dy*dy) so the hit decision is identical to NumPy's
-// (fp.py:1196-1198, :1231-1233).
+// Point-vs-obstacle test of one trajectory sample against `cnt` obstacles stored as planes
+// A = -2x, B = -2y, C = x^2+y^2 (plane stride `ps`, padded to a multiple of 4).
+//   |p - o|^2 = |p|^2 + (px*A + py*B + C): two FMAs and one compare per obstacle.
+// The expanded form rounds differently from the reference's (dx*dx + dy*dy), so the compare uses
+// a threshold widened by a rigorous rounding band; any sample inside the band ("maybe") is re-tested
+// with the reference's exact un-fused expression (fp.py:1196-1198, :1231-1233).  The hit decision
+// is therefore identical to NumPy's; the band is ~1e-11 relative, so re-tests are vanishingly rare.
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ bool hits_any(const double2* __restrict__ ob, int cnt, double px, double py,
-                                         double r2) {
-  const double r2_hi = r2 * (1.0 + 8.8817841970012523e-16);
+__device__ __forceinline__ bool hits_any(const double* __restrict__ A, int cnt, int ps, double px, double py,
+                                         double r2, double omax2) {
+  const double pp = fma(px, px, py * py);
+  const double band = 3.5527136788005009e-15 * (pp + omax2) + 8.8817841970012523e-16 * r2;   // 2^-48, 2^-50
+  const double thr = r2 - pp + band;
+  const double* __restrict__ B = A + ps;
+  const double* __restrict__ C = B + ps;
   bool maybe = false;
-  int j = 0;
-  for (; j + 4 <= cnt; j += 4) {
-    const double2 o0 = __ldg(ob + j), o1 = __ldg(ob + j + 1), o2 = __ldg(ob + j + 2), o3 = __ldg(ob + j + 3);
-    const double dx0 = px - o0.x, dy0 = py - o0.y;
-    const double dx1 = px - o1.x, dy1 = py - o1.y;
-    const double dx2 = px - o2.x, dy2 = py - o2.y;
-    const double dx3 = px - o3.x, dy3 = py - o3.y;
-    const double e0 = fma(dx0, dx0, dy0 * dy0);
-    const double e1 = fma(dx1, dx1, dy1 * dy1);
-    const double e2 = fma(dx2, dx2, dy2 * dy2);
-    const double e3 = fma(dx3, dx3, dy3 * dy3);
-    maybe |= (e0 <= r2_hi) | (e1 <= r2_hi) | (e2 <= r2_hi) | (e3 <= r2_hi);
-  }
-  for (; j < cnt; ++j) {
-    const double2 o = __ldg(ob + j);
-    const double dx = px - o.x, dy = py - o.y;
-    maybe |= (fma(dx, dx, dy * dy) <= r2_hi);
+  const int cntp = pad4(cnt);
+#pragma unroll 2
+  for (int j = 0; j < cntp; j += 4) {
+    const double2 a01 = __ldg(reinterpret_cast<const double2*>(A + j));
+    const double2 a23 = __ldg(reinterpret_cast<const double2*>(A + j + 2));
+    const double2 b01 = __ldg(reinterpret_cast<const double2*>(B + j));
+    const double2 b23 = __ldg(reinterpret_cast<const double2*>(B + j + 2));
+    const double2 c01 = __ldg(reinterpret_cast<const double2*>(C + j));
+    const double2 c23 = __ldg(reinterpret_cast<const double2*>(C + j + 2));
+    const double t0 = fma(px, a01.x, fma(py, b01.x, c01.x));
+    const double t1 = fma(px, a01.y, fma(py, b01.y, c01.y));
+    const double t2 = fma(px, a23.x, fma(py, b23.x, c23.x));
+    const double t3 = fma(px, a23.y, fma(py, b23.y, c23.y));
+    if (t0 <= thr) maybe = true;
+    if (t1 <= thr) maybe = true;
+    if (t2 <= thr) maybe = true;
+    if (t3 <= thr) maybe = true;
   }
   if (!maybe) return false;
-  for (j = 0; j < cnt; ++j) {           // rare: exact re-test
-    const double2 o = __ldg(ob + j);
-    const double dx = px - o.x, dy = py - o.y;
+  for (int j = 0; j < cnt; ++j) {           // rare: exact re-test in the reference's arithmetic
+    const double dx = px - (-0.5 * A[j]), dy = py - (-0.5 * B[j]);
     if (dx * dx + dy * dy <= r2) return true;
   }
   return false;
 }
 
-// Everything the per-candidate pass needs that is uniform over a block.
+// Everything the per-candidate passes need that is uniform over a block.
 struct BlockCtx {
-  const double* tt;    // [5][NT]
-  const double* ref;   // [kRefFields][kv_cap*NT]
-  int NT, N, ref_stride;
+  const double* tt;     // [NT][kTT]
+  const double* ref;    // [kv_cap*NT][kRef]
+  const int* kobs;      // [NT] obstacle time index of sample n (fp.py:1226-1227)
+  int NT, N;
 };
 
-// Result of one candidate.
-struct CandResult {
-  int category;
-  double cost;
+struct KinResult {
+  int category;   // FOT_CAT_* decided by the kinematic chain, or -1: clean, collision test needed
+  int keep;       // samples kept after the NaN-prefix truncation (fp.py:866)
+  double v_last, s_last, s_first;
 };
 
-// The fused per-candidate pass: samples n = 0..N-1 in time order.
-__device__ __forceinline__ int candidate_pass(const Plan& P, const Batch& B, const BlockCtx& C, int q,
-                                              const Lat& lat, int kl, const double* __restrict__ lim,
-                                              double stop_dist) {
-  const int NT = C.NT, N = C.N;
+// Pass K: validity chain of one candidate, samples in time order (fp.py:826-833, :851-875, :933-984).
+__device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCtx& C, const Lat& lat, int kl,
+                                                    const double* __restrict__ lim) {
+  const int N = C.N;
   const double* tt = C.tt;
-  const double* ref = C.ref + (size_t)kl * NT;
-  const int RS = C.ref_stride;
+  const double* ref = C.ref + (size_t)kl * C.NT * kRef;
   const double vmax = lim[0], amax = lim[1], kmax = lim[2], latmax = lim[3];
-  const double dt = P.cfg.dt;
   const double road_thr = P.cfg.max_road_width + 1e-9;                       // fp.py:982
-  const double tele_thr = fmax(vmax, P.cfg.max_speed) * dt * 3.0;            // fp.py:955
-  const int n_circ = P.cfg.n_circles;
-  const int SP = B.S * B.P;
-  const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
-  const double r2_stat = P.cfg.collide_r2;
-  const double r2_dyn = dist_mode ? P.cfg.collide_r2 : P.cfg.collide_r2_single;   // fp.py:1099-1104
-  const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
-  const double2* stat = B.static_obs ? B.static_obs + (B.static_per_query ? (size_t)q * B.n_static : 0) : nullptr;
-  const double2* obs_q = B.obs_tm ? B.obs_tm + (size_t)q * B.T_obs * SP : nullptr;
+  const double tele_thr = fmax(vmax, P.cfg.max_speed) * P.cfg.dt * 3.0;      // fp.py:955
+  const double tele_thr2 = tele_thr * tele_thr;
 
   int first_nan = -1;
-  bool singular = false, nonfinite = false, step_nan = false, coll = false;
-  double max_step = 0.0;
+  bool singular = false, nonfinite = false;
+  double max_step2 = 0.0;
   unsigned flags = 0;
-  unsigned long long viol = 0ull;
-  double x_prev = 0, y_prev = 0, s_prev = 0, d_prev = 0, ang_prev = 0;
-  double v_last = 0, s_last = 0, s_first = 0;
+  double x_prev = 0, y_prev = 0, s_prev = 0, d_prev = 0, dp_prev = 0, q_prev = 1, rth_prev = 0;
+  KinResult R;
+  R.v_last = 0; R.s_last = 0; R.s_first = 0;
 
   for (int n = 0; n < N; ++n) {
-    const double rk = ref[5 * RS + n];
-    const double d = lat_p0(lat, tt, NT, n);
+    const double* r = ref + n * kRef;
+    const double rk = r[4];
+    const double d = lat_p0(lat, tt, n);
     const double q1 = 1.0 - rk * d;                                          // fp.py:826-827
     if (isfinite(q1) && q1 <= 0.05) singular = true;
     if (first_nan >= 0) continue;
-    const double rx = ref[n], sth = ref[3 * RS + n];
-    const double x0 = rx - sth * d;
-    if (x0 != x0) { first_nan = n; continue; }                              // fp.py:851-866
-    const double s = ref[7 * RS + n], sd = ref[8 * RS + n], sdd = ref[9 * RS + n];
-    const CartPt c = to_cartesian(rx, ref[RS + n], ref[2 * RS + n], sth, ref[4 * RS + n], rk,
-                                  ref[6 * RS + n], sd, sdd, d, lat_p1(lat, tt, NT, n), lat_p2(lat, tt, NT, n));
+    const double x = r[0] - r[3] * d;                                        // cc.py:131
+    if (x != x) { first_nan = n; continue; }                                // fp.py:851-866
+    const double y = r[1] + r[2] * d;                                        // cc.py:132
+    const double s = r[6], sd = r[7], sdd = r[8];
+    const KinPt c = kinematics_fast(rk, r[5], sd, sdd, r[9], r[10], d, lat_p1(lat, tt, n), lat_p2(lat, tt, n));
     if (!(isfinite(c.v) && isfinite(c.a) && isfinite(c.kappa))) nonfinite = true;   // fp.py:944-946
-    if (n == 0) s_first = s;
+    if (n == 0) R.s_first = s;
     if (n >= 1) {
-      const double step = hypot(c.x - x_prev, c.y - y_prev);                 // fp.py:954
-      if (step != step) step_nan = true; else max_step = fmax(max_step, step);
+      const double ex = x - x_prev, ey = y - y_prev;
+      const double step2 = fma(ex, ex, ey * ey);                             // fp.py:954 (squared)
+      max_step2 = fmax(max_step2, step2);
       if (c.v > vmax) flags |= F_SPEED;                                      // fp.py:964
       if (fabs(c.a) > amax) flags |= F_ACCEL;                                // fp.py:966
-      if (!(flags & F_CURV)) {                                               // fp.py:995-1033
-        if (c.v > 0.5) {
-          if (fabs(c.kappa) > kmax) flags |= F_CURV;
+      if (c.v > 0.5) {                                                       // fp.py:1019-1021
+        if (fabs(c.kappa) > kmax) flags |= F_CURV;
+      } else if (!(flags & F_CURV)) {                                        // fp.py:1022-1032
+        const double dd = fabs(d - d_prev);
+        const double ds_f = fabs(s - s_prev);
+        if (dd > fmax(1.5 * ds_f, 0.02)) {
+          flags |= F_CURV;
         } else {
-          const double dd = fabs(d - d_prev);
-          const double ds_f = fabs(s - s_prev);
-          if (dd > fmax(1.5 * ds_f, 0.02)) {
-            flags |= F_CURV;
-          } else {
-            const double dy_ = wrap_angle(c.ang) - wrap_angle(ang_prev);
-            double sn, cs;
-            sincos(dy_, &sn, &cs);
-            const double dyaw = fabs(atan2(sn, cs));
-            if (dyaw > fmax(kmax * step, 0.1)) flags |= F_CURV;
-          }
+          const double yaw1 = wrap_angle(atan2(c.d_p, c.q) + r[11]);
+          const double yaw0 = wrap_angle(atan2(dp_prev, q_prev) + rth_prev);
+          double sn, cs;
+          sincos(yaw1 - yaw0, &sn, &cs);
+          const double dyaw = fabs(atan2(sn, cs));
+          if (dyaw > fmax(kmax * hypot(ex, ey), 0.1)) flags |= F_CURV;
         }
       }
       if (c.v * c.v * fabs(c.kappa) > latmax) flags |= F_LAT;               // fp.py:975
       if (fabs(d) > road_thr) flags |= F_ROAD;                               // fp.py:982
     }
-    // ---- collision at this sample's own time index (fp.py:1126-1233) --------------------
-    if (!coll) {
-      double hx = 0.0, hy = 0.0;
-      if (n_circ > 0) {                                                      // fp.py:1158-1167
-        const double yaw = wrap_angle(c.ang);
-        sincos(yaw, &hy, &hx);
+    x_prev = x; y_prev = y; s_prev = s; d_prev = d; dp_prev = c.d_p; q_prev = c.q; rth_prev = r[11];
+    R.v_last = c.v; R.s_last = s;
+  }
+
+  R.keep = first_nan < 0 ? N : (first_nan >= 2 ? first_nan : 0);            // fp.py:866
+  if (singular || R.keep == 0 || nonfinite) R.category = FOT_CAT_DROP;       // fp.py:831-833, :933, :944
+  else if (R.keep >= 2 && max_step2 > tele_thr2) R.category = FOT_CAT_DROP;  // fp.py:953-956
+  else if (flags & F_SPEED) R.category = FOT_CAT_SPEED;
+  else if (flags & F_ACCEL) R.category = FOT_CAT_ACCEL;
+  else if (flags & F_CURV) R.category = FOT_CAT_CURV;
+  else if (flags & F_LAT) R.category = FOT_CAT_LAT;
+  else if (flags & F_ROAD) R.category = FOT_CAT_ROAD;
+  else R.category = -1;
+  return R;
+}
+
+// Pass C: time-aligned collision test of a kinematically clean candidate (fp.py:1035-1233);
+// leaves at the first decisive hit, like the reference's np.any / early return.
+__device__ __forceinline__ bool collision_pass(const Plan& P, const Batch& B, const BlockCtx& C, int q,
+                                               const Lat& lat, int kl, int keep) {
+  const double* tt = C.tt;
+  const double* ref = C.ref + (size_t)kl * C.NT * kRef;
+  const int n_circ = P.cfg.n_circles;
+  const int SP = B.S * B.P, SPp = pad4(SP), Mp = pad4(B.n_static);
+  const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
+  const double r2_stat = P.cfg.collide_r2;
+  const double r2_dyn = dist_mode ? P.cfg.collide_r2 : P.cfg.collide_r2_single;   // fp.py:1099-1104
+  const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
+  const int qs = B.static_per_query ? q : 0;
+  const double* stat = B.static_tm ? B.static_tm + (size_t)qs * 3 * Mp : nullptr;
+  const double smax2 = B.static_tm ? B.static_max2[qs] : 0.0;
+  const double* obs_q = B.obs_tm ? B.obs_tm + (size_t)q * B.T_obs * 3 * SPp : nullptr;
+  const double omax2 = B.obs_tm ? B.obs_max2[q] : 0.0;
+  unsigned long long viol = 0ull;
+
+  for (int n = 0; n < keep; ++n) {
+    const double* r = ref + n * kRef;
+    const double d = lat_p0(lat, tt, n);
+    const double x = r[0] - r[3] * d;
+    const double y = r[1] + r[2] * d;
+    double hx = 0.0, hy = 0.0;
+    if (n_circ > 0) {                                                        // fp.py:1158-1167
+      const double d_p = lat_p1(lat, tt, n) * r[9];
+      const double yaw = wrap_angle(atan2(d_p, 1.0 - r[4] * d) + r[11]);
+      sincos(yaw, &hy, &hx);
+    }
+    const int n_pts = n_circ > 0 ? n_circ : 1;
+    const double* ob = obs_q ? obs_q + (size_t)C.kobs[n] * 3 * SPp : nullptr;
+    for (int ci = 0; ci < n_pts; ++ci) {
+      double px = x, py = y;
+      if (n_circ > 0) {
+        px = x + P.cfg.circle_offsets[ci] * hx;
+        py = y + P.cfg.circle_offsets[ci] * hy;
       }
-      const int n_pts = n_circ > 0 ? n_circ : 1;
-      int k_obs = 0;
-      if (obs_q) {
-        const double kf = rint(tt[n] / dt);                                  // fp.py:1226-1227
-        k_obs = kf < 0.0 ? 0 : (kf > (double)(B.T_obs - 1) ? B.T_obs - 1 : (int)kf);
-      }
-      for (int ci = 0; ci < n_pts && !coll; ++ci) {
-        double px = c.x, py = c.y;
-        if (n_circ > 0) {
-          px = c.x + P.cfg.circle_offsets[ci] * hx;
-          py = c.y + P.cfg.circle_offsets[ci] * hy;
-        }
-        if (stat && hits_any(stat, B.n_static, px, py, r2_stat)) { coll = true; break; }
-        if (obs_q) {
-          const double2* ob = obs_q + (size_t)k_obs * SP;
-          if (max_viol == 0) {
-            if (hits_any(ob, SP, px, py, r2_dyn)) coll = true;
-          } else {
-            for (int sidx = 0; sidx < B.S; ++sidx) {
-              if ((viol >> sidx) & 1ull) continue;
-              if (hits_any(ob + (size_t)sidx * B.P, B.P, px, py, r2_dyn)) viol |= (1ull << sidx);
+      if (stat && hits_any(stat, B.n_static, Mp, px, py, r2_stat, smax2)) return true;
+      if (ob) {
+        if (max_viol == 0) {
+          if (hits_any(ob, SP, SPp, px, py, r2_dyn, omax2)) return true;
+        } else {
+          for (int sidx = 0; sidx < B.S; ++sidx) {
+            if ((viol >> sidx) & 1ull) continue;
+            bool hit = false;
+            for (int p = sidx * B.P; p < (sidx + 1) * B.P && !hit; ++p) {
+              const double dx = px - (-0.5 * ob[p]), dy = py - (-0.5 * ob[SPp + p]);
+              hit = dx * dx + dy * dy <= r2_dyn;
             }
-            if (__popcll(viol) > max_viol) coll = true;                      // fp.py:1121-1123
+            if (hit) viol |= (1ull << sidx);
           }
+          if (__popcll(viol) > max_viol) return true;                        // fp.py:1121-1123
         }
       }
     }
-    x_prev = c.x; y_prev = c.y; s_prev = s; d_prev = d; ang_prev = c.ang;
-    v_last = c.v; s_last = s;
   }
-
-  const int keep = first_nan < 0 ? N : (first_nan >= 2 ? first_nan : 0);    // fp.py:866
-  if (singular || keep == 0 || nonfinite) return FOT_CAT_DROP;               // fp.py:831-833, :933, :944
-  if (keep >= 2 && !step_nan && max_step > tele_thr) return FOT_CAT_DROP;    // fp.py:953-956
-  if (coll) flags |= F_COLL;
-  if (flags & F_SPEED) return FOT_CAT_SPEED;
-  if (flags & F_ACCEL) return FOT_CAT_ACCEL;
-  if (flags & F_CURV) return FOT_CAT_CURV;
-  if (flags & F_LAT) return FOT_CAT_LAT;
-  if (flags & F_ROAD) return FOT_CAT_ROAD;
-  if (flags & F_COLL) return FOT_CAT_COLL;
-  if (stop_dist == stop_dist) {                                              // fp.py:307-324
-    const bool stops = fabs(v_last) <= 0.15;
-    const double travel = s_last - s_first;
-    if (!(stops && travel <= stop_dist + 1e-6)) return FOT_CAT_STOP;
-  }
-  return FOT_CAT_OK;
+  return false;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -234,18 +283,19 @@ __device__ __forceinline__ int candidate_pass(const Plan& P, const Batch& B, con
 // one horizon T_j, or up to `kv_cap` brake-ladder candidates.
 //   phase 0: time-power table; quartic solve + jerk sum per terminal speed; reference-line
 //            samples (s(t), spline, heading, curvature) per (speed, t_n) -> shared memory
-//   phase 1: one thread per candidate streams its samples (candidate_pass)
+//   phase 1: one thread per candidate: cost, kinematic pass, then collision pass if still clean
 //   phase 2: block arg-min by (cost, index) and category histogram
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSweepThreads)
 fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   extern __shared__ double sm[];
   const int NT = P.n_t_max;
-  double* tt = sm;                                   // [5][NT]
-  double* ref = tt + 5 * NT;                         // [kRefFields][kv_cap*NT]
-  double* js = ref + (size_t)kRefFields * G.kv_cap * NT;   // [kv_cap]
-  double* lonc = js + G.kv_cap;                      // [5][kv_cap]
+  double* tt = sm;                                         // [NT][kTT]
+  double* ref = tt + kTT * NT;                             // [kv_cap*NT][kRef]
+  double* js = ref + (size_t)kRef * G.kv_cap * NT;         // [kv_cap]
+  double* lonc = js + G.kv_cap;                            // [5][kv_cap]
   int* holdk = reinterpret_cast<int*>(lonc + 5 * G.kv_cap);   // [kv_cap]
+  int* kobs = holdk + G.kv_cap;                            // [NT]
   __shared__ int s_stats[FOT_N_STATS];
   __shared__ double s_cost[kSweepThreads / 32];
   __shared__ int s_idx[kSweepThreads / 32];
@@ -287,10 +337,11 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
 
   // ---- phase 0 ---------------------------------------------------------------------------
   if (tid < FOT_N_STATS) s_stats[tid] = 0;
-  for (int n = tid; n < NT; n += kSweepThreads) {      // fp.py:594-598
-    const double t = (double)n * P.cfg.dt;
-    const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
-    tt[n] = t; tt[NT + n] = t2; tt[2 * NT + n] = t3; tt[3 * NT + n] = t4; tt[4 * NT + n] = t5;
+  for (int n = tid; n < NT; n += kSweepThreads) {
+    tt_fill(tt, n, P.cfg.dt);
+    const double kf = rint(((double)n * P.cfg.dt) / P.cfg.dt);               // fp.py:1226-1227
+    const int kmax_i = B.T_obs > 0 ? B.T_obs - 1 : 0;
+    kobs[n] = kf < 0.0 ? 0 : (kf > (double)kmax_i ? kmax_i : (int)kf);
   }
   __syncthreads();
   if (tid < n_k) {
@@ -302,24 +353,26 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     lonc[tid] = L.a0; lonc[G.kv_cap + tid] = L.a1; lonc[2 * G.kv_cap + tid] = L.a2;
     lonc[3 * G.kv_cap + tid] = L.a3; lonc[4 * G.kv_cap + tid] = L.a4;
     holdk[tid] = L.hold;
-    auto jerk2 = [&](int n) { const double j = lon_p3(L, tt, NT, n); return j * j; };
+    auto jerk2 = [&](int n) { const double j = lon_p3(L, tt, n); return j * j; };
     js[tid] = np_pairwise_sum(jerk2, 0, N);             // fp.py:722
   }
   __syncthreads();
-  const int RS = G.kv_cap * NT;
   for (int idx = tid; idx < n_k * N; idx += kSweepThreads) {
     const int kl = idx / N, n = idx - kl * N;
     Lon L;
     L.a0 = lonc[kl]; L.a1 = lonc[G.kv_cap + kl]; L.a2 = lonc[2 * G.kv_cap + kl];
     L.a3 = lonc[3 * G.kv_cap + kl]; L.a4 = lonc[4 * G.kv_cap + kl]; L.hold = holdk[kl];
-    const double s = lon_p0(L, tt, NT, n);
-    const RefPt r = spline_ref(P, s);
+    const double s = lon_p0(L, tt, n);
+    const double sd = lon_p1(L, tt, n);
+    const RefPt rp = spline_ref(P, s);
     double sn, cs;
-    sincos(r.rth, &sn, &cs);                            // cc.py:128-129
-    const int o = kl * NT + n;
-    ref[o] = r.rx; ref[RS + o] = r.ry; ref[2 * RS + o] = cs; ref[3 * RS + o] = sn; ref[4 * RS + o] = r.rth;
-    ref[5 * RS + o] = r.rk; ref[6 * RS + o] = r.rdk; ref[7 * RS + o] = s;
-    ref[8 * RS + o] = lon_p1(L, tt, NT, n); ref[9 * RS + o] = lon_p2(L, tt, NT, n);
+    sincos(rp.rth, &sn, &cs);                           // cc.py:128-129
+    const bool moving = fabs(sd) > 1e-3;                // fp.py:792
+    const double inv_sd = moving ? 1.0 / sd : 0.0;
+    double* r = ref + ((size_t)kl * NT + n) * kRef;
+    r[0] = rp.rx; r[1] = rp.ry; r[2] = cs; r[3] = sn;
+    r[4] = rp.rk; r[5] = rp.rdk; r[6] = s; r[7] = sd;
+    r[8] = lon_p2(L, tt, n); r[9] = inv_sd; r[10] = inv_sd * inv_sd; r[11] = rp.rth;
   }
   __syncthreads();
 
@@ -341,20 +394,33 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
       lat = lat_solve(fs, fs[3], P.Tb[k_lo + tid], P.inv5b + 9 * (k_lo + tid), true, P.n_steps_b[k_lo + tid]);
     }
     // cost on the un-truncated profile (fp.py:703-734)
-    auto jerk2 = [&](int n) { const double j = lat_p3(lat, tt, NT, n); return j * j; };
+    auto jerk2 = [&](int n) { const double j = lat_p3(lat, tt, n); return j * j; };
     const double Jp = np_pairwise_sum(jerk2, 0, N);
-    const double d_end = lat_p0(lat, tt, NT, N - 1);
+    const double d_end = lat_p0(lat, tt, N - 1);
     const double Jd = d_end * d_end;
     const double Js = js[kl];
-    const double dv = B.target[q] - ref[8 * RS + kl * NT + (N - 1)];
+    const double dv = B.target[q] - ref[((size_t)kl * NT + (N - 1)) * kRef + 7];
     const double Jv = dv * dv;
-    const double Jt = tt[N - 1];
+    const double Jt = tt[kTT * (N - 1)];
     const double lat_cost = P.cfg.k_j * Jp + P.cfg.k_t * Jt + P.cfg.k_d * Jd;
     const double lon_cost = P.cfg.k_j * Js + P.cfg.k_t * Jt + P.cfg.k_s_dot * Jv;
     const double cost = P.cfg.k_lat * lat_cost + P.cfg.k_lon * lon_cost;
 
-    BlockCtx C{tt, ref, NT, N, RS};
-    const int cat = candidate_pass(P, B, C, q, lat, kl, B.limits + 4 * (size_t)q, B.stop_dist[q]);
+    BlockCtx C{tt, ref, kobs, NT, N};
+    const KinResult K = kinematic_pass(P, C, lat, kl, B.limits + 4 * (size_t)q);
+    int cat = K.category;
+    if (cat < 0) {
+      if (collision_pass(P, B, C, q, lat, kl, K.keep)) {
+        cat = FOT_CAT_COLL;                                                  // fp.py:986-989
+      } else {
+        cat = FOT_CAT_OK;
+        const double stop_dist = B.stop_dist[q];
+        if (stop_dist == stop_dist) {                                        // fp.py:307-324
+          const bool stops = fabs(K.v_last) <= 0.15;
+          if (!(stops && (K.s_last - K.s_first) <= stop_dist + 1e-6)) cat = FOT_CAT_STOP;
+        }
+      }
+    }
     if (cat < FOT_N_STATS) atomicAdd(&s_stats[cat], 1);
     if (O.cand_cat) O.cand_cat[(size_t)q * O.cand_stride + cand_idx] = (uint8_t)cat;
     if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + cand_idx] = cost;
@@ -384,7 +450,7 @@ __global__ void __launch_bounds__(128)
 fot_winner(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   extern __shared__ double sm[];
   const int NT = P.n_t_max;
-  double* tt = sm;   // [5][NT]
+  double* tt = sm;   // [NT][kTT]
   __shared__ double s_cost[4];
   __shared__ int s_idx[4];
   __shared__ int s_first_nan;
@@ -403,11 +469,7 @@ fot_winner(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   }
   if ((tid & 31) == 0) { s_cost[tid >> 5] = c; s_idx[tid >> 5] = i; }
   if (tid == 0) s_first_nan = 0x7fffffff;
-  for (int n = tid; n < NT; n += blockDim.x) {
-    const double t = (double)n * P.cfg.dt;
-    const double t2 = t * t, t3 = t2 * t, t4 = t2 * t2, t5 = t4 * t;
-    tt[n] = t; tt[NT + n] = t2; tt[2 * NT + n] = t3; tt[3 * NT + n] = t4; tt[4 * NT + n] = t5;
-  }
+  for (int n = tid; n < NT; n += blockDim.x) tt_fill(tt, n, P.cfg.dt);
   __syncthreads();
   c = s_cost[0]; i = s_idx[0];
   for (int w = 1; w < (int)(blockDim.x >> 5); ++w) argmin_merge(c, i, s_cost[w], s_idx[w]);
@@ -434,16 +496,16 @@ fot_winner(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     lat = lat_solve(fs, fs[3], P.Tb[bi], P.inv5b + 9 * bi, true, P.n_steps_b[bi]);
   }
   for (int n = tid; n < N; n += blockDim.x) {
-    const double s = lon_p0(lon, tt, NT, n), sd = lon_p1(lon, tt, NT, n), sdd = lon_p2(lon, tt, NT, n);
-    const double d = lat_p0(lat, tt, NT, n), dd = lat_p1(lat, tt, NT, n), ddd = lat_p2(lat, tt, NT, n);
+    const double s = lon_p0(lon, tt, n), sd = lon_p1(lon, tt, n), sdd = lon_p2(lon, tt, n);
+    const double d = lat_p0(lat, tt, n), dd = lat_p1(lat, tt, n), ddd = lat_p2(lat, tt, n);
     const RefPt r = spline_ref(P, s);
     double sn, cs;
     sincos(r.rth, &sn, &cs);
     const CartPt cp = to_cartesian(r.rx, r.ry, cs, sn, r.rth, r.rk, r.rdk, sd, sdd, d, dd, ddd);
     if (cp.x != cp.x) atomicMin(&s_first_nan, n);
-    W[0 * NT + n] = tt[n];
-    W[1 * NT + n] = s;   W[2 * NT + n] = sd;  W[3 * NT + n] = sdd; W[4 * NT + n] = lon_p3(lon, tt, NT, n);
-    W[5 * NT + n] = d;   W[6 * NT + n] = dd;  W[7 * NT + n] = ddd; W[8 * NT + n] = lat_p3(lat, tt, NT, n);
+    W[0 * NT + n] = tt[kTT * n];
+    W[1 * NT + n] = s;   W[2 * NT + n] = sd;  W[3 * NT + n] = sdd; W[4 * NT + n] = lon_p3(lon, tt, n);
+    W[5 * NT + n] = d;   W[6 * NT + n] = dd;  W[7 * NT + n] = ddd; W[8 * NT + n] = lat_p3(lat, tt, n);
     W[9 * NT + n] = cp.x; W[10 * NT + n] = cp.y; W[11 * NT + n] = wrap_angle(cp.ang);
     W[12 * NT + n] = cp.kappa; W[13 * NT + n] = cp.v; W[14 * NT + n] = cp.a;
   }

@@ -241,5 +241,11 @@ class SweepEngine:
                                                   C.c_void_p(stream) if stream else None),
                    "fot_plan_batch_device")
 
+    def launch_stage_ms(self, back: int = 0):
+        """(prepass, sweep, winner) device ms of the `back`-th most recent launch."""
+        ms = (C.c_float * 3)()
+        _lib.check(self.lib.fot_launch_stage_ms(self._h, int(back), C.byref(ms)), "fot_launch_stage_ms")
+        return tuple(float(v) for v in ms)
+
     def last_kernel_ms(self) -> float:
         return float(self.lib.fot_last_kernel_ms(self._h))
