@@ -163,11 +163,24 @@ extern "C" int fot_candidate_count(const fot_handle_t* h, int n_v, int has_brake
 
 // Block geometry: how many (speed, lateral) candidates one block takes, bounded by the shared
 // memory its per-speed reference samples need.
-static int sweep_geometry(const fot_handle* h, int n_v_max, SweepGeom* g, size_t* smem_bytes) {
+static int sweep_geometry(const fot_handle* h, const fot_batch_t* b, SweepGeom* g, size_t* smem_bytes) {
+  const int n_v_max = b->n_v_max;
   const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B;
   const size_t budget = std::min<size_t>((size_t)h->smem_optin, 200 * 1024);
+  // obstacle ring: stage capacity in entries per plane.  Small fields: several whole time planes per
+  // stage (about 4 KB); large fields: 512-entry chunks (12 KB).
+  const int SPp = b->dyn_mode != FOT_DYN_NONE ? ((b->S * b->P + 3) & ~3) : 0;
+  const int Mp = (b->n_static + 3) & ~3;
+  int tile_cap = 0, n_stages = 0;
+  if (SPp > 0 || Mp > 0) {
+    if (SPp > 0 && SPp <= 512) tile_cap = std::max(1, 256 / SPp) * SPp;   // whole planes, about 6 KB per stage
+    else if (SPp > 512) tile_cap = 512;
+    else tile_cap = std::min(512, Mp);
+    n_stages = 3;
+  }
   auto bytes = [&](int kv) {
-    return ((size_t)kTT * NT + (size_t)kRef * kv * NT + 6 * (size_t)kv) * sizeof(double) +
+    return ((size_t)kTT * NT + (size_t)kRef * kv * NT + 6 * (size_t)kv + 2 * (size_t)std::max(nd, kv) +
+            (size_t)n_stages * 3 * tile_cap) * sizeof(double) +
            ((size_t)kv + NT) * sizeof(int32_t) + 16;
   };
   int ch = std::min(kSweepThreads, n_v_max * nd);
@@ -182,10 +195,14 @@ static int sweep_geometry(const fot_handle* h, int n_v_max, SweepGeom* g, size_t
   if (bytes(kv) > budget) return fail(FOT_ERR_TOO_LARGE, "time grid too long for shared memory");
   g->ch_eff = ch;
   g->kv_cap = std::max(kv, 1);
+  g->jp_cap = std::max(nd, g->kv_cap);
+  g->jp_cap += g->jp_cap & 1;                       // keeps the ring 16-byte aligned (see kernel layout)
+  g->tile_cap = tile_cap;
+  g->n_stages = n_stages;
   g->chunks_per_T = (n_v_max * nd + ch - 1) / ch;
   g->brake_blocks = nB > 0 ? (nB + g->kv_cap - 1) / g->kv_cap : 0;
   g->blocks_per_query = h->plan.cfg.n_T * g->chunks_per_T + g->brake_blocks;
-  *smem_bytes = bytes(g->kv_cap);
+  *smem_bytes = bytes(g->kv_cap) + 64;
   return FOT_OK;
 }
 
@@ -213,7 +230,7 @@ static int check_batch(const fot_handle* h, const fot_batch_t* b, const fot_resu
 static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r, cudaStream_t st) {
   SweepGeom g;
   size_t smem = 0;
-  int rc = sweep_geometry(h, b->n_v_max, &g, &smem);
+  int rc = sweep_geometry(h, b, &g, &smem);
   if (rc != FOT_OK) return rc;
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const size_t n_part = (size_t)b->n_q * g.blocks_per_query;

@@ -25,7 +25,11 @@ struct SweepGeom {
   int32_t ch_eff;            // candidates per grid block (<= kSweepThreads)
   int32_t kv_cap;            // terminal speeds (or brake horizons) whose reference samples fit one block
   int32_t brake_blocks;
+  int32_t jp_cap;            // max(n_d, kv_cap): per-block lateral-profile slots
+  int32_t tile_cap;          // obstacle entries (per plane) one ring stage holds; multiple of 4
+  int32_t n_stages;          // ring depth
 };
+constexpr int kMaxStages = 4;
 
 __device__ __forceinline__ int pad4(int n) { return (n + 3) & ~3; }
 
@@ -107,12 +111,12 @@ __device__ __forceinline__ bool hits_any(const double* __restrict__ A, int cnt, 
   const int cntp = pad4(cnt);
 #pragma unroll 2
   for (int j = 0; j < cntp; j += 4) {
-    const double2 a01 = __ldg(reinterpret_cast<const double2*>(A + j));
-    const double2 a23 = __ldg(reinterpret_cast<const double2*>(A + j + 2));
-    const double2 b01 = __ldg(reinterpret_cast<const double2*>(B + j));
-    const double2 b23 = __ldg(reinterpret_cast<const double2*>(B + j + 2));
-    const double2 c01 = __ldg(reinterpret_cast<const double2*>(C + j));
-    const double2 c23 = __ldg(reinterpret_cast<const double2*>(C + j + 2));
+    const double2 a01 = *reinterpret_cast<const double2*>(A + j);
+    const double2 a23 = *reinterpret_cast<const double2*>(A + j + 2);
+    const double2 b01 = *reinterpret_cast<const double2*>(B + j);
+    const double2 b23 = *reinterpret_cast<const double2*>(B + j + 2);
+    const double2 c01 = *reinterpret_cast<const double2*>(C + j);
+    const double2 c23 = *reinterpret_cast<const double2*>(C + j + 2);
     const double t0 = fma(px, a01.x, fma(py, b01.x, c01.x));
     const double t1 = fma(px, a01.y, fma(py, b01.y, c01.y));
     const double t2 = fma(px, a23.x, fma(py, b23.x, c23.x));
@@ -123,7 +127,8 @@ __device__ __forceinline__ bool hits_any(const double* __restrict__ A, int cnt, 
     if (t3 <= thr) maybe = true;
   }
   if (!maybe) return false;
-  for (int j = 0; j < cnt; ++j) {           // rare: exact re-test in the reference's arithmetic
+  for (int j = 0; j < cnt; ++j) {           // exact re-test in the reference's arithmetic
+    if (C[j] != C[j]) continue;             // padding / NaN-trajectory entries never hit
     const double dx = px - (-0.5 * A[j]), dy = py - (-0.5 * B[j]);
     if (dx * dx + dy * dy <= r2) return true;
   }
@@ -159,7 +164,7 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
   bool singular = false, nonfinite = false;
   double max_step2 = 0.0;
   unsigned flags = 0;
-  double x_prev = 0, y_prev = 0, s_prev = 0, d_prev = 0, dp_prev = 0, q_prev = 1, rth_prev = 0;
+  double x_prev = 0, y_prev = 0, s_prev = 0, d_prev = 0, ux_prev = 1, uy_prev = 0;
   KinResult R;
   R.v_last = 0; R.s_last = 0; R.s_first = 0;
 
@@ -180,6 +185,7 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
     if (n >= 1) {
       const double ex = x - x_prev, ey = y - y_prev;
       const double step2 = fma(ex, ex, ey * ey);                             // fp.py:954 (squared)
+      const double ux = r[2] * c.q - r[3] * c.d_p, uy = r[3] * c.q + r[2] * c.d_p;
       max_step2 = fmax(max_step2, step2);
       if (c.v > vmax) flags |= F_SPEED;                                      // fp.py:964
       if (fabs(c.a) > amax) flags |= F_ACCEL;                                // fp.py:966
@@ -191,18 +197,17 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
         if (dd > fmax(1.5 * ds_f, 0.02)) {
           flags |= F_CURV;
         } else {
-          const double yaw1 = wrap_angle(atan2(c.d_p, c.q) + r[11]);
-          const double yaw0 = wrap_angle(atan2(dp_prev, q_prev) + rth_prev);
-          double sn, cs;
-          sincos(yaw1 - yaw0, &sn, &cs);
-          const double dyaw = fabs(atan2(sn, cs));
-          if (dyaw > fmax(kmax * hypot(ex, ey), 0.1)) flags |= F_CURV;
+          // |wrap(yaw_i - yaw_{i-1})| is the angle between the two heading vectors
+          // u = R(rtheta) (q, d'), which needs one atan2 instead of the reference's five.
+          const double dyaw = fabs(atan2(ux_prev * uy - uy_prev * ux, ux_prev * ux + uy_prev * uy));
+          if (dyaw > fmax(kmax * sqrt(step2), 0.1)) flags |= F_CURV;
         }
       }
       if (c.v * c.v * fabs(c.kappa) > latmax) flags |= F_LAT;               // fp.py:975
       if (fabs(d) > road_thr) flags |= F_ROAD;                               // fp.py:982
     }
-    x_prev = x; y_prev = y; s_prev = s; d_prev = d; dp_prev = c.d_p; q_prev = c.q; rth_prev = r[11];
+    x_prev = x; y_prev = y; s_prev = s; d_prev = d;
+    ux_prev = r[2] * c.q - r[3] * c.d_p; uy_prev = r[3] * c.q + r[2] * c.d_p;
     R.v_last = c.v; R.s_last = s;
   }
 
@@ -218,61 +223,121 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
   return R;
 }
 
-// Pass C: time-aligned collision test of a kinematically clean candidate (fp.py:1035-1233);
-// leaves at the first decisive hit, like the reference's np.any / early return.
-__device__ __forceinline__ bool collision_pass(const Plan& P, const Batch& B, const BlockCtx& C, int q,
-                                               const Lat& lat, int kl, int keep) {
-  const double* tt = C.tt;
-  const double* ref = C.ref + (size_t)kl * C.NT * kRef;
-  const int n_circ = P.cfg.n_circles;
-  const int SP = B.S * B.P, SPp = pad4(SP), Mp = pad4(B.n_static);
-  const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
-  const double r2_stat = P.cfg.collide_r2;
-  const double r2_dyn = dist_mode ? P.cfg.collide_r2 : P.cfg.collide_r2_single;   // fp.py:1099-1104
-  const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
-  const int qs = B.static_per_query ? q : 0;
-  const double* stat = B.static_tm ? B.static_tm + (size_t)qs * 3 * Mp : nullptr;
-  const double smax2 = B.static_tm ? B.static_max2[qs] : 0.0;
-  const double* obs_q = B.obs_tm ? B.obs_tm + (size_t)q * B.T_obs * 3 * SPp : nullptr;
-  const double omax2 = B.obs_tm ? B.obs_max2[q] : 0.0;
-  unsigned long long viol = 0ull;
+// ---- TMA / mbarrier helpers (cp.async.bulk global -> shared, completion on an mbarrier) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
+// One obstacle tile of the collision pass: `n_planes` time planes (small fields: several whole
+// planes per tile) or one chunk of one plane (large fields).  Entries of a plane are stored in the
+// stage as [A | B | C] with plane stride 3*cnt.
+struct Tile {
+  int k0, n_planes, e0, cnt;   // first time plane, planes in the tile, first entry, entries per plane (multiple of 4)
+};
+struct TilePlan {
+  int SPp, cap, planes_per_tile, chunks_per_plane, n_tiles, K_used;
+  __device__ __forceinline__ void init(int SPp_, int cap_, int K_used_) {
+    SPp = SPp_; cap = cap_; K_used = K_used_;
+    if (SPp <= cap) { planes_per_tile = cap / SPp; chunks_per_plane = 1; n_tiles = (K_used + planes_per_tile - 1) / planes_per_tile; }
+    else { planes_per_tile = 1; chunks_per_plane = (SPp + cap - 1) / cap; n_tiles = K_used * chunks_per_plane; }
+  }
+  __device__ __forceinline__ Tile tile(int t) const {
+    Tile T;
+    if (chunks_per_plane == 1) { T.k0 = t * planes_per_tile; T.n_planes = min(planes_per_tile, K_used - T.k0); T.e0 = 0; T.cnt = SPp; }
+    else { T.k0 = t / chunks_per_plane; T.n_planes = 1; T.e0 = (t % chunks_per_plane) * cap; T.cnt = min(cap, SPp - T.e0); }
+    return T;
+  }
+};
+
+// Issue the bulk copies of tile `T` of `planes` ([K][3][SPp] doubles) into `stage`.
+__device__ __forceinline__ void tile_issue(const double* planes, const TilePlan& TP, const Tile& T, double* stage, uint64_t* bar) {
+  const uint32_t bytes = (uint32_t)T.n_planes * 3u * (uint32_t)T.cnt * 8u;
+  mbar_expect_tx(bar, bytes);
+  if (TP.chunks_per_plane == 1) {
+    tma_bulk_g2s(stage, planes + (size_t)T.k0 * 3 * TP.SPp, bytes, bar);
+  } else {
+    const double* src = planes + (size_t)T.k0 * 3 * TP.SPp + T.e0;
+    for (int pl = 0; pl < 3; ++pl) tma_bulk_g2s(stage + pl * T.cnt, src + (size_t)pl * TP.SPp, (uint32_t)T.cnt * 8u, bar);
+  }
+}
+
+// Per-thread state of the collision pass.
+struct CollState {
+  bool live;        // still needs testing (kinematically clean, no decisive hit yet)
+  bool hit;
+  int keep, kl;
+};
+
+// Test sample n of this thread's candidate against one staged plane (cnt entries at A).
+__device__ __forceinline__ bool sample_hits(const Plan& P, const BlockCtx& C, const Lat& lat, int kl, int n,
+                                            const double* A, int cnt, double r2, double omax2) {
+  const double* r = C.ref + ((size_t)kl * C.NT + n) * kRef;
+  const double d = lat_p0(lat, C.tt, n);
+  const double x = r[0] - r[3] * d;
+  const double y = r[1] + r[2] * d;
+  const int n_circ = P.cfg.n_circles;
+  if (n_circ == 0) return hits_any(A, cnt, cnt, x, y, r2, omax2);
+  const double d_p = lat_p1(lat, C.tt, n) * r[9];                              // fp.py:1158-1167
+  const double yaw = wrap_angle(atan2(d_p, 1.0 - r[4] * d) + r[11]);
+  double hx, hy;
+  sincos(yaw, &hy, &hx);
+  for (int ci = 0; ci < n_circ; ++ci)
+    if (hits_any(A, cnt, cnt, x + P.cfg.circle_offsets[ci] * hx, y + P.cfg.circle_offsets[ci] * hy, r2, omax2)) return true;
+  return false;
+}
+
+// Chance-constrained variant with a violation budget (fp.py:1113-1124): rare mode, straight from
+// global memory, exact arithmetic, per-sample early-out.
+__device__ __forceinline__ bool collision_budget(const Plan& P, const Batch& B, const BlockCtx& C, int q,
+                                                 const Lat& lat, int kl, int keep, int max_viol) {
+  const int SP = B.S * B.P, SPp = pad4(SP);
+  const double* obs_q = B.obs_tm + (size_t)q * B.T_obs * 3 * SPp;
+  const double r2 = P.cfg.collide_r2;
+  const int n_circ = P.cfg.n_circles;
+  unsigned long long viol = 0ull;
   for (int n = 0; n < keep; ++n) {
-    const double* r = ref + n * kRef;
-    const double d = lat_p0(lat, tt, n);
-    const double x = r[0] - r[3] * d;
-    const double y = r[1] + r[2] * d;
+    const double* r = C.ref + ((size_t)kl * C.NT + n) * kRef;
+    const double d = lat_p0(lat, C.tt, n);
+    const double x = r[0] - r[3] * d, y = r[1] + r[2] * d;
     double hx = 0.0, hy = 0.0;
-    if (n_circ > 0) {                                                        // fp.py:1158-1167
-      const double d_p = lat_p1(lat, tt, n) * r[9];
+    if (n_circ > 0) {
+      const double d_p = lat_p1(lat, C.tt, n) * r[9];
       const double yaw = wrap_angle(atan2(d_p, 1.0 - r[4] * d) + r[11]);
       sincos(yaw, &hy, &hx);
     }
-    const int n_pts = n_circ > 0 ? n_circ : 1;
-    const double* ob = obs_q ? obs_q + (size_t)C.kobs[n] * 3 * SPp : nullptr;
-    for (int ci = 0; ci < n_pts; ++ci) {
-      double px = x, py = y;
-      if (n_circ > 0) {
-        px = x + P.cfg.circle_offsets[ci] * hx;
-        py = y + P.cfg.circle_offsets[ci] * hy;
-      }
-      if (stat && hits_any(stat, B.n_static, Mp, px, py, r2_stat, smax2)) return true;
-      if (ob) {
-        if (max_viol == 0) {
-          if (hits_any(ob, SP, SPp, px, py, r2_dyn, omax2)) return true;
-        } else {
-          for (int sidx = 0; sidx < B.S; ++sidx) {
-            if ((viol >> sidx) & 1ull) continue;
-            bool hit = false;
-            for (int p = sidx * B.P; p < (sidx + 1) * B.P && !hit; ++p) {
-              const double dx = px - (-0.5 * ob[p]), dy = py - (-0.5 * ob[SPp + p]);
-              hit = dx * dx + dy * dy <= r2_dyn;
-            }
-            if (hit) viol |= (1ull << sidx);
-          }
-          if (__popcll(viol) > max_viol) return true;                        // fp.py:1121-1123
+    const double* ob = obs_q + (size_t)C.kobs[n] * 3 * SPp;
+    for (int ci = 0; ci < (n_circ > 0 ? n_circ : 1); ++ci) {
+      const double px = n_circ > 0 ? x + P.cfg.circle_offsets[ci] * hx : x;
+      const double py = n_circ > 0 ? y + P.cfg.circle_offsets[ci] * hy : y;
+      for (int sidx = 0; sidx < B.S; ++sidx) {
+        if ((viol >> sidx) & 1ull) continue;
+        bool hit = false;
+        for (int p = sidx * B.P; p < (sidx + 1) * B.P && !hit; ++p) {
+          const double dx = px - (-0.5 * ob[p]), dy = py - (-0.5 * ob[SPp + p]);
+          hit = dx * dx + dy * dy <= r2;
         }
+        if (hit) viol |= (1ull << sidx);
       }
+      if (__popcll(viol) > max_viol) return true;
     }
   }
   return false;
@@ -281,12 +346,15 @@ __device__ __forceinline__ bool collision_pass(const Plan& P, const Batch& B, co
 // ----------------------------------------------------------------------------------------
 // The sweep kernel.  Block b of query q covers either `ch_eff` consecutive (v, d) candidates of
 // one horizon T_j, or up to `kv_cap` brake-ladder candidates.
-//   phase 0: time-power table; quartic solve + jerk sum per terminal speed; reference-line
-//            samples (s(t), spline, heading, curvature) per (speed, t_n) -> shared memory
-//   phase 1: one thread per candidate: cost, kinematic pass, then collision pass if still clean
-//   phase 2: block arg-min by (cost, index) and category histogram
+//   phase 0: time-power table; quartic solve + jerk sum per terminal speed; lateral jerk sums;
+//            reference-line samples (s(t), spline, heading, curvature) per (speed, t_n) -> smem
+//   phase 1: one thread per candidate: cost + kinematic validity chain
+//   phase 2: collision test of the kinematically clean candidates, the block in lockstep over
+//            obstacle tiles that one thread streams into a shared-memory ring with TMA bulk
+//            copies (cp.async.bulk + mbarrier), static obstacles first, then the time planes
+//   phase 3: stop-distance filter, block arg-min by (cost, index), category histogram
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, 4)
 fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   extern __shared__ double sm[];
   const int NT = P.n_t_max;
@@ -294,11 +362,15 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   double* ref = tt + kTT * NT;                             // [kv_cap*NT][kRef]
   double* js = ref + (size_t)kRef * G.kv_cap * NT;         // [kv_cap]
   double* lonc = js + G.kv_cap;                            // [5][kv_cap]
-  int* holdk = reinterpret_cast<int*>(lonc + 5 * G.kv_cap);   // [kv_cap]
+  double* jp = lonc + 5 * G.kv_cap;                        // [jp_cap] lateral jerk sums
+  double* dend = jp + G.jp_cap;                            // [jp_cap] terminal lateral offsets
+  double* ring = dend + G.jp_cap;                          // [n_stages][3*tile_cap] obstacle tiles (16 B aligned)
+  int* holdk = reinterpret_cast<int*>(ring + (size_t)G.n_stages * 3 * G.tile_cap);   // [kv_cap]
   int* kobs = holdk + G.kv_cap;                            // [NT]
   __shared__ int s_stats[FOT_N_STATS];
   __shared__ double s_cost[kSweepThreads / 32];
   __shared__ int s_idx[kSweepThreads / 32];
+  __shared__ __align__(8) uint64_t s_bar[kMaxStages];
 
   const int q = blockIdx.x / G.blocks_per_query;
   const int b = blockIdx.x % G.blocks_per_query;
@@ -337,6 +409,10 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
 
   // ---- phase 0 ---------------------------------------------------------------------------
   if (tid < FOT_N_STATS) s_stats[tid] = 0;
+  if (tid == 0) {
+    for (int i = 0; i < G.n_stages; ++i) mbar_init(&s_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int n = tid; n < NT; n += kSweepThreads) {
     tt_fill(tt, n, P.cfg.dt);
     const double kf = rint(((double)n * P.cfg.dt) / P.cfg.dt);               // fp.py:1226-1227
@@ -355,6 +431,15 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     holdk[tid] = L.hold;
     auto jerk2 = [&](int n) { const double j = lon_p3(L, tt, n); return j * j; };
     js[tid] = np_pairwise_sum(jerk2, 0, N);             // fp.py:722
+  }
+  // lateral jerk sum and terminal offset once per lateral profile of this block (fp.py:718-719)
+  for (int i = tid; i < (brake_blk ? n_k : n_d); i += kSweepThreads) {
+    const Lat L = brake_blk
+        ? lat_solve(fs, fs[3], P.Tb[k_lo + i], P.inv5b + 9 * (k_lo + i), true, P.n_steps_b[k_lo + i])
+        : lat_solve(fs, P.d_grid[i], P.T[jT], P.inv5 + 9 * jT, n_d == 1, N - 1);
+    auto jerk2 = [&](int n) { const double j = lat_p3(L, tt, n); return j * j; };
+    jp[i] = np_pairwise_sum(jerk2, 0, N);
+    dend[i] = lat_p0(L, tt, N - 1);
   }
   __syncthreads();
   for (int idx = tid; idx < n_k * N; idx += kSweepThreads) {
@@ -376,27 +461,31 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   }
   __syncthreads();
 
-  // ---- phase 1 ---------------------------------------------------------------------------
-  double my_cost = INFINITY;
-  int my_idx = 0x7fffffff;
+  // ---- phase 1: cost + kinematic chain ----------------------------------------------------
+  const BlockCtx C{tt, ref, kobs, NT, N};
+  int kl = 0, cand_idx = 0, cat = FOT_CAT_DROP + 1;     // idle threads: no category
+  double cost = INFINITY;
+  Lat lat{};
+  KinResult K{};
+  CollState cs{false, false, 0, 0};
   if (tid < n_cand) {
-    int kl, cand_idx;
-    Lat lat;
+    int li;
     if (!brake_blk) {
       const int m = m0 + tid;
       const int kv = m / n_d, id = m - kv * n_d;
       kl = kv - k_lo;
+      li = id;
       cand_idx = (jT * n_v + kv) * n_d + id;
       lat = lat_solve(fs, P.d_grid[id], P.T[jT], P.inv5 + 9 * jT, n_d == 1, N - 1);
     } else {
       kl = tid;
+      li = tid;
       cand_idx = P.cfg.n_T * n_v * n_d + k_lo + tid;
       lat = lat_solve(fs, fs[3], P.Tb[k_lo + tid], P.inv5b + 9 * (k_lo + tid), true, P.n_steps_b[k_lo + tid]);
     }
     // cost on the un-truncated profile (fp.py:703-734)
-    auto jerk2 = [&](int n) { const double j = lat_p3(lat, tt, n); return j * j; };
-    const double Jp = np_pairwise_sum(jerk2, 0, N);
-    const double d_end = lat_p0(lat, tt, N - 1);
+    const double Jp = jp[li];
+    const double d_end = dend[li];
     const double Jd = d_end * d_end;
     const double Js = js[kl];
     const double dv = B.target[q] - ref[((size_t)kl * NT + (N - 1)) * kRef + 7];
@@ -404,13 +493,82 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     const double Jt = tt[kTT * (N - 1)];
     const double lat_cost = P.cfg.k_j * Jp + P.cfg.k_t * Jt + P.cfg.k_d * Jd;
     const double lon_cost = P.cfg.k_j * Js + P.cfg.k_t * Jt + P.cfg.k_s_dot * Jv;
-    const double cost = P.cfg.k_lat * lat_cost + P.cfg.k_lon * lon_cost;
+    cost = P.cfg.k_lat * lat_cost + P.cfg.k_lon * lon_cost;
+    K = kinematic_pass(P, C, lat, kl, B.limits + 4 * (size_t)q);
+    cat = K.category;
+    cs.live = cat < 0;
+    cs.keep = K.keep;
+    cs.kl = kl;
+  }
 
-    BlockCtx C{tt, ref, kobs, NT, N};
-    const KinResult K = kinematic_pass(P, C, lat, kl, B.limits + 4 * (size_t)q);
-    int cat = K.category;
+  // ---- phase 2: collision test (fp.py:1035-1233) -------------------------------------------
+  const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
+  const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
+  const int qs = B.static_per_query ? q : 0;
+  uint32_t n_issued = 0, n_waited = 0;                  // running tile counters -> stage + parity
+  auto run_tiles = [&](const double* planes, int SPp_, int K_used, bool is_static, double r2, double omax2) {
+    TilePlan TP;
+    TP.init(SPp_, G.tile_cap, K_used);
+    // prologue: fill the ring
+    int t_issue = 0;                                    // counters are uniform; only thread 0 issues
+    for (; t_issue < min(G.n_stages - 1, TP.n_tiles); ++t_issue, ++n_issued) {
+      const int st = n_issued % G.n_stages;
+      if (tid == 0) tile_issue(planes, TP, TP.tile(t_issue), ring + (size_t)st * 3 * G.tile_cap, &s_bar[st]);
+    }
+    for (int t = 0; t < TP.n_tiles; ++t) {
+      if (t_issue < TP.n_tiles) {                       // refill the stage freed by the previous barrier
+        const int st = n_issued % G.n_stages;
+        if (tid == 0) tile_issue(planes, TP, TP.tile(t_issue), ring + (size_t)st * 3 * G.tile_cap, &s_bar[st]);
+        ++t_issue; ++n_issued;
+      }
+      const int st = n_waited % G.n_stages;
+      mbar_wait(&s_bar[st], (n_waited / G.n_stages) & 1u);
+      ++n_waited;
+      if (cs.live) {
+        const Tile T = TP.tile(t);
+        const double* stage = ring + (size_t)st * 3 * G.tile_cap;
+        if (is_static) {                                 // every kept sample against this static chunk
+          for (int n = 0; n < cs.keep && !cs.hit; ++n)
+            cs.hit = sample_hits(P, C, lat, kl, n, stage, T.cnt, r2, omax2);
+        } else {                                         // samples whose time index falls in the tile
+          const int n_lo = T.k0;
+          const int n_hi = (T.k0 + T.n_planes >= K_used) ? N : T.k0 + T.n_planes;
+          for (int n = n_lo; n < min(n_hi, cs.keep) && !cs.hit; ++n)
+            cs.hit = sample_hits(P, C, lat, kl, n, stage + (size_t)(kobs[n] - T.k0) * 3 * T.cnt, T.cnt, r2, omax2);
+        }
+        if (cs.hit) cs.live = false;
+      }
+      // all reads of this stage are done before it is refilled; leave early once nobody is live
+      const int any_live = __syncthreads_or(cs.live ? 1 : 0);
+      if (!any_live) {
+        // drain copies already in flight so the ring can be reused / the block can exit
+        for (; n_waited < n_issued; ++n_waited) mbar_wait(&s_bar[n_waited % G.n_stages], (n_waited / G.n_stages) & 1u);
+        break;
+      }
+    }
+    __syncthreads();
+  };
+  if (__syncthreads_or(cs.live ? 1 : 0)) {
+    if (B.static_tm)
+      run_tiles(B.static_tm + (size_t)qs * 3 * pad4(B.n_static), pad4(B.n_static), 1, true, P.cfg.collide_r2,
+                B.static_max2[qs]);
+    if (B.obs_tm) {
+      const int SPp = pad4(B.S * B.P);
+      if (max_viol == 0) {
+        run_tiles(B.obs_tm + (size_t)q * B.T_obs * 3 * SPp, SPp, kobs[N - 1] + 1, false,
+                  dist_mode ? P.cfg.collide_r2 : P.cfg.collide_r2_single, B.obs_max2[q]);   // fp.py:1099-1104
+      } else if (cs.live) {
+        cs.hit = collision_budget(P, B, C, q, lat, kl, cs.keep, max_viol);
+      }
+    }
+  }
+
+  // ---- phase 3 ---------------------------------------------------------------------------
+  double my_cost = INFINITY;
+  int my_idx = 0x7fffffff;
+  if (tid < n_cand) {
     if (cat < 0) {
-      if (collision_pass(P, B, C, q, lat, kl, K.keep)) {
+      if (cs.hit) {
         cat = FOT_CAT_COLL;                                                  // fp.py:986-989
       } else {
         cat = FOT_CAT_OK;
@@ -426,8 +584,6 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + cand_idx] = cost;
     if (cat == FOT_CAT_OK && cost < INFINITY) { my_cost = cost; my_idx = cand_idx; }
   }
-
-  // ---- phase 2 ---------------------------------------------------------------------------
   for (int off = 16; off > 0; off >>= 1) {
     const double oc = __shfl_down_sync(0xffffffffu, my_cost, off);
     const int oi = __shfl_down_sync(0xffffffffu, my_idx, off);

@@ -38,7 +38,7 @@ for r, key in zip(body, lines):
 ti, ts = sum(inst.values()), sum(smp.values())
 print(f"total warp instructions {ti:.4g}, samples {ts:.0f}, avg active threads {sum(thr.values())/ti:.1f}")
 srcs = {}
-for key, c in sorted(inst.items(), key=lambda kv: -kv[1])[:top]:
+for key, c in sorted(inst.items(), key=lambda kv: -(smp[kv[0]] if os.environ.get("BY_SMP") else kv[1]))[:top]:
     if key is None:
         text = "?"
     else:
