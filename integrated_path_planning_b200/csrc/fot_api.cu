@@ -173,16 +173,27 @@ static int sweep_geometry(const fot_handle* h, const fot_batch_t* b, SweepGeom* 
   const int Mp = (b->n_static + 3) & ~3;
   int tile_cap = 0, n_stages = 0;
   if (SPp > 0 || Mp > 0) {
-    if (SPp > 0 && SPp <= 512) tile_cap = std::max(1, 256 / SPp) * SPp;   // whole planes, about 6 KB per stage
+    if (SPp > 0 && SPp <= 512) tile_cap = std::min(kGmax, std::max(1, 160 / SPp)) * SPp;   // whole planes, about 4 KB per stage
     else if (SPp > 512) tile_cap = 512;
     else tile_cap = std::min(512, Mp);
     n_stages = 3;
   }
-  auto bytes = [&](int kv) {
-    return ((size_t)kTT * NT + (size_t)kRef * kv * NT + 6 * (size_t)kv + 2 * (size_t)std::max(nd, kv) +
-            (size_t)n_stages * 3 * tile_cap) * sizeof(double) +
-           ((size_t)kv + NT) * sizeof(int32_t) + 16;
+  const bool footprint = h->plan.cfg.n_circles > 0;
+  // layout (doubles): tt | hot | js,lonc (6 kv) | jp,dend (2 jp_cap) | kin | [phase-2 region] | ints
+  auto layout = [&](int kv, int* phase2_off, int* ints_off) {
+    const size_t jp_cap = (size_t)std::max(nd, kv) + (std::max(nd, kv) & 1);
+    const size_t head = (size_t)kTT * NT + (size_t)kHot * kv * NT + 6 * (size_t)kv + 2 * jp_cap;
+    const size_t kin_sz = (size_t)kKin * kv * NT;
+    const size_t p2 = (size_t)n_stages * 3 * tile_cap + (size_t)kSweepThreads * kRec;
+    const bool alias = !footprint && p2 <= kin_sz;
+    const size_t p2_off = alias ? head : head + kin_sz;
+    const size_t ints = std::max(head + kin_sz, p2_off + p2);
+    if (phase2_off) *phase2_off = (int)p2_off;
+    if (ints_off) *ints_off = (int)ints;
+    return ints * sizeof(double) + ((size_t)2 * kv + NT + kSweepThreads + (size_t)kv * kGmax) * sizeof(int32_t) +
+           (size_t)kv * kGmax * kCullCap * sizeof(unsigned short) + 16;
   };
+  auto bytes = [&](int kv) { return layout(kv, nullptr, nullptr); };
   int ch = std::min(kSweepThreads, n_v_max * nd);
   ch = std::max(ch, 1);
   int kv;
@@ -196,13 +207,17 @@ static int sweep_geometry(const fot_handle* h, const fot_batch_t* b, SweepGeom* 
   g->ch_eff = ch;
   g->kv_cap = std::max(kv, 1);
   g->jp_cap = std::max(nd, g->kv_cap);
-  g->jp_cap += g->jp_cap & 1;                       // keeps the ring 16-byte aligned (see kernel layout)
+  g->jp_cap += g->jp_cap & 1;                       // keeps the following tables 16-byte aligned
+  int p2 = 0, io = 0;
+  layout(g->kv_cap, &p2, &io);
+  g->phase2_off = p2;
+  g->ints_off = io;
   g->tile_cap = tile_cap;
   g->n_stages = n_stages;
   g->chunks_per_T = (n_v_max * nd + ch - 1) / ch;
   g->brake_blocks = nB > 0 ? (nB + g->kv_cap - 1) / g->kv_cap : 0;
   g->blocks_per_query = h->plan.cfg.n_T * g->chunks_per_T + g->brake_blocks;
-  *smem_bytes = bytes(g->kv_cap) + 64;
+  *smem_bytes = bytes(g->kv_cap);
   return FOT_OK;
 }
 

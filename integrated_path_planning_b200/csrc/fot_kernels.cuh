@@ -14,7 +14,10 @@
 namespace fot {
 
 constexpr int kSweepThreads = 128;
-constexpr int kRef = 12;   // doubles per reference-line sample: rx ry cos sin | rk rdk s sd | sdd 1/sd 1/sd^2 rth
+// Reference-line samples per (terminal speed, t_n), two shared-memory tables:
+constexpr int kHot = 4;    // rx ry cos(rtheta) sin(rtheta)            -- both passes
+constexpr int kKin = 8;    // rk rdk s sd | sdd 1/sd 1/sd^2 rtheta      -- kinematic pass (+ footprint heading)
+constexpr int kRec = 8;    // doubles per compacted collision record: a0..a5, {hold,kl}, {keep,owner}
 
 // flag bits of the priority chain fp.py:964-991
 enum : unsigned { F_SPEED = 1u, F_ACCEL = 2u, F_CURV = 4u, F_LAT = 8u, F_ROAD = 16u };
@@ -28,8 +31,12 @@ struct SweepGeom {
   int32_t jp_cap;            // max(n_d, kv_cap): per-block lateral-profile slots
   int32_t tile_cap;          // obstacle entries (per plane) one ring stage holds; multiple of 4
   int32_t n_stages;          // ring depth
+  int32_t phase2_off;        // offset (doubles) of the ring + record region in dynamic shared memory
+  int32_t ints_off;          // offset (doubles) of the int tables
 };
 constexpr int kMaxStages = 4;
+constexpr int kGmax = 8;       // time steps culled / consumed per group
+constexpr int kCullCap = 16;   // relevant obstacles listed per (speed, step); more -> full scan of the plane
 
 __device__ __forceinline__ int pad4(int n) { return (n + 3) & ~3; }
 
@@ -107,7 +114,6 @@ __device__ __forceinline__ bool hits_any(const double* __restrict__ A, int cnt, 
   const double thr = r2 - pp + band;
   const double* __restrict__ B = A + ps;
   const double* __restrict__ C = B + ps;
-  bool maybe = false;
   const int cntp = pad4(cnt);
 #pragma unroll 2
   for (int j = 0; j < cntp; j += 4) {
@@ -121,16 +127,17 @@ __device__ __forceinline__ bool hits_any(const double* __restrict__ A, int cnt, 
     const double t1 = fma(px, a01.y, fma(py, b01.y, c01.y));
     const double t2 = fma(px, a23.x, fma(py, b23.x, c23.x));
     const double t3 = fma(px, a23.y, fma(py, b23.y, c23.y));
-    if (t0 <= thr) maybe = true;
-    if (t1 <= thr) maybe = true;
-    if (t2 <= thr) maybe = true;
-    if (t3 <= thr) maybe = true;
-  }
-  if (!maybe) return false;
-  for (int j = 0; j < cnt; ++j) {           // exact re-test in the reference's arithmetic
-    if (C[j] != C[j]) continue;             // padding / NaN-trajectory entries never hit
-    const double dx = px - (-0.5 * A[j]), dy = py - (-0.5 * B[j]);
-    if (dx * dx + dy * dy <= r2) return true;
+    if ((t0 <= thr) | (t1 <= thr) | (t2 <= thr) | (t3 <= thr)) {
+      // inside the band: decide with the reference's exact un-fused arithmetic
+      const double ax[4] = {a01.x, a01.y, a23.x, a23.y}, bx[4] = {b01.x, b01.y, b23.x, b23.y};
+      const double cx[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (cx[e] != cx[e]) continue;         // padding / NaN-trajectory entries never hit
+        const double dx = px - (-0.5 * ax[e]), dy = py - (-0.5 * bx[e]);
+        if (dx * dx + dy * dy <= r2) return true;
+      }
+    }
   }
   return false;
 }
@@ -138,7 +145,8 @@ __device__ __forceinline__ bool hits_any(const double* __restrict__ A, int cnt, 
 // Everything the per-candidate passes need that is uniform over a block.
 struct BlockCtx {
   const double* tt;     // [NT][kTT]
-  const double* ref;    // [kv_cap*NT][kRef]
+  const double* hot;    // [kv_cap*NT][kHot]
+  const double* kin;    // [kv_cap*NT][kKin]
   const int* kobs;      // [NT] obstacle time index of sample n (fp.py:1226-1227)
   int NT, N;
 };
@@ -154,7 +162,8 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
                                                     const double* __restrict__ lim) {
   const int N = C.N;
   const double* tt = C.tt;
-  const double* ref = C.ref + (size_t)kl * C.NT * kRef;
+  const double* hot = C.hot + (size_t)kl * C.NT * kHot;
+  const double* kin = C.kin + (size_t)kl * C.NT * kKin;
   const double vmax = lim[0], amax = lim[1], kmax = lim[2], latmax = lim[3];
   const double road_thr = P.cfg.max_road_width + 1e-9;                       // fp.py:982
   const double tele_thr = fmax(vmax, P.cfg.max_speed) * P.cfg.dt * 3.0;      // fp.py:955
@@ -164,28 +173,28 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
   bool singular = false, nonfinite = false;
   double max_step2 = 0.0;
   unsigned flags = 0;
-  double x_prev = 0, y_prev = 0, s_prev = 0, d_prev = 0, ux_prev = 1, uy_prev = 0;
+  double x_prev = 0, y_prev = 0, s_prev = 0, d_prev = 0, q_prev = 1, dp_prev = 0;
   KinResult R;
   R.v_last = 0; R.s_last = 0; R.s_first = 0;
 
   for (int n = 0; n < N; ++n) {
-    const double* r = ref + n * kRef;
-    const double rk = r[4];
+    const double* h = hot + n * kHot;
+    const double* r = kin + n * kKin;
+    const double rk = r[0];
     const double d = lat_p0(lat, tt, n);
     const double q1 = 1.0 - rk * d;                                          // fp.py:826-827
     if (isfinite(q1) && q1 <= 0.05) singular = true;
     if (first_nan >= 0) continue;
-    const double x = r[0] - r[3] * d;                                        // cc.py:131
+    const double x = h[0] - h[3] * d;                                        // cc.py:131
     if (x != x) { first_nan = n; continue; }                                // fp.py:851-866
-    const double y = r[1] + r[2] * d;                                        // cc.py:132
-    const double s = r[6], sd = r[7], sdd = r[8];
-    const KinPt c = kinematics_fast(rk, r[5], sd, sdd, r[9], r[10], d, lat_p1(lat, tt, n), lat_p2(lat, tt, n));
+    const double y = h[1] + h[2] * d;                                        // cc.py:132
+    const double s = r[2], sd = r[3], sdd = r[4];
+    const KinPt c = kinematics_fast(rk, r[1], sd, sdd, r[5], r[6], d, lat_p1(lat, tt, n), lat_p2(lat, tt, n));
     if (!(isfinite(c.v) && isfinite(c.a) && isfinite(c.kappa))) nonfinite = true;   // fp.py:944-946
     if (n == 0) R.s_first = s;
     if (n >= 1) {
       const double ex = x - x_prev, ey = y - y_prev;
       const double step2 = fma(ex, ex, ey * ey);                             // fp.py:954 (squared)
-      const double ux = r[2] * c.q - r[3] * c.d_p, uy = r[3] * c.q + r[2] * c.d_p;
       max_step2 = fmax(max_step2, step2);
       if (c.v > vmax) flags |= F_SPEED;                                      // fp.py:964
       if (fabs(c.a) > amax) flags |= F_ACCEL;                                // fp.py:966
@@ -199,6 +208,9 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
         } else {
           // |wrap(yaw_i - yaw_{i-1})| is the angle between the two heading vectors
           // u = R(rtheta) (q, d'), which needs one atan2 instead of the reference's five.
+          const double* hp = h - kHot;
+          const double ux = h[2] * c.q - h[3] * c.d_p, uy = h[3] * c.q + h[2] * c.d_p;
+          const double ux_prev = hp[2] * q_prev - hp[3] * dp_prev, uy_prev = hp[3] * q_prev + hp[2] * dp_prev;
           const double dyaw = fabs(atan2(ux_prev * uy - uy_prev * ux, ux_prev * ux + uy_prev * uy));
           if (dyaw > fmax(kmax * sqrt(step2), 0.1)) flags |= F_CURV;
         }
@@ -206,8 +218,7 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
       if (c.v * c.v * fabs(c.kappa) > latmax) flags |= F_LAT;               // fp.py:975
       if (fabs(d) > road_thr) flags |= F_ROAD;                               // fp.py:982
     }
-    x_prev = x; y_prev = y; s_prev = s; d_prev = d;
-    ux_prev = r[2] * c.q - r[3] * c.d_p; uy_prev = r[3] * c.q + r[2] * c.d_p;
+    x_prev = x; y_prev = y; s_prev = s; d_prev = d; q_prev = c.q; dp_prev = c.d_p;
     R.v_last = c.v; R.s_last = s;
   }
 
@@ -290,14 +301,15 @@ struct CollState {
 // Test sample n of this thread's candidate against one staged plane (cnt entries at A).
 __device__ __forceinline__ bool sample_hits(const Plan& P, const BlockCtx& C, const Lat& lat, int kl, int n,
                                             const double* A, int cnt, double r2, double omax2) {
-  const double* r = C.ref + ((size_t)kl * C.NT + n) * kRef;
+  const double* h = C.hot + ((size_t)kl * C.NT + n) * kHot;
   const double d = lat_p0(lat, C.tt, n);
-  const double x = r[0] - r[3] * d;
-  const double y = r[1] + r[2] * d;
+  const double x = h[0] - h[3] * d;
+  const double y = h[1] + h[2] * d;
   const int n_circ = P.cfg.n_circles;
   if (n_circ == 0) return hits_any(A, cnt, cnt, x, y, r2, omax2);
-  const double d_p = lat_p1(lat, C.tt, n) * r[9];                              // fp.py:1158-1167
-  const double yaw = wrap_angle(atan2(d_p, 1.0 - r[4] * d) + r[11]);
+  const double* r = C.kin + ((size_t)kl * C.NT + n) * kKin;                    // (not aliased in footprint mode)
+  const double d_p = lat_p1(lat, C.tt, n) * r[5];                              // fp.py:1158-1167
+  const double yaw = wrap_angle(atan2(d_p, 1.0 - r[0] * d) + r[7]);
   double hx, hy;
   sincos(yaw, &hy, &hx);
   for (int ci = 0; ci < n_circ; ++ci)
@@ -315,13 +327,14 @@ __device__ __forceinline__ bool collision_budget(const Plan& P, const Batch& B, 
   const int n_circ = P.cfg.n_circles;
   unsigned long long viol = 0ull;
   for (int n = 0; n < keep; ++n) {
-    const double* r = C.ref + ((size_t)kl * C.NT + n) * kRef;
+    const double* h = C.hot + ((size_t)kl * C.NT + n) * kHot;
+    const double* r = C.kin + ((size_t)kl * C.NT + n) * kKin;
     const double d = lat_p0(lat, C.tt, n);
-    const double x = r[0] - r[3] * d, y = r[1] + r[2] * d;
+    const double x = h[0] - h[3] * d, y = h[1] + h[2] * d;
     double hx = 0.0, hy = 0.0;
     if (n_circ > 0) {
-      const double d_p = lat_p1(lat, C.tt, n) * r[9];
-      const double yaw = wrap_angle(atan2(d_p, 1.0 - r[4] * d) + r[11]);
+      const double d_p = lat_p1(lat, C.tt, n) * r[5];
+      const double yaw = wrap_angle(atan2(d_p, 1.0 - r[0] * d) + r[7]);
       sincos(yaw, &hy, &hx);
     }
     const double* ob = obs_q + (size_t)C.kobs[n] * 3 * SPp;
@@ -359,14 +372,23 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   extern __shared__ double sm[];
   const int NT = P.n_t_max;
   double* tt = sm;                                         // [NT][kTT]
-  double* ref = tt + kTT * NT;                             // [kv_cap*NT][kRef]
-  double* js = ref + (size_t)kRef * G.kv_cap * NT;         // [kv_cap]
+  double* hot = tt + kTT * NT;                             // [kv_cap*NT][kHot]
+  double* js = hot + (size_t)kHot * G.kv_cap * NT;         // [kv_cap]
   double* lonc = js + G.kv_cap;                            // [5][kv_cap]
   double* jp = lonc + 5 * G.kv_cap;                        // [jp_cap] lateral jerk sums
   double* dend = jp + G.jp_cap;                            // [jp_cap] terminal lateral offsets
-  double* ring = dend + G.jp_cap;                          // [n_stages][3*tile_cap] obstacle tiles (16 B aligned)
-  int* holdk = reinterpret_cast<int*>(ring + (size_t)G.n_stages * 3 * G.tile_cap);   // [kv_cap]
+  double* kin = dend + G.jp_cap;                           // [kv_cap*NT][kKin]
+  // phase-2 region: obstacle ring + compacted records.  When it fits (and no footprint needs the
+  // kinematic table in phase 2) it re-uses the kinematic table's memory, which is dead by then.
+  double* ring = sm + G.phase2_off;                        // [n_stages][3*tile_cap] obstacle tiles (16 B aligned)
+  double* rec = ring + (size_t)G.n_stages * 3 * G.tile_cap;   // [kSweepThreads][kRec]
+  int* holdk = reinterpret_cast<int*>(sm + G.ints_off);    // [kv_cap]
   int* kobs = holdk + G.kv_cap;                            // [NT]
+  int* hitf = kobs + NT;                                   // [kSweepThreads] collision verdict per owner thread
+  int* pair_live = hitf + kSweepThreads;                   // [kv_cap] any clean candidate with this terminal speed?
+  int* ccnt = pair_live + G.kv_cap;                        // [kv_cap*kGmax] relevant obstacles per (speed, step)
+  unsigned short* clist = reinterpret_cast<unsigned short*>(ccnt + G.kv_cap * kGmax);   // [kv_cap*kGmax][kCullCap]
+  __shared__ int s_wcnt[kSweepThreads / 32];
   __shared__ int s_stats[FOT_N_STATS];
   __shared__ double s_cost[kSweepThreads / 32];
   __shared__ int s_idx[kSweepThreads / 32];
@@ -454,15 +476,16 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     sincos(rp.rth, &sn, &cs);                           // cc.py:128-129
     const bool moving = fabs(sd) > 1e-3;                // fp.py:792
     const double inv_sd = moving ? 1.0 / sd : 0.0;
-    double* r = ref + ((size_t)kl * NT + n) * kRef;
-    r[0] = rp.rx; r[1] = rp.ry; r[2] = cs; r[3] = sn;
-    r[4] = rp.rk; r[5] = rp.rdk; r[6] = s; r[7] = sd;
-    r[8] = lon_p2(L, tt, n); r[9] = inv_sd; r[10] = inv_sd * inv_sd; r[11] = rp.rth;
+    double* h = hot + ((size_t)kl * NT + n) * kHot;
+    double* r = kin + ((size_t)kl * NT + n) * kKin;
+    h[0] = rp.rx; h[1] = rp.ry; h[2] = cs; h[3] = sn;
+    r[0] = rp.rk; r[1] = rp.rdk; r[2] = s; r[3] = sd;
+    r[4] = lon_p2(L, tt, n); r[5] = inv_sd; r[6] = inv_sd * inv_sd; r[7] = rp.rth;
   }
   __syncthreads();
 
   // ---- phase 1: cost + kinematic chain ----------------------------------------------------
-  const BlockCtx C{tt, ref, kobs, NT, N};
+  const BlockCtx C{tt, hot, kin, kobs, NT, N};
   int kl = 0, cand_idx = 0, cat = FOT_CAT_DROP + 1;     // idle threads: no category
   double cost = INFINITY;
   Lat lat{};
@@ -488,7 +511,7 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     const double d_end = dend[li];
     const double Jd = d_end * d_end;
     const double Js = js[kl];
-    const double dv = B.target[q] - ref[((size_t)kl * NT + (N - 1)) * kRef + 7];
+    const double dv = B.target[q] - kin[((size_t)kl * NT + (N - 1)) * kKin + 3];
     const double Jv = dv * dv;
     const double Jt = tt[kTT * (N - 1)];
     const double lat_cost = P.cfg.k_j * Jp + P.cfg.k_t * Jt + P.cfg.k_d * Jd;
@@ -506,6 +529,9 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
   const int qs = B.static_per_query ? q : 0;
   uint32_t n_issued = 0, n_waited = 0;                  // running tile counters -> stage + parity
+  const int n_circ = P.cfg.n_circles;
+  double max_off = 0.0;                                 // footprint circles sit within max|offset| of the path point
+  for (int i = 0; i < n_circ; ++i) max_off = fmax(max_off, fabs(P.cfg.circle_offsets[i]));
   auto run_tiles = [&](const double* planes, int SPp_, int K_used, bool is_static, double r2, double omax2) {
     TilePlan TP;
     TP.init(SPp_, G.tile_cap, K_used);
@@ -524,23 +550,83 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
       const int st = n_waited % G.n_stages;
       mbar_wait(&s_bar[st], (n_waited / G.n_stages) & 1u);
       ++n_waited;
-      if (cs.live) {
-        const Tile T = TP.tile(t);
-        const double* stage = ring + (size_t)st * 3 * G.tile_cap;
-        if (is_static) {                                 // every kept sample against this static chunk
-          for (int n = 0; n < cs.keep && !cs.hit; ++n)
-            cs.hit = sample_hits(P, C, lat, kl, n, stage, T.cnt, r2, omax2);
-        } else {                                         // samples whose time index falls in the tile
-          const int n_lo = T.k0;
-          const int n_hi = (T.k0 + T.n_planes >= K_used) ? N : T.k0 + T.n_planes;
-          for (int n = n_lo; n < min(n_hi, cs.keep) && !cs.hit; ++n)
-            cs.hit = sample_hits(P, C, lat, kl, n, stage + (size_t)(kobs[n] - T.k0) * 3 * T.cnt, T.cnt, r2, omax2);
+      // A clean candidate's sample n lies on the normal of the reference line through the
+      // (speed, n) reference point, at lateral offset |d| <= wc - rc (road-bound check passed; n = 0
+      // is the ego's own offset).  So only obstacles within rc along the tangent and wc across it
+      // can touch any candidate of that speed at that step: the block first lists those (a handful
+      // out of the whole plane), then every candidate tests its own point against the short list
+      // with the reference's exact arithmetic.  Conservative margins make the list a superset.
+      const Tile T = TP.tile(t);
+      const double* stage = ring + (size_t)st * 3 * G.tile_cap;
+      const int n_lo = is_static ? 0 : T.k0;
+      const int n_hi = is_static ? N : ((T.k0 + T.n_planes >= K_used) ? N : T.k0 + T.n_planes);
+      const double rc = sqrt(r2) * (1.0 + 1e-9) + 1e-9 + max_off;
+      const double wc = fmax(P.cfg.max_road_width + 1e-9, fabs(fs[3])) + rc;
+      const int lane = tid & 31, warp = tid >> 5;
+      bool done = false;
+      for (int g0 = n_lo; g0 < n_hi; g0 += kGmax) {
+        const int ng = min(kGmax, n_hi - g0);
+        for (int pg = warp; pg < n_k * ng; pg += kSweepThreads / 32) {       // cull: one warp per (speed, step)
+          const int klc = pg / ng, n = g0 + (pg - klc * ng);
+          int total = 0;
+          if (pair_live[klc]) {
+            const double* h = hot + ((size_t)klc * NT + n) * kHot;
+            const double rx = h[0], ry = h[1], cth = h[2], sth = h[3];
+            const double* A = stage + (is_static ? 0 : (size_t)(kobs[n] - T.k0) * 3 * T.cnt);
+            for (int j0 = 0; j0 < T.cnt; j0 += 32) {
+              const int j = j0 + lane;
+              bool rel = false;
+              if (j < T.cnt) {
+                const double ex = -0.5 * A[j] - rx, ey = -0.5 * A[T.cnt + j] - ry;
+                const double cc = A[2 * T.cnt + j];                          // NaN marks padding entries
+                rel = fabs(ex * cth + ey * sth) <= rc && fabs(ey * cth - ex * sth) <= wc && cc == cc;   // NaN -> false
+              }
+              const unsigned m = __ballot_sync(0xffffffffu, rel);
+              if (rel) {
+                const int pos = total + __popc(m & ((1u << lane) - 1u));
+                if (pos < kCullCap) clist[pg * kCullCap + pos] = (unsigned short)j;
+              }
+              total += __popc(m);
+            }
+          }
+          if (lane == 0) ccnt[pg] = total;
         }
-        if (cs.hit) cs.live = false;
+        __syncthreads();
+        if (cs.live) {                                                       // consume
+          for (int n = g0; n < min(g0 + ng, cs.keep) && !cs.hit; ++n) {
+            const int pg = kl * ng + (n - g0);
+            const int c = ccnt[pg];
+            if (c == 0) continue;
+            const double* A = stage + (is_static ? 0 : (size_t)(kobs[n] - T.k0) * 3 * T.cnt);
+            if (c > kCullCap || T.cnt > 65535) {                             // list overflow: scan the plane
+              cs.hit = sample_hits(P, C, lat, kl, n, A, T.cnt, r2, omax2);
+              continue;
+            }
+            const double* h = hot + ((size_t)kl * NT + n) * kHot;
+            const double d = lat_p0(lat, tt, n);
+            const double x = h[0] - h[3] * d, y = h[1] + h[2] * d;
+            double hx = 0.0, hy = 0.0;
+            if (n_circ > 0) {                                                // fp.py:1158-1167
+              const double* r = kin + ((size_t)kl * NT + n) * kKin;
+              const double d_p = lat_p1(lat, tt, n) * r[5];
+              sincos(wrap_angle(atan2(d_p, 1.0 - r[0] * d) + r[7]), &hy, &hx);
+            }
+            for (int ci = 0; ci < (n_circ > 0 ? n_circ : 1) && !cs.hit; ++ci) {
+              const double px = n_circ > 0 ? x + P.cfg.circle_offsets[ci] * hx : x;
+              const double py = n_circ > 0 ? y + P.cfg.circle_offsets[ci] * hy : y;
+              for (int e = 0; e < c; ++e) {
+                const int j = clist[pg * kCullCap + e];
+                const double dx = px - (-0.5 * A[j]), dy = py - (-0.5 * A[T.cnt + j]);
+                if (dx * dx + dy * dy <= r2) { cs.hit = true; break; }       // fp.py:1196-1198, :1231-1233
+              }
+            }
+          }
+          if (cs.hit) cs.live = false;
+        }
+        // all reads of the lists / this stage are done; leave early once nobody is live
+        if (!__syncthreads_or(cs.live ? 1 : 0)) { done = true; break; }
       }
-      // all reads of this stage are done before it is refilled; leave early once nobody is live
-      const int any_live = __syncthreads_or(cs.live ? 1 : 0);
-      if (!any_live) {
+      if (done) {
         // drain copies already in flight so the ring can be reused / the block can exit
         for (; n_waited < n_issued; ++n_waited) mbar_wait(&s_bar[n_waited % G.n_stages], (n_waited / G.n_stages) & 1u);
         break;
@@ -548,7 +634,36 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     }
     __syncthreads();
   };
-  if (__syncthreads_or(cs.live ? 1 : 0)) {
+  // Compact the kinematically clean candidates to the low threads so the collision pass runs in
+  // dense warps; each record remembers its owner thread, which gets the verdict back through hitf.
+  hitf[tid] = 0;
+  if (tid < G.kv_cap) pair_live[tid] = 0;
+  const unsigned live_mask = __ballot_sync(0xffffffffu, cs.live);
+  if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(live_mask);
+  __syncthreads();                                       // also: every read of `kin` is done
+  int n_live = 0, slot = __popc(live_mask & ((1u << (tid & 31)) - 1u));
+  for (int w = 0; w < kSweepThreads / 32; ++w) {
+    if (w < (tid >> 5)) slot += s_wcnt[w];
+    n_live += s_wcnt[w];
+  }
+  if (n_live > 0) {
+    if (cs.live) {
+      double* rc = rec + (size_t)slot * kRec;
+      rc[0] = lat.a0; rc[1] = lat.a1; rc[2] = lat.a2; rc[3] = lat.a3; rc[4] = lat.a4; rc[5] = lat.a5;
+      reinterpret_cast<int*>(rc + 6)[0] = lat.hold; reinterpret_cast<int*>(rc + 6)[1] = kl;
+      reinterpret_cast<int*>(rc + 7)[0] = cs.keep;  reinterpret_cast<int*>(rc + 7)[1] = tid;
+      pair_live[kl] = 1;
+    }
+    __syncthreads();
+    int owner = 0;
+    cs.live = tid < n_live;
+    cs.hit = false;
+    if (cs.live) {
+      const double* rc = rec + (size_t)tid * kRec;
+      lat.a0 = rc[0]; lat.a1 = rc[1]; lat.a2 = rc[2]; lat.a3 = rc[3]; lat.a4 = rc[4]; lat.a5 = rc[5];
+      lat.hold = reinterpret_cast<const int*>(rc + 6)[0]; kl = reinterpret_cast<const int*>(rc + 6)[1];
+      cs.keep = reinterpret_cast<const int*>(rc + 7)[0];  owner = reinterpret_cast<const int*>(rc + 7)[1];
+    }
     if (B.static_tm)
       run_tiles(B.static_tm + (size_t)qs * 3 * pad4(B.n_static), pad4(B.n_static), 1, true, P.cfg.collide_r2,
                 B.static_max2[qs]);
@@ -561,6 +676,8 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
         cs.hit = collision_budget(P, B, C, q, lat, kl, cs.keep, max_viol);
       }
     }
+    if (cs.hit) hitf[owner] = 1;
+    __syncthreads();
   }
 
   // ---- phase 3 ---------------------------------------------------------------------------
@@ -568,7 +685,7 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   int my_idx = 0x7fffffff;
   if (tid < n_cand) {
     if (cat < 0) {
-      if (cs.hit) {
+      if (hitf[tid]) {
         cat = FOT_CAT_COLL;                                                  // fp.py:986-989
       } else {
         cat = FOT_CAT_OK;
