@@ -153,6 +153,21 @@ __device__ __forceinline__ double lat_p3(const Lat& L, const double* tt, int n) 
   return 6.0 * L.a3 + 24.0 * L.a4 * r[0] + 60.0 * L.a5 * r[1];
 }
 
+// Lateral offset and its first two time derivatives at time t by Horner's scheme with running
+// derivatives (12 FMAs, needs only t).  Used by the sweep's validity and collision passes; differs from
+// the reference-order lat_p0/1/2 by a few ulp.  The cost and the returned winner use the latter.
+__device__ __forceinline__ void lat_fast(const Lat& L, double t, double& d, double& d1, double& d2) {
+  double p = fma(L.a5, t, L.a4), dp = L.a5, ddp;
+  ddp = dp;             dp = fma(dp, t, p);  p = fma(p, t, L.a3);
+  ddp = fma(ddp, t, dp); dp = fma(dp, t, p);  p = fma(p, t, L.a2);
+  ddp = fma(ddp, t, dp); dp = fma(dp, t, p);  p = fma(p, t, L.a1);
+  ddp = fma(ddp, t, dp); dp = fma(dp, t, p);  p = fma(p, t, L.a0);
+  d = p; d1 = dp; d2 = 2.0 * ddp;
+}
+__device__ __forceinline__ double lat_fast0(const Lat& L, double t) {
+  return fma(fma(fma(fma(fma(L.a5, t, L.a4), t, L.a3), t, L.a2), t, L.a1), t, L.a0);
+}
+
 // np.sum over a contiguous float64 vector: NumPy's pairwise summation (8 interleaved
 // accumulators per <=128-element block, halving above that).  The jerk costs fp.py:718,:722
 // go through it, so the cost -- and with it the arg-min -- only reproduces with this order.
@@ -176,15 +191,18 @@ __device__ __forceinline__ double np_block_sum(const F& f, int lo, int n) {   //
   return res;
 }
 template <class F>
-__device__ __noinline__ double np_split_sum(const F& f, int lo, int n) {      // n > 128: halve, 8-aligned
-  if (n <= 128) return np_block_sum(f, lo, n);
+__device__ __noinline__ double np_split_sum(const F& f, int lo, int n) {      // only reached for n > 128: halve, 8-aligned
   int n2 = n / 2;
   n2 -= n2 % 8;
-  return np_split_sum(f, lo, n2) + np_split_sum(f, lo + n2, n - n2);
+  const int n3 = n - n2;
+  const double left = n2 <= 128 ? np_block_sum(f, lo, n2) : np_split_sum(f, lo, n2);
+  const double right = n3 <= 128 ? np_block_sum(f, lo + n2, n3) : np_split_sum(f, lo + n2, n3);
+  return left + right;
 }
 template <class F>
 __device__ __forceinline__ double np_pairwise_sum(const F& f, int lo, int n) {
-  return n <= 128 ? np_block_sum(f, lo, n) : np_split_sum(f, lo, n);
+  if (n <= 128) return np_block_sum(f, lo, n);
+  return np_split_sum(f, lo, n);
 }
 
 // Reference-line sample at arc length s (cs.py:47-166, :215-288).  NaN outside the knot range.

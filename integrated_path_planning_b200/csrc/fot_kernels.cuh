@@ -168,6 +168,7 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
   const double road_thr = P.cfg.max_road_width + 1e-9;                       // fp.py:982
   const double tele_thr = fmax(vmax, P.cfg.max_speed) * P.cfg.dt * 3.0;      // fp.py:955
   const double tele_thr2 = tele_thr * tele_thr;
+  const double kTan01Sq = 0.010067046422495888;                              // tan(0.1)^2
 
   int first_nan = -1;
   bool singular = false, nonfinite = false;
@@ -175,51 +176,58 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
   unsigned flags = 0;
   double x_prev = 0, y_prev = 0, s_prev = 0, d_prev = 0, q_prev = 1, dp_prev = 0;
   KinResult R;
-  R.v_last = 0; R.s_last = 0; R.s_first = 0;
+  R.v_last = 0; R.s_last = 0; R.s_first = kin[2];
 
   for (int n = 0; n < N; ++n) {
     const double* h = hot + n * kHot;
     const double* r = kin + n * kKin;
     const double rk = r[0];
-    const double d = lat_p0(lat, tt, n);
-    const double q1 = 1.0 - rk * d;                                          // fp.py:826-827
-    if (isfinite(q1) && q1 <= 0.05) singular = true;
-    if (first_nan >= 0) continue;
-    const double x = h[0] - h[3] * d;                                        // cc.py:131
-    if (x != x) { first_nan = n; continue; }                                // fp.py:851-866
-    const double y = h[1] + h[2] * d;                                        // cc.py:132
-    const double s = r[2], sd = r[3], sdd = r[4];
-    const KinPt c = kinematics_fast(rk, r[1], sd, sdd, r[5], r[6], d, lat_p1(lat, tt, n), lat_p2(lat, tt, n));
-    if (!(isfinite(c.v) && isfinite(c.a) && isfinite(c.kappa))) nonfinite = true;   // fp.py:944-946
-    if (n == 0) R.s_first = s;
-    if (n >= 1) {
-      const double ex = x - x_prev, ey = y - y_prev;
-      const double step2 = fma(ex, ex, ey * ey);                             // fp.py:954 (squared)
-      max_step2 = fmax(max_step2, step2);
-      if (c.v > vmax) flags |= F_SPEED;                                      // fp.py:964
-      if (fabs(c.a) > amax) flags |= F_ACCEL;                                // fp.py:966
-      if (c.v > 0.5) {                                                       // fp.py:1019-1021
-        if (fabs(c.kappa) > kmax) flags |= F_CURV;
-      } else if (!(flags & F_CURV)) {                                        // fp.py:1022-1032
-        const double dd = fabs(d - d_prev);
-        const double ds_f = fabs(s - s_prev);
-        if (dd > fmax(1.5 * ds_f, 0.02)) {
-          flags |= F_CURV;
-        } else {
-          // |wrap(yaw_i - yaw_{i-1})| is the angle between the two heading vectors
-          // u = R(rtheta) (q, d'), which needs one atan2 instead of the reference's five.
-          const double* hp = h - kHot;
-          const double ux = h[2] * c.q - h[3] * c.d_p, uy = h[3] * c.q + h[2] * c.d_p;
-          const double ux_prev = hp[2] * q_prev - hp[3] * dp_prev, uy_prev = hp[3] * q_prev + hp[2] * dp_prev;
-          const double dyaw = fabs(atan2(ux_prev * uy - uy_prev * ux, ux_prev * ux + uy_prev * uy));
-          if (dyaw > fmax(kmax * sqrt(step2), 0.1)) flags |= F_CURV;
+    double d, d1, d2;
+    lat_fast(lat, tt[kTT * (n > lat.hold ? lat.hold : n)], d, d1, d2);
+    if (n > lat.hold) { d1 = 0.0; d2 = 0.0; }                                // fp.py:487-499 brake padding
+    const double q1 = fma(-rk, d, 1.0);                                      // fp.py:826-827
+    singular |= (q1 <= 0.05) & (fabs(q1) < INFINITY);
+    const double x = fma(-h[3], d, h[0]);                                    // cc.py:131
+    if (first_nan < 0) {
+      if (x != x) {                                                          // fp.py:851-866
+        first_nan = n;
+      } else {
+        const double y = fma(h[2], d, h[1]);                                 // cc.py:132
+        const double s = r[2], sd = r[3], sdd = r[4];
+        const KinPt c = kinematics_fast(rk, r[1], sd, sdd, r[5], r[6], d, d1, d2);
+        nonfinite |= !(fabs(c.v) + fabs(c.a) + fabs(c.kappa) < INFINITY);    // fp.py:944-946
+        if (n >= 1) {
+          const double ex = x - x_prev, ey = y - y_prev;
+          const double step2 = fma(ex, ex, ey * ey);                         // fp.py:954 (squared)
+          if (step2 > max_step2) max_step2 = step2;
+          if (c.v > vmax) flags |= F_SPEED;                                  // fp.py:964
+          if (fabs(c.a) > amax) flags |= F_ACCEL;                            // fp.py:966
+          if (c.v > 0.5) {                                                   // fp.py:1019-1021
+            if (fabs(c.kappa) > kmax) flags |= F_CURV;
+          } else if (!(flags & F_CURV)) {                                    // fp.py:1022-1032
+            if (fabs(d - d_prev) > fmax(1.5 * fabs(s - s_prev), 0.02)) {
+              flags |= F_CURV;
+            } else {
+              // |wrap(yaw_i - yaw_{i-1})| is the angle between the heading vectors u = R(rtheta)(q, d').
+              const double* hp = h - kHot;
+              const double ux = h[2] * c.q - h[3] * c.d_p, uy = h[3] * c.q + h[2] * c.d_p;
+              const double ux_prev = hp[2] * q_prev - hp[3] * dp_prev, uy_prev = hp[3] * q_prev + hp[2] * dp_prev;
+              const double cr = ux_prev * uy - uy_prev * ux, dt_ = ux_prev * ux + uy_prev * uy;
+              if (kmax * kmax * step2 <= 0.01) {
+                // threshold is the 0.1 rad floor: angle > 0.1  <=>  dot <= 0 or cross^2 > tan(0.1)^2 dot^2
+                if (dt_ <= 0.0 || cr * cr > kTan01Sq * dt_ * dt_) flags |= F_CURV;
+              } else if (fabs(atan2(cr, dt_)) > kmax * sqrt(step2)) {
+                flags |= F_CURV;
+              }
+            }
+          }
+          if (c.v * c.v * fabs(c.kappa) > latmax) flags |= F_LAT;           // fp.py:975
+          if (fabs(d) > road_thr) flags |= F_ROAD;                           // fp.py:982
         }
+        x_prev = x; y_prev = y; s_prev = s; d_prev = d; q_prev = c.q; dp_prev = c.d_p;
+        R.v_last = c.v; R.s_last = s;
       }
-      if (c.v * c.v * fabs(c.kappa) > latmax) flags |= F_LAT;               // fp.py:975
-      if (fabs(d) > road_thr) flags |= F_ROAD;                               // fp.py:982
     }
-    x_prev = x; y_prev = y; s_prev = s; d_prev = d; q_prev = c.q; dp_prev = c.d_p;
-    R.v_last = c.v; R.s_last = s;
   }
 
   R.keep = first_nan < 0 ? N : (first_nan >= 2 ? first_nan : 0);            // fp.py:866
@@ -302,9 +310,9 @@ struct CollState {
 __device__ __forceinline__ bool sample_hits(const Plan& P, const BlockCtx& C, const Lat& lat, int kl, int n,
                                             const double* A, int cnt, double r2, double omax2) {
   const double* h = C.hot + ((size_t)kl * C.NT + n) * kHot;
-  const double d = lat_p0(lat, C.tt, n);
-  const double x = h[0] - h[3] * d;
-  const double y = h[1] + h[2] * d;
+  const double d = lat_fast0(lat, C.tt[kTT * (n > lat.hold ? lat.hold : n)]);
+  const double x = fma(-h[3], d, h[0]);
+  const double y = fma(h[2], d, h[1]);
   const int n_circ = P.cfg.n_circles;
   if (n_circ == 0) return hits_any(A, cnt, cnt, x, y, r2, omax2);
   const double* r = C.kin + ((size_t)kl * C.NT + n) * kKin;                    // (not aliased in footprint mode)
@@ -329,8 +337,8 @@ __device__ __forceinline__ bool collision_budget(const Plan& P, const Batch& B, 
   for (int n = 0; n < keep; ++n) {
     const double* h = C.hot + ((size_t)kl * C.NT + n) * kHot;
     const double* r = C.kin + ((size_t)kl * C.NT + n) * kKin;
-    const double d = lat_p0(lat, C.tt, n);
-    const double x = h[0] - h[3] * d, y = h[1] + h[2] * d;
+    const double d = lat_fast0(lat, C.tt[kTT * (n > lat.hold ? lat.hold : n)]);
+    const double x = fma(-h[3], d, h[0]), y = fma(h[2], d, h[1]);
     double hx = 0.0, hy = 0.0;
     if (n_circ > 0) {
       const double d_p = lat_p1(lat, C.tt, n) * r[5];
@@ -367,7 +375,7 @@ __device__ __forceinline__ bool collision_budget(const Plan& P, const Batch& B, 
 //            copies (cp.async.bulk + mbarrier), static obstacles first, then the time planes
 //   phase 3: stop-distance filter, block arg-min by (cost, index), category histogram
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSweepThreads, 4)
+__global__ void __launch_bounds__(kSweepThreads, 5)
 fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   extern __shared__ double sm[];
   const int NT = P.n_t_max;
@@ -603,8 +611,8 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
               continue;
             }
             const double* h = hot + ((size_t)kl * NT + n) * kHot;
-            const double d = lat_p0(lat, tt, n);
-            const double x = h[0] - h[3] * d, y = h[1] + h[2] * d;
+            const double d = lat_fast0(lat, tt[kTT * (n > lat.hold ? lat.hold : n)]);
+            const double x = fma(-h[3], d, h[0]), y = fma(h[2], d, h[1]);
             double hx = 0.0, hy = 0.0;
             if (n_circ > 0) {                                                // fp.py:1158-1167
               const double* r = kin + ((size_t)kl * NT + n) * kKin;
