@@ -59,7 +59,8 @@ struct fot_handle {
   int device = 0;
   Plan plan{};
   void* tables_dev = nullptr;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_copy[8] = {}, ev_done[8] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   static constexpr int kRing = 256;
@@ -67,8 +68,8 @@ struct fot_handle {
   long long n_launch = 0;
   int smem_optin = 0;
   Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx;   // device scratch
-  Buf stage_h, stage_d, out_h, out_d, dyn_d, stat_d;   // host-API staging
-  fot_handle() { stage_h.host = true; out_h.host = true; }
+  Buf stage_h, stage_d, out_d, dyn_d, stat_d;   // host-API staging
+  fot_handle() { stage_h.host = true; }
 };
 
 extern "C" int fot_abi_version(void) { return FOT_ABI_VERSION; }
@@ -127,6 +128,10 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   P.n_steps = I; P.n_steps_b = I + nT;
 
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev_copy) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto& ev : h->ev_done) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   h->ring.resize((size_t)fot_handle::kRing * 4);
@@ -142,13 +147,17 @@ extern "C" int fot_destroy(fot_handle_t* h) {
   if (!h) return FOT_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->stage_h, &h->stage_d, &h->out_h, &h->out_d,
+  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->stage_h, &h->stage_d, &h->out_d,
                  &h->dyn_d, &h->stat_d})
     b->release();
   if (h->tables_dev) cudaFree(h->tables_dev);
   for (auto ev : h->ring) if (ev) cudaEventDestroy(ev);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto ev : h->ev_copy) if (ev) cudaEventDestroy(ev);
+  for (auto ev : h->ev_done) if (ev) cudaEventDestroy(ev);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return FOT_OK;
@@ -281,18 +290,22 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
 
   cudaEvent_t* ring = h->ring.data() + (size_t)(h->n_launch % fot_handle::kRing) * 4;
   CK(cudaEventRecord(h->ev0, st));
-  CK(cudaMemsetAsync(r->stats, 0, (size_t)b->n_q * FOT_N_STATS * sizeof(int32_t), st));
-  if (r->cand_cat) CK(cudaMemsetAsync(r->cand_cat, FOT_CAT_DROP + 1, (size_t)b->n_q * r->cand_stride, st));
+  {
+    const size_t n_cat = r->cand_cat ? (size_t)b->n_q * r->cand_stride : 0;
+    const size_t work = std::max<size_t>((size_t)b->n_q * FOT_N_STATS, n_cat);
+    const int blocks = (int)std::min<size_t>(1024, (work + 255) / 256);
+    fot_init_kernel<<<blocks, 256, 0, st>>>(r->stats, b->n_q * FOT_N_STATS, has_dyn ? (double*)h->obs_max2.p : nullptr,
+                                            has_dyn ? b->n_q : 0, b->n_static > 0 ? (double*)h->stat_max2.p : nullptr,
+                                            b->n_static > 0 ? nq_s : 0, r->cand_cat, n_cat);
+  }
   CK(cudaEventRecord(ring[0], st));
   if (has_dyn) {
-    CK(cudaMemsetAsync(h->obs_max2.p, 0, (size_t)b->n_q * sizeof(double), st));
     const long long warps = (long long)b->n_q * SP;
     const int blocks = (int)((warps * 32 + 255) / 256);
     fot_obstacle_prepass<<<blocks, 256, 0, st>>>((const double2*)b->dyn, (double*)h->obs_tm.p,
                                                  (double*)h->obs_max2.p, b->n_q, SP, b->T_obs);
   }
   if (b->n_static > 0) {
-    CK(cudaMemsetAsync(h->stat_max2.p, 0, (size_t)nq_s * sizeof(double), st));
     const int total = nq_s * b->n_static;
     fot_static_prepass<<<(total + 255) / 256, 256, 0, st>>>((const double2*)b->static_obs, (double*)h->stat_tm.p,
                                                             (double*)h->stat_max2.p, nq_s, b->n_static);
@@ -320,6 +333,11 @@ extern "C" int fot_plan_batch_device(fot_handle_t* h, const fot_batch_t* b, cons
   return FOT_OK;
 }
 
+// Host-pointer entry point.  Small per-query arrays go through one pinned blob; the obstacle tensor
+// is copied straight from the caller's memory (pinned memory makes that a true async DMA).  Large
+// batches are cut into chunks of queries: chunk c+1's obstacle upload runs on the copy stream while
+// chunk c's kernels run on the compute stream, and each chunk's winners go back as soon as its
+// kernels finish, directly into the caller's result arrays.
 extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r) {
   int rc = check_batch(h, b, r);
   if (rc != FOT_OK) return rc;
@@ -340,26 +358,20 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   memcpy(sh + o_sd, b->stop_dist, (size_t)nq * 8);
   memcpy(sh + o_vg, b->v_grid, (size_t)nq * b->n_v_max * 8);
   memcpy(sh + o_nv, b->n_v, (size_t)nq * 4);
-  CK(cudaMemcpyAsync(h->stage_d.p, sh, off, cudaMemcpyHostToDevice, st));
-  // ---- obstacle arrays straight from the caller's memory (pinned or pageable) ------------
-  fot_batch_t db = *b;
+  // The compute stream carries kernels and event records only: every copy runs on the copy / d2h
+  // streams.  (A copy on the compute stream makes the driver service that stream's later timed event
+  // records on the copy engine, where they queue behind the uploads and serialise the pipeline.)
+  CK(cudaMemcpyAsync(h->stage_d.p, sh, off, cudaMemcpyHostToDevice, h->copy_stream));
   char* sd = (char*)h->stage_d.p;
-  db.frenet = (const double*)(sd + o_fr); db.target_speed = (const double*)(sd + o_tg);
-  db.limits = (const double*)(sd + o_lm); db.stop_dist = (const double*)(sd + o_sd);
-  db.v_grid = (const double*)(sd + o_vg); db.n_v = (const int32_t*)(sd + o_nv);
-  if (b->dyn_mode != FOT_DYN_NONE) {
-    const size_t bytes = (size_t)nq * b->S * b->P * b->T_obs * 16;
-    CK(h->dyn_d.reserve(bytes));
-    CK(cudaMemcpyAsync(h->dyn_d.p, b->dyn, bytes, cudaMemcpyHostToDevice, st));
-    db.dyn = (const double*)h->dyn_d.p;
-  }
+  const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
+  const size_t dyn_q_bytes = has_dyn ? (size_t)b->S * b->P * b->T_obs * 16 : 0;
+  if (has_dyn) CK(h->dyn_d.reserve((size_t)nq * dyn_q_bytes));
   if (b->n_static > 0) {
     const size_t bytes = (size_t)(b->static_per_query ? nq : 1) * b->n_static * 16;
     CK(h->stat_d.reserve(bytes));
-    CK(cudaMemcpyAsync(h->stat_d.p, b->static_obs, bytes, cudaMemcpyHostToDevice, st));
-    db.static_obs = (const double*)h->stat_d.p;
+    CK(cudaMemcpyAsync(h->stat_d.p, b->static_obs, bytes, cudaMemcpyHostToDevice, h->copy_stream));
   }
-  // ---- results: one device blob, one D2H ----------------------------------------------
+  // ---- device result blob ---------------------------------------------------------------
   size_t ro = 0;
   auto rtake = [&](size_t bytes) { size_t o = ro; ro = align_up(ro + bytes); return o; };
   const size_t r_bi = rtake((size_t)nq * 4), r_bc = rtake((size_t)nq * 8), r_st = rtake((size_t)nq * FOT_N_STATS * 4),
@@ -367,25 +379,88 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   const size_t r_cc = r->cand_cat ? rtake((size_t)nq * r->cand_stride) : 0;
   const size_t r_cs = r->cand_cost ? rtake((size_t)nq * r->cand_stride * 8) : 0;
   CK(h->out_d.reserve(ro));
-  CK(h->out_h.reserve(ro));
   char* od = (char*)h->out_d.p;
-  fot_result_t dr = *r;
-  dr.best_idx = (int32_t*)(od + r_bi); dr.best_cost = (double*)(od + r_bc); dr.stats = (int32_t*)(od + r_st);
-  dr.winner_len = (int32_t*)(od + r_wl); dr.winner = (double*)(od + r_w);
-  dr.cand_cat = r->cand_cat ? (uint8_t*)(od + r_cc) : nullptr;
-  dr.cand_cost = r->cand_cost ? (double*)(od + r_cs) : nullptr;
-  rc = launch_all(h, &db, &dr, st);
-  if (rc != FOT_OK) return rc;
-  CK(cudaMemcpyAsync(h->out_h.p, od, ro, cudaMemcpyDeviceToHost, st));
+
+  // chunking: only worth it when the obstacle upload is large
+  int n_chunks = 1;
+  if ((size_t)nq * dyn_q_bytes > ((size_t)8 << 20)) n_chunks = std::min(8, std::max(1, nq / 1024));
+  if (const char* env = getenv("FOT_HOST_CHUNKS")) n_chunks = std::max(1, std::min(8, atoi(env)));
+  const int per = (nq + n_chunks - 1) / n_chunks;
+  static const bool dbg = getenv("FOT_DEBUG_TIMING") != nullptr;
+  cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr, d3 = nullptr, d4 = nullptr;
+  if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventCreate(&d2); cudaEventCreate(&d3); cudaEventCreate(&d4);
+             cudaEventRecord(d0, st); cudaEventRecord(d4, h->copy_stream); }
+  // every obstacle upload is queued first (they depend on nothing), one event per chunk
+  if (has_dyn)
+    for (int c = 0; c < n_chunks; ++c) {
+      const int q0 = c * per, cq = std::min(per, nq - q0);
+      if (cq <= 0) break;
+      char* dst = (char*)h->dyn_d.p + (size_t)q0 * dyn_q_bytes;
+      const char* src = (const char*)b->dyn + (size_t)q0 * dyn_q_bytes;
+      CK(cudaMemcpyAsync(dst, src, (size_t)cq * dyn_q_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaEventRecord(h->ev_copy[c], h->copy_stream));
+    }
+  else
+    CK(cudaEventRecord(h->ev_copy[0], h->copy_stream));   // small arrays / static obstacles only
+  if (dbg) {
+    cudaEventRecord(d1, h->copy_stream);
+    cudaPointerAttributes pa{};
+    cudaError_t pe = cudaPointerGetAttributes(&pa, b->dyn);
+    fprintf(stderr, "[fot] dyn pointer attr: err=%d type=%d (0 unregistered, 1 host, 2 device, 3 managed)\n", (int)pe, (int)pa.type);
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const int q0 = c * per, cq = std::min(per, nq - q0);
+    if (cq <= 0) break;
+    if (has_dyn || c == 0) CK(cudaStreamWaitEvent(st, h->ev_copy[c], 0));
+    if (dbg && c == 0) cudaEventRecord(d2, st);
+    fot_batch_t db = *b;
+    db.n_q = cq;
+    db.frenet = (const double*)(sd + o_fr) + (size_t)q0 * 6;
+    db.target_speed = (const double*)(sd + o_tg) + q0;
+    db.limits = (const double*)(sd + o_lm) + (size_t)q0 * 4;
+    db.stop_dist = (const double*)(sd + o_sd) + q0;
+    db.v_grid = (const double*)(sd + o_vg) + (size_t)q0 * b->n_v_max;
+    db.n_v = (const int32_t*)(sd + o_nv) + q0;
+    if (has_dyn) db.dyn = (const double*)((char*)h->dyn_d.p + (size_t)q0 * dyn_q_bytes);
+    if (b->n_static > 0)
+      db.static_obs = (const double*)h->stat_d.p + (b->static_per_query ? (size_t)q0 * b->n_static * 2 : 0);
+    fot_result_t dr = *r;
+    dr.best_idx = (int32_t*)(od + r_bi) + q0;
+    dr.best_cost = (double*)(od + r_bc) + q0;
+    dr.stats = (int32_t*)(od + r_st) + (size_t)q0 * FOT_N_STATS;
+    dr.winner_len = (int32_t*)(od + r_wl) + q0;
+    dr.winner = (double*)(od + r_w) + (size_t)q0 * FOT_N_SERIES * NT;
+    dr.cand_cat = r->cand_cat ? (uint8_t*)(od + r_cc) + (size_t)q0 * r->cand_stride : nullptr;
+    dr.cand_cost = r->cand_cost ? (double*)(od + r_cs) + (size_t)q0 * r->cand_stride : nullptr;
+    rc = launch_all(h, &db, &dr, st);
+    if (rc != FOT_OK) return rc;
+    // winners of this chunk straight into the caller's arrays, on their own stream so the next
+    // chunk's kernels never queue behind a copy engine that is busy with the uploads
+    cudaStream_t ds = h->d2h_stream;
+    CK(cudaEventRecord(h->ev_done[c], st));
+    CK(cudaStreamWaitEvent(ds, h->ev_done[c], 0));
+    CK(cudaMemcpyAsync(r->best_idx + q0, dr.best_idx, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
+    CK(cudaMemcpyAsync(r->best_cost + q0, dr.best_cost, (size_t)cq * 8, cudaMemcpyDeviceToHost, ds));
+    CK(cudaMemcpyAsync(r->stats + (size_t)q0 * FOT_N_STATS, dr.stats, (size_t)cq * FOT_N_STATS * 4, cudaMemcpyDeviceToHost, ds));
+    CK(cudaMemcpyAsync(r->winner_len + q0, dr.winner_len, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
+    CK(cudaMemcpyAsync(r->winner + (size_t)q0 * FOT_N_SERIES * NT, dr.winner, (size_t)cq * FOT_N_SERIES * NT * 8,
+                       cudaMemcpyDeviceToHost, ds));
+    if (r->cand_cat)
+      CK(cudaMemcpyAsync(r->cand_cat + (size_t)q0 * r->cand_stride, dr.cand_cat, (size_t)cq * r->cand_stride,
+                         cudaMemcpyDeviceToHost, ds));
+    if (r->cand_cost)
+      CK(cudaMemcpyAsync(r->cand_cost + (size_t)q0 * r->cand_stride, dr.cand_cost, (size_t)cq * r->cand_stride * 8,
+                         cudaMemcpyDeviceToHost, ds));
+  }
+  if (dbg) cudaEventRecord(d3, st);
   CK(cudaStreamSynchronize(st));
-  const char* oh = (const char*)h->out_h.p;
-  memcpy(r->best_idx, oh + r_bi, (size_t)nq * 4);
-  memcpy(r->best_cost, oh + r_bc, (size_t)nq * 8);
-  memcpy(r->stats, oh + r_st, (size_t)nq * FOT_N_STATS * 4);
-  memcpy(r->winner_len, oh + r_wl, (size_t)nq * 4);
-  memcpy(r->winner, oh + r_w, (size_t)nq * FOT_N_SERIES * NT * 8);
-  if (r->cand_cat) memcpy(r->cand_cat, oh + r_cc, (size_t)nq * r->cand_stride);
-  if (r->cand_cost) memcpy(r->cand_cost, oh + r_cs, (size_t)nq * r->cand_stride * 8);
+  CK(cudaStreamSynchronize(h->d2h_stream));
+  if (dbg) {
+    float a = 0, bb = 0, cc = 0, dd = 0;
+    cudaEventElapsedTime(&a, d0, d1); cudaEventElapsedTime(&bb, d0, d2); cudaEventElapsedTime(&cc, d0, d3); cudaEventElapsedTime(&dd, d0, d4);
+    fprintf(stderr, "[fot] chunks=%d copy-stream start %.3f ms, copies done %.3f ms, first kernel may start %.3f ms, kernels done %.3f ms\n", n_chunks, dd, a, bb, cc);
+    cudaEventDestroy(d0); cudaEventDestroy(d1); cudaEventDestroy(d2); cudaEventDestroy(d3); cudaEventDestroy(d4);
+  }
   return FOT_OK;
 }
 

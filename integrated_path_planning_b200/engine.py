@@ -163,6 +163,7 @@ class SweepEngine:
         self.n_circles = int(cfg.n_circles)
         self.T, self.d_grid, self.Tb = self._keep["T"], self._keep["d_grid"], self._keep["Tb"]
         self.n_steps, self.n_steps_b, self.n_total = self._keep["n_steps"], self._keep["n_steps_b"], n_total
+        self._pinned = {}
         self._h = C.c_void_p()
         _lib.check(self.lib.fot_create(C.byref(cfg), C.byref(tb), self.device, C.byref(self._h)), "fot_create")
         self.n_t_max = self.lib.fot_n_t_max(self._h)
@@ -218,22 +219,37 @@ class SweepEngine:
             b.S, b.P, b.T_obs = dyn.shape[1], dyn.shape[2], dyn.shape[3]
             b.dyn, b.dyn_mode = _ptr(dyn), dyn_mode
             keep.append(dyn)
-        res = SweepResult(
-            best_idx=np.empty(n_q, np.int32), best_cost=np.empty(n_q, np.float64),
-            stats=np.empty((n_q, _lib.FOT_N_STATS), np.int32), winner_len=np.empty(n_q, np.int32),
-            winner=np.empty((n_q, _lib.FOT_N_SERIES, self.n_t_max), np.float64))
+        res = self._result_buffers(n_q, want_candidates, int(b.n_v_max))
         r = _lib.FotResult()
         r.best_idx, r.best_cost, r.stats = _ptr(res.best_idx), _ptr(res.best_cost), _ptr(res.stats)
         r.winner_len, r.winner = _ptr(res.winner_len), _ptr(res.winner)
         if want_candidates:
-            stride = self.lib.fot_candidate_count(self._h, int(b.n_v_max), 1)
-            res.cand_cat = np.empty((n_q, stride), np.uint8)
-            res.cand_cost = np.empty((n_q, stride), np.float64)
-            r.cand_cat, r.cand_cost, r.cand_stride = _ptr(res.cand_cat), _ptr(res.cand_cost), stride
+            r.cand_cat, r.cand_cost, r.cand_stride = _ptr(res.cand_cat), _ptr(res.cand_cost), res.cand_cat.shape[1]
         _lib.check(self.lib.fot_plan_batch_host(self._h, C.byref(b), C.byref(r)), "fot_plan_batch_host")
         res.n_cand = self.candidate_counts(frenet, n_v)
         res.kernel_ms = float(self.lib.fot_last_kernel_ms(self._h))
         return res
+
+    def _result_buffers(self, n_q: int, want_candidates: bool, n_v_max: int) -> SweepResult:
+        """Result arrays in pinned host memory (torch is only the allocator), cached per batch size so
+        the device->host copies are true async DMAs.  The arrays of a returned SweepResult stay valid
+        until the next call on this engine with the same batch size."""
+        import torch
+        stride = self.lib.fot_candidate_count(self._h, n_v_max, 1) if want_candidates else 0
+        key = (n_q, stride)
+        cached = self._pinned.get(key)
+        if cached is None:
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+            cached = dict(best_idx=pin((n_q,), torch.int32), best_cost=pin((n_q,), torch.float64),
+                          stats=pin((n_q, _lib.FOT_N_STATS), torch.int32), winner_len=pin((n_q,), torch.int32),
+                          winner=pin((n_q, _lib.FOT_N_SERIES, self.n_t_max), torch.float64))
+            if want_candidates:
+                cached["cand_cat"] = pin((n_q, stride), torch.uint8)
+                cached["cand_cost"] = pin((n_q, stride), torch.float64)
+            if len(self._pinned) > 8:
+                self._pinned.clear()
+            self._pinned[key] = cached
+        return SweepResult(**cached)
 
     def run_device(self, batch: "_lib.FotBatch", result: "_lib.FotResult", stream=None) -> None:
         """fot_plan_batch_device with caller-owned device pointers (torch tensors as buffers)."""
