@@ -94,3 +94,61 @@ def bit_exact_report(ref: O.OracleResult, pl, path) -> dict:
         for name in SERIES:
             out[name] = float(np.mean(np.asarray(getattr(path, name), dtype=float) == ref.arrays[name]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures (made by tests/golden/make_golden.py from the unmodified reference)
+# ---------------------------------------------------------------------------------------------
+import os as _os
+
+GOLDEN_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+GOLDEN_STAT_KEYS = ("ok", "max_speed_error", "max_accel_error", "max_curvature_error", "max_lat_accel_error",
+                    "road_bound_error", "collision_error", "stop_distance_error")
+
+
+def load_golden(name):
+    return np.load(_os.path.join(GOLDEN_DIR, name))
+
+
+def golden_case(store, prefix):
+    """One recorded reference plan() result as a dict."""
+    out = {k[len(prefix) + 1:]: store[k] for k in store.files if k.startswith(prefix + "/")}
+    out["stats_dict"] = {k: int(v) for k, v in zip(GOLDEN_STAT_KEYS, out["stats"]) if v >= 0}
+    return out
+
+
+def assert_oracle_matches_golden(name, res: O.OracleResult, g, rtol=1e-12):
+    """Oracle vs the recorded reference: identical decisions; values to 1e-12 (bit-identical on the
+    machine that made the fixtures; a different host libm/BLAS may move the last bits)."""
+    assert np.array_equal(res.categories.astype(np.uint8), g["cats"]), name
+    np.testing.assert_allclose(res.costs, g["costs"], rtol=rtol, atol=0, err_msg=name)
+    assert res.best_index == int(g["best"]), (name, res.best_index, int(g["best"]))
+    assert res.stats == g["stats_dict"], (name, res.stats, g["stats_dict"])
+    np.testing.assert_allclose(np.array(res.frenet_state), g["fs"], rtol=rtol, atol=1e-15, err_msg=name)
+    if res.best_index >= 0:
+        np.testing.assert_allclose(res.cost, float(g["cost"]), rtol=rtol)
+        for s in SERIES:
+            if "w_" + s in g:
+                np.testing.assert_allclose(res.arrays[s], g["w_" + s], rtol=1e-10, atol=1e-10, err_msg=f"{name} {s}")
+
+
+def assert_cuda_matches_golden(name, pl, path, g):
+    """CUDA planner vs the recorded reference: the north-star bar (index identical, 1e-9 on values)."""
+    res = pl.last_result
+    n_c = len(g["cats"])
+    assert int(res.n_cand[0]) == n_c, (name, int(res.n_cand[0]), n_c)
+    cats = res.cand_cat[0, :n_c]
+    mism = np.nonzero(cats != g["cats"])[0]
+    assert mism.size == 0, (name, "category mismatch", mism[:10], cats[mism[:10]], g["cats"][mism[:10]])
+    np.testing.assert_allclose(res.cand_cost[0, :n_c], g["costs"], rtol=RTOL, atol=0, err_msg=name)
+    assert pl.last_check_stats == g["stats_dict"], (name, pl.last_check_stats, g["stats_dict"])
+    assert int(res.best_idx[0]) == int(g["best"]), (name, int(res.best_idx[0]), int(g["best"]))
+    if int(g["best"]) < 0:
+        assert path is None
+        return
+    np.testing.assert_allclose(float(path.cost), float(g["cost"]), rtol=RTOL)
+    for s in SERIES:
+        if "w_" + s in g:
+            got = np.asarray(getattr(path, s), dtype=float)
+            assert got.shape == g["w_" + s].shape, (name, s)
+            np.testing.assert_allclose(got, g["w_" + s], rtol=RTOL, atol=ATOL, err_msg=f"{name} {s}")
