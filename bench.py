@@ -264,8 +264,11 @@ def main():
     peak = C.c_double()
     _lib.check(eng.lib.fot_probe_fma_tflops(local_rank, 0, C.byref(peak)), "probe")
     achieved_tf = FLOP_PER_EVAL * evals_step / (sweep_ms * 1e-3) / 1e12
+    # DRAM traffic of one fot_sweep launch from the committed ncu --set full capture
+    # (profiles/r1/sweep_ncu_full_summary.txt: 142.2 MB read + 6.0 MB written for 4096 queries), per query
+    traffic = (142.210816e6 + 5.962752e6) / 4096 * Q
     roofline = {"bound": "fp64_pipe", "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak.value, "traffic": None,
+                "frac": achieved_tf / peak.value, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1)",
                 "kernel": "fot_sweep", "kernel_ms": sweep_ms,
                 "stage_ms": {"prepass": float(stage[:, 0].mean()), "sweep": sweep_ms, "winner": float(stage[:, 2].mean())},
                 "peak_source": "fot_probe_fma_tflops on this GPU (dependent-chain DFMA, 2 FLOP/FMA); "
