@@ -188,57 +188,61 @@ __device__ __forceinline__ KinResult kinematic_pass(const Plan& P, const BlockCt
   double x_prev = 0, y_prev = 0, s_prev = 0, d_prev = 0, q_prev = 1, dp_prev = 0;
   KinResult R;
   R.v_last = 0; R.s_last = 0; R.s_first = kin[2];
+  const int hold = lat.hold;
 
+  // Straight-line body: every quantity is computed for every sample and the updates are masked by
+  // `valid` (sample belongs to the kept prefix), so the loop has no control-flow merges except the
+  // rare low-speed regime.  NaN samples beyond the prefix only feed masked updates.
   for (int n = 0; n < N; ++n) {
     const double* h = hot + n * kHot;
     const double* r = kin + n * kKin;
     const double rk = r[0];
     double d, d1, d2;
-    lat_fast(lat, tt[kTT * (n > lat.hold ? lat.hold : n)], d, d1, d2);
-    if (n > lat.hold) { d1 = 0.0; d2 = 0.0; }                                // fp.py:487-499 brake padding
+    lat_fast(lat, tt[kTT * min(n, hold)], d, d1, d2);
+    const bool held = n > hold;                                              // fp.py:487-499 brake padding
+    d1 = held ? 0.0 : d1;
+    d2 = held ? 0.0 : d2;
     const double q1 = fma(-rk, d, 1.0);                                      // fp.py:826-827
     singular |= (q1 <= 0.05) & (fabs(q1) < INFINITY);
     const double x = fma(-h[3], d, h[0]);                                    // cc.py:131
-    if (first_nan < 0) {
-      if (x != x) {                                                          // fp.py:851-866
-        first_nan = n;
+    const double y = fma(h[2], d, h[1]);                                     // cc.py:132
+    first_nan = (first_nan < 0 && x != x) ? n : first_nan;                   // fp.py:851-866
+    const bool valid = first_nan < 0;
+    const double s = r[2], sd = r[3], sdd = r[4];
+    const KinPt c = kinematics_fast(rk, r[1], sd, sdd, r[5], r[6], d, d1, d2);
+    nonfinite |= valid & !(fabs(c.v) + fabs(c.a) + fabs(c.kappa) < INFINITY);   // fp.py:944-946
+    const bool chk = valid & (n >= 1);                                       // limits skip index 0 (fp.py:964-983)
+    const double ex = x - x_prev, ey = y - y_prev;
+    const double step2 = fma(ex, ex, ey * ey);                               // fp.py:954 (squared)
+    max_step2 = (chk & (step2 > max_step2)) ? step2 : max_step2;
+    const bool fast = c.v > 0.5;                                             // fp.py:1019
+    unsigned f = 0;
+    f |= (c.v > vmax) ? F_SPEED : 0u;                                        // fp.py:964
+    f |= (fabs(c.a) > amax) ? F_ACCEL : 0u;                                  // fp.py:966
+    f |= (fast & (fabs(c.kappa) > kmax)) ? F_CURV : 0u;                      // fp.py:1020
+    f |= (c.v * c.v * fabs(c.kappa) > latmax) ? F_LAT : 0u;                  // fp.py:975
+    f |= (fabs(d) > road_thr) ? F_ROAD : 0u;                                 // fp.py:982
+    flags |= chk ? f : 0u;
+    if (chk & !fast & !(flags & F_CURV)) {                                   // fp.py:1022-1032 (rare)
+      if (fabs(d - d_prev) > fmax(1.5 * fabs(s - s_prev), 0.02)) {
+        flags |= F_CURV;
       } else {
-        const double y = fma(h[2], d, h[1]);                                 // cc.py:132
-        const double s = r[2], sd = r[3], sdd = r[4];
-        const KinPt c = kinematics_fast(rk, r[1], sd, sdd, r[5], r[6], d, d1, d2);
-        nonfinite |= !(fabs(c.v) + fabs(c.a) + fabs(c.kappa) < INFINITY);    // fp.py:944-946
-        if (n >= 1) {
-          const double ex = x - x_prev, ey = y - y_prev;
-          const double step2 = fma(ex, ex, ey * ey);                         // fp.py:954 (squared)
-          if (step2 > max_step2) max_step2 = step2;
-          if (c.v > vmax) flags |= F_SPEED;                                  // fp.py:964
-          if (fabs(c.a) > amax) flags |= F_ACCEL;                            // fp.py:966
-          if (c.v > 0.5) {                                                   // fp.py:1019-1021
-            if (fabs(c.kappa) > kmax) flags |= F_CURV;
-          } else if (!(flags & F_CURV)) {                                    // fp.py:1022-1032
-            if (fabs(d - d_prev) > fmax(1.5 * fabs(s - s_prev), 0.02)) {
-              flags |= F_CURV;
-            } else {
-              // |wrap(yaw_i - yaw_{i-1})| is the angle between the heading vectors u = R(rtheta)(q, d').
-              const double* hp = h - kHot;
-              const double ux = h[2] * c.q - h[3] * c.d_p, uy = h[3] * c.q + h[2] * c.d_p;
-              const double ux_prev = hp[2] * q_prev - hp[3] * dp_prev, uy_prev = hp[3] * q_prev + hp[2] * dp_prev;
-              const double cr = ux_prev * uy - uy_prev * ux, dt_ = ux_prev * ux + uy_prev * uy;
-              if (kmax * kmax * step2 <= 0.01) {
-                // threshold is the 0.1 rad floor: angle > 0.1  <=>  dot <= 0 or cross^2 > tan(0.1)^2 dot^2
-                if (dt_ <= 0.0 || cr * cr > kTan01Sq * dt_ * dt_) flags |= F_CURV;
-              } else if (fabs(atan2(cr, dt_)) > kmax * sqrt(step2)) {
-                flags |= F_CURV;
-              }
-            }
-          }
-          if (c.v * c.v * fabs(c.kappa) > latmax) flags |= F_LAT;           // fp.py:975
-          if (fabs(d) > road_thr) flags |= F_ROAD;                           // fp.py:982
+        // |wrap(yaw_i - yaw_{i-1})| is the angle between the heading vectors u = R(rtheta)(q, d').
+        const double* hp = h - kHot;
+        const double ux = h[2] * c.q - h[3] * c.d_p, uy = h[3] * c.q + h[2] * c.d_p;
+        const double ux_prev = hp[2] * q_prev - hp[3] * dp_prev, uy_prev = hp[3] * q_prev + hp[2] * dp_prev;
+        const double cr = ux_prev * uy - uy_prev * ux, dt_ = ux_prev * ux + uy_prev * uy;
+        if (kmax * kmax * step2 <= 0.01) {
+          // threshold is the 0.1 rad floor: angle > 0.1  <=>  dot <= 0 or cross^2 > tan(0.1)^2 dot^2
+          if (dt_ <= 0.0 || cr * cr > kTan01Sq * dt_ * dt_) flags |= F_CURV;
+        } else if (fabs(atan2(cr, dt_)) > kmax * sqrt(step2)) {
+          flags |= F_CURV;
         }
-        x_prev = x; y_prev = y; s_prev = s; d_prev = d; q_prev = c.q; dp_prev = c.d_p;
-        R.v_last = c.v; R.s_last = s;
       }
     }
+    x_prev = x; y_prev = y; s_prev = s; d_prev = d; q_prev = c.q; dp_prev = c.d_p;
+    R.v_last = valid ? c.v : R.v_last;
+    R.s_last = valid ? s : R.s_last;
   }
 
   R.keep = first_nan < 0 ? N : (first_nan >= 2 ? first_nan : 0);            // fp.py:866
