@@ -190,7 +190,7 @@ static int sweep_geometry(const fot_handle* h, const fot_batch_t* b, SweepGeom* 
   const bool footprint = h->plan.cfg.n_circles > 0;
   // layout (doubles): tt | hot | js,lonc (6 kv) | jp,dend (2 jp_cap) | kin | [phase-2 region] | ints
   auto layout = [&](int kv, int* phase2_off, int* ints_off) {
-    const size_t jp_cap = (size_t)std::max(nd, kv) + (std::max(nd, kv) & 1);
+    const size_t jp_cap = (size_t)kv * nd + (((size_t)kv * nd) & 1);
     const size_t head = (size_t)kTT * NT + (size_t)kHot * kv * NT + 6 * (size_t)kv + 2 * jp_cap;
     const size_t kin_sz = (size_t)kKin * kv * NT;
     const size_t p2 = (size_t)n_stages * 3 * tile_cap + (size_t)kSweepThreads * kRec;
@@ -199,33 +199,40 @@ static int sweep_geometry(const fot_handle* h, const fot_batch_t* b, SweepGeom* 
     const size_t ints = std::max(head + kin_sz, p2_off + p2);
     if (phase2_off) *phase2_off = (int)p2_off;
     if (ints_off) *ints_off = (int)ints;
-    return ints * sizeof(double) + ((size_t)2 * kv + NT + kSweepThreads + (size_t)kv * kGmax) * sizeof(int32_t) +
+    return ints * sizeof(double) + ((size_t)4 * kv + NT + kSweepThreads + (size_t)kv * kGmax) * sizeof(int32_t) +
            (size_t)kv * kGmax * kCullCap * sizeof(unsigned short) + 16;
   };
   auto bytes = [&](int kv) { return layout(kv, nullptr, nullptr); };
-  int ch = std::min(kSweepThreads, n_v_max * nd);
+  const int nT = h->plan.cfg.n_T;
+  const long long grid_total = (long long)nT * n_v_max * nd;
+  // whole pairs per block when a pair fits (no pair straddles two blocks, so its reference samples and
+  // cull lists are built once); otherwise plain 128-candidate chunks
+  int ch = nd <= kSweepThreads ? (kSweepThreads / nd) * nd : kSweepThreads;
+  ch = (int)std::min<long long>(ch, grid_total);
   ch = std::max(ch, 1);
-  int kv;
-  for (;;) {
-    kv = std::min(n_v_max, (ch - 1) / nd + 2);
-    if (bytes(kv) <= std::min<size_t>(budget, 72 * 1024) || ch <= nd || ch == 1) break;   // keep >= 3 blocks/SM when possible
-    ch = std::max(nd, ch / 2);
+  auto pairs_of = [&](int c) {
+    const int p = (c % nd == 0) ? c / nd : (c - 1) / nd + 2;
+    return (int)std::min<long long>((long long)nT * n_v_max, p);
+  };
+  int kv = std::max(pairs_of(ch), std::min(nB, 8));
+  while (bytes(kv) > std::min<size_t>(budget, 72 * 1024) && ch > nd && ch > 1) {   // keep >= 3 blocks/SM when possible
+    ch = nd <= ch / 2 ? (ch / 2 / nd) * nd : std::max(nd, ch / 2);
+    kv = std::max(pairs_of(ch), std::min(nB, 8));
   }
-  while (bytes(kv) > budget && ch > 1) { ch = std::max(1, ch / 2); kv = std::min(n_v_max, (ch - 1) / nd + 2); }
+  while (bytes(kv) > budget && ch > 1) { ch = std::max(1, ch / 2); kv = std::max(pairs_of(ch), 1); }
   if (bytes(kv) > budget) return fail(FOT_ERR_TOO_LARGE, "time grid too long for shared memory");
   g->ch_eff = ch;
   g->kv_cap = std::max(kv, 1);
-  g->jp_cap = std::max(nd, g->kv_cap);
-  g->jp_cap += g->jp_cap & 1;                       // keeps the following tables 16-byte aligned
+  g->jp_cap = g->kv_cap * nd + ((g->kv_cap * nd) & 1);   // even: keeps the following tables 16-byte aligned
   int p2 = 0, io = 0;
   layout(g->kv_cap, &p2, &io);
   g->phase2_off = p2;
   g->ints_off = io;
   g->tile_cap = tile_cap;
   g->n_stages = n_stages;
-  g->chunks_per_T = (n_v_max * nd + ch - 1) / ch;
+  g->grid_blocks = (int)((grid_total + ch - 1) / ch);
   g->brake_blocks = nB > 0 ? (nB + g->kv_cap - 1) / g->kv_cap : 0;
-  g->blocks_per_query = h->plan.cfg.n_T * g->chunks_per_T + g->brake_blocks;
+  g->blocks_per_query = g->grid_blocks + g->brake_blocks;
   *smem_bytes = bytes(g->kv_cap);
   return FOT_OK;
 }

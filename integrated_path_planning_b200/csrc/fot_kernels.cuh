@@ -23,8 +23,8 @@ constexpr int kRec = 8;    // doubles per compacted collision record: a0..a5, {h
 enum : unsigned { F_SPEED = 1u, F_ACCEL = 2u, F_CURV = 4u, F_LAT = 8u, F_ROAD = 16u };
 
 struct SweepGeom {
-  int32_t blocks_per_query;  // n_T * chunks_per_T + brake_blocks
-  int32_t chunks_per_T;
+  int32_t blocks_per_query;  // grid_blocks + brake_blocks
+  int32_t grid_blocks;       // ceil(n_T * n_v_max * n_d / ch_eff): the (T, v, d) grid flattened in generation order
   int32_t ch_eff;            // candidates per grid block (<= kSweepThreads)
   int32_t kv_cap;            // terminal speeds (or brake horizons) whose reference samples fit one block
   int32_t brake_blocks;
@@ -408,10 +408,13 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   int* holdk = reinterpret_cast<int*>(sm + G.ints_off);    // [kv_cap]
   int* kobs = holdk + G.kv_cap;                            // [NT]
   int* hitf = kobs + NT;                                   // [kSweepThreads] collision verdict per owner thread
-  int* pair_live = hitf + kSweepThreads;                   // [kv_cap] any clean candidate with this terminal speed?
-  int* ccnt = pair_live + G.kv_cap;                        // [kv_cap*kGmax] relevant obstacles per (speed, step)
+  int* pair_live = hitf + kSweepThreads;                   // [kv_cap] any clean candidate with this profile?
+  int* pairN = pair_live + G.kv_cap;                       // [kv_cap] samples of the pair's profile
+  int* pairT = pairN + G.kv_cap;                           // [kv_cap] horizon index (or brake horizon index)
+  int* ccnt = pairT + G.kv_cap;                        // [kv_cap*kGmax] relevant obstacles per (speed, step)
   unsigned short* clist = reinterpret_cast<unsigned short*>(ccnt + G.kv_cap * kGmax);   // [kv_cap*kGmax][kCullCap]
   __shared__ int s_wcnt[kSweepThreads / 32];
+  __shared__ int s_Nmax;
   __shared__ int s_stats[FOT_N_STATS];
   __shared__ double s_cost[kSweepThreads / 32];
   __shared__ int s_idx[kSweepThreads / 32];
@@ -423,20 +426,22 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   const double* fs = B.frenet + 6 * (size_t)q;
   const int n_v = B.n_v[q];
   const int n_d = P.cfg.n_d;
-  const int n_grid_blocks = P.cfg.n_T * G.chunks_per_T;
+  const int n_grid_blocks = G.grid_blocks;
   const bool brake_blk = b >= n_grid_blocks;
   const size_t part = (size_t)q * G.blocks_per_query + b;
 
-  int jT = 0, m0 = 0, k_lo = 0, n_k = 0, n_cand = 0, N = 0;
+  // A "pair" is one longitudinal profile: (horizon T_j, terminal speed v_k) of the grid, or one brake
+  // horizon.  The grid's candidates are flattened in generation order m = (j_T*n_v + k_v)*n_d + i_d
+  // and cut into blocks of ch_eff, so every thread of every block but the last owns a candidate; a
+  // block therefore spans a few pairs, possibly of two horizons (different sample counts).
+  int m0 = 0, k_lo = 0, n_k = 0, n_cand = 0;
   if (!brake_blk) {
-    jT = b / G.chunks_per_T;
-    m0 = (b % G.chunks_per_T) * G.ch_eff;
-    const int total = n_v * n_d;
+    m0 = b * G.ch_eff;
+    const int total = P.cfg.n_T * n_v * n_d;
     if (m0 < total) {
       n_cand = min(G.ch_eff, total - m0);
       k_lo = m0 / n_d;
       n_k = (m0 + n_cand - 1) / n_d - k_lo + 1;
-      N = P.n_steps[jT] + 1;
     }
   } else {
     const int b0 = (b - n_grid_blocks) * G.kv_cap;
@@ -444,7 +449,6 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
       k_lo = b0;
       n_k = min(G.kv_cap, P.cfg.n_B - b0);
       n_cand = n_k;
-      N = P.cfg.n_total;
     }
   }
   if (n_cand == 0) {                                   // uniform per block
@@ -464,31 +468,53 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     const int kmax_i = B.T_obs > 0 ? B.T_obs - 1 : 0;
     kobs[n] = kf < 0.0 ? 0 : (kf > (double)kmax_i ? kmax_i : (int)kf);
   }
+  if (tid == 0) s_Nmax = 0;
   __syncthreads();
+  const int jT_lo = brake_blk ? 0 : k_lo / n_v;
   if (tid < n_k) {
     Lon L;
-    if (!brake_blk)
-      L = lon_solve(fs, B.v_grid[(size_t)q * B.n_v_max + k_lo + tid], P.T[jT], P.inv4 + 4 * jT, n_v == 1, N - 1);
-    else
+    int Nk;
+    if (!brake_blk) {
+      const int p = k_lo + tid, jT = p / n_v, kv = p - jT * n_v;
+      Nk = P.n_steps[jT] + 1;
+      L = lon_solve(fs, B.v_grid[(size_t)q * B.n_v_max + kv], P.T[jT], P.inv4 + 4 * jT, n_v == 1, Nk - 1);
+      pairT[tid] = jT;
+    } else {
+      Nk = P.cfg.n_total;
       L = lon_solve(fs, 0.0, P.Tb[k_lo + tid], P.inv4b + 4 * (k_lo + tid), true, P.n_steps_b[k_lo + tid]);
+      pairT[tid] = k_lo + tid;
+    }
+    pairN[tid] = Nk;
+    atomicMax(&s_Nmax, Nk);
     lonc[tid] = L.a0; lonc[G.kv_cap + tid] = L.a1; lonc[2 * G.kv_cap + tid] = L.a2;
     lonc[3 * G.kv_cap + tid] = L.a3; lonc[4 * G.kv_cap + tid] = L.a4;
     holdk[tid] = L.hold;
     auto jerk2 = [&](int n) { const double j = lon_p3(L, tt, n); return j * j; };
-    js[tid] = np_pairwise_sum(jerk2, 0, N);             // fp.py:722
+    js[tid] = np_pairwise_sum(jerk2, 0, Nk);            // fp.py:722
   }
-  // lateral jerk sum and terminal offset once per lateral profile of this block (fp.py:718-719)
-  for (int i = tid; i < (brake_blk ? n_k : n_d); i += kSweepThreads) {
-    const Lat L = brake_blk
-        ? lat_solve(fs, fs[3], P.Tb[k_lo + i], P.inv5b + 9 * (k_lo + i), true, P.n_steps_b[k_lo + i])
-        : lat_solve(fs, P.d_grid[i], P.T[jT], P.inv5 + 9 * jT, n_d == 1, N - 1);
+  // lateral jerk sum and terminal offset once per lateral profile of this block (fp.py:718-719):
+  // slot (j_T - jT_lo) * n_d + i_d for the grid, the brake horizon's index for the ladder
+  const int n_Tl = brake_blk ? 0 : (k_lo + n_k - 1) / n_v - jT_lo + 1;
+  for (int i = tid; i < (brake_blk ? n_k : n_Tl * n_d); i += kSweepThreads) {
+    Lat L;
+    int Nl;
+    if (brake_blk) {
+      Nl = P.cfg.n_total;
+      L = lat_solve(fs, fs[3], P.Tb[k_lo + i], P.inv5b + 9 * (k_lo + i), true, P.n_steps_b[k_lo + i]);
+    } else {
+      const int jT = jT_lo + i / n_d, id = i % n_d;
+      Nl = P.n_steps[jT] + 1;
+      L = lat_solve(fs, P.d_grid[id], P.T[jT], P.inv5 + 9 * jT, n_d == 1, Nl - 1);
+    }
     auto jerk2 = [&](int n) { const double j = lat_p3(L, tt, n); return j * j; };
-    jp[i] = np_pairwise_sum(jerk2, 0, N);
-    dend[i] = lat_p0(L, tt, N - 1);
+    jp[i] = np_pairwise_sum(jerk2, 0, Nl);
+    dend[i] = lat_p0(L, tt, Nl - 1);
   }
   __syncthreads();
+  const int N = s_Nmax;                                 // longest profile in the block
   for (int idx = tid; idx < n_k * N; idx += kSweepThreads) {
     const int kl = idx / N, n = idx - kl * N;
+    if (n >= pairN[kl]) continue;
     Lon L;
     L.a0 = lonc[kl]; L.a1 = lonc[G.kv_cap + kl]; L.a2 = lonc[2 * G.kv_cap + kl];
     L.a3 = lonc[3 * G.kv_cap + kl]; L.a4 = lonc[4 * G.kv_cap + kl]; L.hold = holdk[kl];
@@ -508,24 +534,27 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   __syncthreads();
 
   // ---- phase 1: cost + kinematic chain ----------------------------------------------------
-  const BlockCtx C{tt, hot, kin, kobs, NT, N};
+  BlockCtx C{tt, hot, kin, kobs, NT, N};
   int kl = 0, cand_idx = 0, cat = FOT_CAT_DROP + 1;     // idle threads: no category
   double cost = INFINITY;
   Lat lat{};
   KinResult K{};
   CollState cs{false, false, 0, 0};
   if (tid < n_cand) {
-    int li;
+    int li, Nc;
     if (!brake_blk) {
       const int m = m0 + tid;
-      const int kv = m / n_d, id = m - kv * n_d;
-      kl = kv - k_lo;
-      li = id;
-      cand_idx = (jT * n_v + kv) * n_d + id;
-      lat = lat_solve(fs, P.d_grid[id], P.T[jT], P.inv5 + 9 * jT, n_d == 1, N - 1);
+      const int p = m / n_d, id = m - p * n_d;
+      kl = p - k_lo;
+      const int jT = pairT[kl];
+      Nc = pairN[kl];
+      li = (jT - jT_lo) * n_d + id;
+      cand_idx = m;                                      // generation order (fp.py:398-449)
+      lat = lat_solve(fs, P.d_grid[id], P.T[jT], P.inv5 + 9 * jT, n_d == 1, Nc - 1);
     } else {
       kl = tid;
       li = tid;
+      Nc = P.cfg.n_total;
       cand_idx = P.cfg.n_T * n_v * n_d + k_lo + tid;
       lat = lat_solve(fs, fs[3], P.Tb[k_lo + tid], P.inv5b + 9 * (k_lo + tid), true, P.n_steps_b[k_lo + tid]);
     }
@@ -534,13 +563,15 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     const double d_end = dend[li];
     const double Jd = d_end * d_end;
     const double Js = js[kl];
-    const double dv = B.target[q] - kin[((size_t)kl * NT + (N - 1)) * kKin + 3];
+    const double dv = B.target[q] - kin[((size_t)kl * NT + (Nc - 1)) * kKin + 3];
     const double Jv = dv * dv;
-    const double Jt = tt[kTT * (N - 1)];
+    const double Jt = tt[kTT * (Nc - 1)];
     const double lat_cost = P.cfg.k_j * Jp + P.cfg.k_t * Jt + P.cfg.k_d * Jd;
     const double lon_cost = P.cfg.k_j * Js + P.cfg.k_t * Jt + P.cfg.k_s_dot * Jv;
     cost = P.cfg.k_lat * lat_cost + P.cfg.k_lon * lon_cost;
+    C.N = Nc;
     K = kinematic_pass(P, C, lat, kl, B.limits + 4 * (size_t)q);
+    C.N = N;
     cat = K.category;
     cs.live = cat < 0;
     cs.keep = K.keep;
@@ -592,7 +623,7 @@ fot_sweep(const Plan P, const Batch B, const Out O, const SweepGeom G) {
         for (int pg = warp; pg < n_k * ng; pg += kSweepThreads / 32) {       // cull: one warp per (speed, step)
           const int klc = pg / ng, n = g0 + (pg - klc * ng);
           int total = 0;
-          if (pair_live[klc]) {
+          if (pair_live[klc] && n < pairN[klc]) {
             const double* h = hot + ((size_t)klc * NT + n) * kHot;
             const double rx = h[0], ry = h[1], cth = h[2], sth = h[3];
             const double* A = stage + (is_static ? 0 : (size_t)(kobs[n] - T.k0) * 3 * T.cnt);
