@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "fot_kernels.cuh"
+#include "fot_sweep_items.cuh"
 
 using namespace fot;
 
@@ -67,7 +68,8 @@ struct fot_handle {
   std::vector<cudaEvent_t> ring;     // kRing x 4 events: start, after prepass, after sweep, after winner
   long long n_launch = 0;
   int smem_optin = 0;
-  Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx;   // device scratch
+  Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_bad;   // device scratch
+  int last_sweep_kind = 0;           // 1: fot_sweep_items, 2: fot_sweep (generic)
   Buf stage_h, stage_d, out_d, dyn_d, stat_d;   // host-API staging
   fot_handle() { stage_h.host = true; }
 };
@@ -139,6 +141,7 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   CK(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   h->smem_optin -= 2048;   // leave room for the kernels' static shared memory
   CK(cudaFuncSetAttribute(fot_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_items, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   *out = h;
   return FOT_OK;
 }
@@ -147,7 +150,7 @@ extern "C" int fot_destroy(fot_handle_t* h) {
   if (!h) return FOT_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->stage_h, &h->stage_d, &h->out_d,
+  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->dyn_bad, &h->stage_h, &h->stage_d, &h->out_d,
                  &h->dyn_d, &h->stat_d})
     b->release();
   if (h->tables_dev) cudaFree(h->tables_dev);
@@ -237,6 +240,73 @@ static int sweep_geometry(const fot_handle* h, const fot_batch_t* b, SweepGeom* 
   return FOT_OK;
 }
 
+
+// Geometry of the sample-major kernel (fot_sweep_items).  Returns false when the batch's shape is
+// outside what that kernel covers (very long time grids); the candidate-major fot_sweep then runs.
+static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g, size_t* smem_bytes) {
+  const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B, nx = h->plan.cfg.nx;
+  if (NT > kItemThreads || nd > 8192) return false;
+  const int ppc_max = kItemThreads / NT;
+  ItemGeom G{};
+  G.chunks = (b->n_v_max + ppc_max - 1) / ppc_max;
+  G.ppc = (b->n_v_max + G.chunks - 1) / G.chunks;
+  G.grid_blocks = h->plan.cfg.n_T * G.chunks;
+  G.ppb = nB > 0 ? std::min(nB, ppc_max) : 0;
+  G.brake_blocks = nB > 0 ? (nB + G.ppb - 1) / G.ppb : 0;
+  G.blocks_per_query = G.grid_blocks + G.brake_blocks;
+  G.pcap = std::max(G.ppc, std::max(G.ppb, 1));
+  G.threads = (G.pcap * NT + 31) / 32 * 32;
+  G.nlat_cap = std::max(1, G.ppb);
+  G.jcap = std::max(nd, G.ppb);
+  G.nw4 = (nd + 3) / 4;
+  G.nwc = (nd + 31) / 32;
+  const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
+  const int SP = has_dyn ? b->S * b->P : 0;
+  const int max_viol = b->dyn_mode == FOT_DYN_DISTRIBUTION ? (int)std::floor(h->plan.cfg.chance_epsilon * (double)b->S) : 0;
+  G.vwords = max_viol > 0 ? (b->S + 31) / 32 : 0;
+  G.n_bad = std::max(1, (SP + 31) / 32);
+  const int n_obs_max = std::max(SP, b->n_static);
+  G.ochunk = n_obs_max <= 256 ? std::max(n_obs_max, 1) : 128;
+  G.qcap = 2048;
+  G.spline_smem = nx <= 128 ? 1 : 0;
+  const size_t dyn_bytes = (size_t)SP * b->T_obs * 16;
+  auto layout = [&](bool stage) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
+    G.o_tt = take((size_t)kTT * NT * 8);
+    G.o_ref = take((size_t)G.pcap * NT * kRefW * 8);
+    G.o_lab = take((size_t)G.nlat_cap * NT * kLabW * 8);
+    G.o_labc = take((size_t)G.nlat_cap * kLabC * 8);
+    G.o_lonc = take((size_t)G.pcap * 6 * 8);
+    G.o_js = take((size_t)G.pcap * 8);
+    G.o_jp = take((size_t)G.jcap * 8);
+    G.o_dend = take((size_t)G.jcap * 8);
+    G.o_dgrid = take((size_t)nd * 8);
+    G.o_vlast = take((size_t)G.pcap * nd * 8);
+    G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);
+    G.o_dyn = take(stage ? dyn_bytes : 0);
+    G.o_pi = take((size_t)2 * G.pcap * 4);
+    G.o_flags = take((size_t)G.pcap * G.nw4 * 4);
+    G.o_clean = take((size_t)G.pcap * G.nwc * 4);
+    G.o_hit = take((size_t)G.pcap * G.nwc * 4);
+    G.o_viol = take((size_t)G.pcap * nd * G.vwords * 4);
+    G.o_queue = take((size_t)G.qcap * 4);
+    G.o_kobs = take((size_t)NT * 4);
+    G.o_bad = take((size_t)G.n_bad * 4);
+    G.stage_dyn = stage ? 1 : 0;
+    return off;
+  };
+  // stage the query's obstacle block in shared memory when two blocks per SM still fit
+  bool stage = has_dyn && dyn_bytes > 0 && dyn_bytes <= 64 * 1024 && ((uintptr_t)b->dyn & 15) == 0 &&
+               dyn_bytes < (1u << 20);
+  size_t bytes = layout(stage);
+  if (stage && bytes > 110 * 1024) { stage = false; bytes = layout(false); }
+  if (bytes > (size_t)h->smem_optin) return false;
+  *g = G;
+  *smem_bytes = bytes;
+  return true;
+}
+
 static int check_batch(const fot_handle* h, const fot_batch_t* b, const fot_result_t* r) {
   if (!h || !b || !r) return fail(FOT_ERR_ARG, "null argument");
   if (b->n_q < 1 || b->n_v_max < 1) return fail(FOT_ERR_ARG, "n_q and n_v_max must be >= 1");
@@ -259,10 +329,22 @@ static int check_batch(const fot_handle* h, const fot_batch_t* b, const fot_resu
 }
 
 static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r, cudaStream_t st) {
-  SweepGeom g;
+  // kernel choice: the sample-major fot_sweep_items unless the shape is outside its range (or
+  // FOT_SWEEP=generic asks for the candidate-major kernel, which the tests use as a cross-check)
+  ItemGeom ig{};
+  size_t ismem = 0;
+  static const char* force = getenv("FOT_SWEEP");
+  bool use_items = item_geometry(h, b, &ig, &ismem);
+  if (force && !strcmp(force, "generic")) use_items = false;
+  if (force && !strcmp(force, "items") && !use_items) return fail(FOT_ERR_ARG, "FOT_SWEEP=items: shape not supported by fot_sweep_items");
+  SweepGeom g{};
   size_t smem = 0;
-  int rc = sweep_geometry(h, b, &g, &smem);
-  if (rc != FOT_OK) return rc;
+  if (!use_items) {
+    int rc = sweep_geometry(h, b, &g, &smem);
+    if (rc != FOT_OK) return rc;
+  } else {
+    g.blocks_per_query = ig.blocks_per_query;   // fot_winner reads the partials
+  }
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const size_t n_part = (size_t)b->n_q * g.blocks_per_query;
   if ((size_t)b->n_q * (size_t)g.blocks_per_query > 0x7fffffffull) return fail(FOT_ERR_ARG, "batch too large for one launch");
@@ -271,25 +353,33 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   const int SP = has_dyn ? b->S * b->P : 0;
   const int SPp = (SP + 3) & ~3, Mp = (b->n_static + 3) & ~3;
   const int nq_s = b->static_per_query ? b->n_q : 1;
-  if (has_dyn) {
-    CK(h->obs_tm.reserve((size_t)b->n_q * b->T_obs * 3 * SPp * sizeof(double)));
-    CK(h->obs_max2.reserve((size_t)b->n_q * sizeof(double)));
-  }
-  if (b->n_static > 0) {
-    CK(h->stat_tm.reserve((size_t)nq_s * 3 * Mp * sizeof(double)));
-    CK(h->stat_max2.reserve((size_t)nq_s * sizeof(double)));
+  const bool need_bad = use_items && has_dyn && !ig.stage_dyn;
+  if (!use_items) {
+    if (has_dyn) {
+      CK(h->obs_tm.reserve((size_t)b->n_q * b->T_obs * 3 * SPp * sizeof(double)));
+      CK(h->obs_max2.reserve((size_t)b->n_q * sizeof(double)));
+    }
+    if (b->n_static > 0) {
+      CK(h->stat_tm.reserve((size_t)nq_s * 3 * Mp * sizeof(double)));
+      CK(h->stat_max2.reserve((size_t)nq_s * sizeof(double)));
+    }
+  } else if (need_bad) {
+    CK(h->dyn_bad.reserve((size_t)b->n_q * ig.n_bad * sizeof(unsigned)));
   }
 
   Batch B{};
   B.n_q = b->n_q; B.n_v_max = b->n_v_max;
   B.frenet = b->frenet; B.target = b->target_speed; B.limits = b->limits; B.stop_dist = b->stop_dist;
   B.v_grid = b->v_grid; B.n_v = b->n_v;
-  B.static_tm = b->n_static > 0 ? (const double*)h->stat_tm.p : nullptr;
-  B.static_max2 = b->n_static > 0 ? (const double*)h->stat_max2.p : nullptr;
+  B.static_tm = (!use_items && b->n_static > 0) ? (const double*)h->stat_tm.p : nullptr;
+  B.static_max2 = (!use_items && b->n_static > 0) ? (const double*)h->stat_max2.p : nullptr;
   B.n_static = b->n_static; B.static_per_query = b->static_per_query;
-  B.obs_tm = has_dyn ? (const double*)h->obs_tm.p : nullptr;
-  B.obs_max2 = has_dyn ? (const double*)h->obs_max2.p : nullptr;
+  B.obs_tm = (!use_items && has_dyn) ? (const double*)h->obs_tm.p : nullptr;
+  B.obs_max2 = (!use_items && has_dyn) ? (const double*)h->obs_max2.p : nullptr;
   B.S = has_dyn ? b->S : 0; B.P = has_dyn ? b->P : 0; B.T_obs = has_dyn ? b->T_obs : 0; B.dyn_mode = b->dyn_mode;
+  B.dyn_raw = has_dyn ? b->dyn : nullptr;
+  B.static_raw = b->n_static > 0 ? b->static_obs : nullptr;
+  B.dyn_bad = need_bad ? (const unsigned*)h->dyn_bad.p : nullptr;
   Out O{};
   O.best_idx = r->best_idx; O.best_cost = r->best_cost; O.stats = r->stats; O.winner_len = r->winner_len;
   O.winner = r->winner; O.cand_cat = r->cand_cat; O.cand_cost = r->cand_cost; O.cand_stride = r->cand_stride;
@@ -299,26 +389,39 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   CK(cudaEventRecord(h->ev0, st));
   {
     const size_t n_cat = r->cand_cat ? (size_t)b->n_q * r->cand_stride : 0;
-    const size_t work = std::max<size_t>((size_t)b->n_q * FOT_N_STATS, n_cat);
+    const size_t n_badw = need_bad ? (size_t)b->n_q * ig.n_bad : 0;
+    const size_t work = std::max<size_t>(std::max<size_t>((size_t)b->n_q * FOT_N_STATS, n_cat), n_badw);
     const int blocks = (int)std::min<size_t>(1024, (work + 255) / 256);
-    fot_init_kernel<<<blocks, 256, 0, st>>>(r->stats, b->n_q * FOT_N_STATS, has_dyn ? (double*)h->obs_max2.p : nullptr,
-                                            has_dyn ? b->n_q : 0, b->n_static > 0 ? (double*)h->stat_max2.p : nullptr,
-                                            b->n_static > 0 ? nq_s : 0, r->cand_cat, n_cat);
+    const bool planes = !use_items;
+    fot_init_kernel<<<blocks, 256, 0, st>>>(r->stats, b->n_q * FOT_N_STATS,
+                                            planes && has_dyn ? (double*)h->obs_max2.p : nullptr, planes && has_dyn ? b->n_q : 0,
+                                            planes && b->n_static > 0 ? (double*)h->stat_max2.p : nullptr,
+                                            planes && b->n_static > 0 ? nq_s : 0, r->cand_cat, n_cat,
+                                            need_bad ? (unsigned*)h->dyn_bad.p : nullptr, n_badw);
   }
   CK(cudaEventRecord(ring[0], st));
-  if (has_dyn) {
+  if (!use_items) {
+    if (has_dyn) {
+      const long long warps = (long long)b->n_q * SP;
+      const int blocks = (int)((warps * 32 + 255) / 256);
+      fot_obstacle_prepass<<<blocks, 256, 0, st>>>((const double2*)b->dyn, (double*)h->obs_tm.p,
+                                                   (double*)h->obs_max2.p, b->n_q, SP, b->T_obs);
+    }
+    if (b->n_static > 0) {
+      const int total = nq_s * b->n_static;
+      fot_static_prepass<<<(total + 255) / 256, 256, 0, st>>>((const double2*)b->static_obs, (double*)h->stat_tm.p,
+                                                              (double*)h->stat_max2.p, nq_s, b->n_static);
+    }
+  } else if (need_bad) {
     const long long warps = (long long)b->n_q * SP;
-    const int blocks = (int)((warps * 32 + 255) / 256);
-    fot_obstacle_prepass<<<blocks, 256, 0, st>>>((const double2*)b->dyn, (double*)h->obs_tm.p,
-                                                 (double*)h->obs_max2.p, b->n_q, SP, b->T_obs);
-  }
-  if (b->n_static > 0) {
-    const int total = nq_s * b->n_static;
-    fot_static_prepass<<<(total + 255) / 256, 256, 0, st>>>((const double2*)b->static_obs, (double*)h->stat_tm.p,
-                                                            (double*)h->stat_max2.p, nq_s, b->n_static);
+    const long long blocks = (warps * 32 + 255) / 256;
+    if (blocks > 0x7fffffffll) return fail(FOT_ERR_ARG, "obstacle field too large for one launch");
+    fot_bad_prepass<<<(unsigned)blocks, 256, 0, st>>>((const double2*)b->dyn, (unsigned*)h->dyn_bad.p, b->n_q, SP, b->T_obs, ig.n_bad);
   }
   CK(cudaEventRecord(ring[1], st));
-  fot_sweep<<<(unsigned)n_part, kSweepThreads, smem, st>>>(h->plan, B, O, g);
+  if (use_items) fot_sweep_items<<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
+  else fot_sweep<<<(unsigned)n_part, kSweepThreads, smem, st>>>(h->plan, B, O, g);
+  h->last_sweep_kind = use_items ? 1 : 2;
   CK(cudaEventRecord(ring[2], st));
   fot_winner<<<b->n_q, 128, (size_t)kTT * h->plan.n_t_max * sizeof(double), st>>>(h->plan, B, O, g);
   CK(cudaEventRecord(ring[3], st));

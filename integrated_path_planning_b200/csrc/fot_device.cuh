@@ -33,6 +33,10 @@ struct Batch {
   const double* obs_tm;       // dynamic obstacles, time-major planes [n_q][T_obs][3][pad4(S*P)]
   const double* obs_max2;     // [n_q]
   int32_t S, P, T_obs, dyn_mode;
+  // fot_sweep_items reads the caller's tensors directly:
+  const double* dyn_raw;      // [n_q][S][P][T_obs][2] (reference layout) or null
+  const double* static_raw;   // [n_q or 1][M][2] or null
+  const unsigned* dyn_bad;    // [n_q][ceil(S*P/32)] NaN-trajectory bitmap (only when the field is not staged in smem)
 };
 
 struct Out {

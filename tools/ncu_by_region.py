@@ -36,10 +36,10 @@ for r, key in zip(body, lines):
     smp[key] += float(r[ix["# Samples"]] or 0)
     thr[key] += float(r[ix["Thread Instructions Executed"]] or 0)
 ti, ts = sum(inst.values()), sum(smp.values())
-src = open("integrated_path_planning_b200/csrc/fot_kernels.cuh").read().splitlines()
+src = open("integrated_path_planning_b200/csrc/" + os.environ.get("REGION_FILE", "fot_kernels.cuh")).read().splitlines()
 print(f"total warp instructions {ti:.4g}")
-for key in sorted(k for k in inst if k and k[0] == "fot_kernels.cuh"):
+for key in sorted(k for k in inst if k and k[0] == os.environ.get("REGION_FILE", "fot_kernels.cuh")):
     if inst[key] / ti < 0.004 and smp[key] / ts < 0.004: continue
     print(f"{inst[key]/ti*100:5.1f}% inst {smp[key]/ts*100:5.1f}% smp lanes {thr[key]/max(inst[key],1):4.1f}  L{key[1]}: {src[key[1]-1].strip()[:95]}")
-other = sum(v for k, v in inst.items() if not k or k[0] != "fot_kernels.cuh")
+other = sum(v for k, v in inst.items() if not k or k[0] != os.environ.get("REGION_FILE", "fot_kernels.cuh"))
 print(f"{other/ti*100:5.1f}% inst attributed elsewhere")
