@@ -242,10 +242,14 @@ static int sweep_geometry(const fot_handle* h, const fot_batch_t* b, SweepGeom* 
 
 
 // Geometry of the sample-major kernel (fot_sweep_items).  Returns false when the batch's shape is
-// outside what that kernel covers (very long time grids); the candidate-major fot_sweep then runs.
+// outside what that kernel covers (very long time grids, huge per-step obstacle counts); the
+// candidate-major fot_sweep then runs.
 static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g, size_t* smem_bytes) {
   const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B, nx = h->plan.cfg.nx;
-  if (NT > kItemThreads || nd > 8192) return false;
+  const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
+  const long long SPl = has_dyn ? (long long)b->S * b->P : 0;
+  if (NT > kItemThreads || nd > 8192 || SPl > 32768 || b->n_static > 32768) return false;
+  const int SP = (int)SPl;
   const int ppc_max = kItemThreads / NT;
   ItemGeom G{};
   G.chunks = (b->n_v_max + ppc_max - 1) / ppc_max;
@@ -256,49 +260,42 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   G.blocks_per_query = G.grid_blocks + G.brake_blocks;
   G.pcap = std::max(G.ppc, std::max(G.ppb, 1));
   G.threads = (G.pcap * NT + 31) / 32 * 32;
-  G.nlat_cap = std::max(1, G.ppb);
   G.jcap = std::max(nd, G.ppb);
   G.nw4 = (nd + 3) / 4;
   G.nwc = (nd + 31) / 32;
-  const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
-  const int SP = has_dyn ? b->S * b->P : 0;
   const int max_viol = b->dyn_mode == FOT_DYN_DISTRIBUTION ? (int)std::floor(h->plan.cfg.chance_epsilon * (double)b->S) : 0;
   G.vwords = max_viol > 0 ? (b->S + 31) / 32 : 0;
-  G.n_bad = std::max(1, (SP + 31) / 32);
-  const int n_obs_max = std::max(SP, b->n_static);
-  G.ochunk = n_obs_max <= 256 ? std::max(n_obs_max, 1) : 128;
-  G.qcap = 2048;
+  G.lcap = std::max(1, SP + b->n_static);
+  G.ochunk = G.lcap <= 256 ? G.lcap : 128;
+  G.qcap = 1024;
   G.spline_smem = nx <= 128 ? 1 : 0;
   const size_t dyn_bytes = (size_t)SP * b->T_obs * 16;
   auto layout = [&](bool stage) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
-    G.o_tt = take((size_t)kTT * NT * 8);
-    G.o_ref = take((size_t)G.pcap * NT * kRefW * 8);
-    G.o_lab = take((size_t)G.nlat_cap * NT * kLabW * 8);
-    G.o_labc = take((size_t)G.nlat_cap * kLabC * 8);
-    G.o_lonc = take((size_t)G.pcap * 6 * 8);
+    G.o_row = take((size_t)G.pcap * NT * kRowW * 8);
     G.o_js = take((size_t)G.pcap * 8);
+    G.o_sdl = take((size_t)G.pcap * 8);
     G.o_jp = take((size_t)G.jcap * 8);
     G.o_dend = take((size_t)G.jcap * 8);
     G.o_dgrid = take((size_t)nd * 8);
     G.o_vlast = take((size_t)G.pcap * nd * 8);
     G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);
     G.o_dyn = take(stage ? dyn_bytes : 0);
-    G.o_pi = take((size_t)2 * G.pcap * 4);
+    G.o_fn = take((size_t)G.pcap * 4);
     G.o_flags = take((size_t)G.pcap * G.nw4 * 4);
-    G.o_clean = take((size_t)G.pcap * G.nwc * 4);
     G.o_hit = take((size_t)G.pcap * G.nwc * 4);
     G.o_viol = take((size_t)G.pcap * nd * G.vwords * 4);
+    G.n_zero = (int32_t)((off - (size_t)G.o_flags) / 4);
     G.o_queue = take((size_t)G.qcap * 4);
-    G.o_kobs = take((size_t)NT * 4);
-    G.o_bad = take((size_t)G.n_bad * 4);
+    G.o_list = take((size_t)G.lcap * 2);
+    G.o_slow = take((size_t)G.threads * 2);
     G.stage_dyn = stage ? 1 : 0;
     return off;
   };
   // stage the query's obstacle block in shared memory when two blocks per SM still fit
-  bool stage = has_dyn && dyn_bytes > 0 && dyn_bytes <= 64 * 1024 && ((uintptr_t)b->dyn & 15) == 0 &&
-               dyn_bytes < (1u << 20);
+  bool stage = has_dyn && dyn_bytes > 0 && dyn_bytes <= 64 * 1024 && ((uintptr_t)b->dyn & 15) == 0;
+  if (const char* env = getenv("FOT_STAGE_DYN")) stage = stage && atoi(env) != 0;
   size_t bytes = layout(stage);
   if (stage && bytes > 110 * 1024) { stage = false; bytes = layout(false); }
   if (bytes > (size_t)h->smem_optin) return false;
@@ -353,7 +350,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   const int SP = has_dyn ? b->S * b->P : 0;
   const int SPp = (SP + 3) & ~3, Mp = (b->n_static + 3) & ~3;
   const int nq_s = b->static_per_query ? b->n_q : 1;
-  const bool need_bad = use_items && has_dyn && !ig.stage_dyn;
+  const bool need_box = use_items && has_dyn;
   if (!use_items) {
     if (has_dyn) {
       CK(h->obs_tm.reserve((size_t)b->n_q * b->T_obs * 3 * SPp * sizeof(double)));
@@ -363,8 +360,8 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
       CK(h->stat_tm.reserve((size_t)nq_s * 3 * Mp * sizeof(double)));
       CK(h->stat_max2.reserve((size_t)nq_s * sizeof(double)));
     }
-  } else if (need_bad) {
-    CK(h->dyn_bad.reserve((size_t)b->n_q * ig.n_bad * sizeof(unsigned)));
+  } else if (need_box) {
+    CK(h->dyn_bad.reserve((size_t)b->n_q * SP * sizeof(float4)));
   }
 
   Batch B{};
@@ -379,7 +376,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   B.S = has_dyn ? b->S : 0; B.P = has_dyn ? b->P : 0; B.T_obs = has_dyn ? b->T_obs : 0; B.dyn_mode = b->dyn_mode;
   B.dyn_raw = has_dyn ? b->dyn : nullptr;
   B.static_raw = b->n_static > 0 ? b->static_obs : nullptr;
-  B.dyn_bad = need_bad ? (const unsigned*)h->dyn_bad.p : nullptr;
+  B.dyn_box = need_box ? (const float4*)h->dyn_bad.p : nullptr;
   Out O{};
   O.best_idx = r->best_idx; O.best_cost = r->best_cost; O.stats = r->stats; O.winner_len = r->winner_len;
   O.winner = r->winner; O.cand_cat = r->cand_cat; O.cand_cost = r->cand_cost; O.cand_stride = r->cand_stride;
@@ -389,15 +386,13 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   CK(cudaEventRecord(h->ev0, st));
   {
     const size_t n_cat = r->cand_cat ? (size_t)b->n_q * r->cand_stride : 0;
-    const size_t n_badw = need_bad ? (size_t)b->n_q * ig.n_bad : 0;
-    const size_t work = std::max<size_t>(std::max<size_t>((size_t)b->n_q * FOT_N_STATS, n_cat), n_badw);
+    const size_t work = std::max<size_t>((size_t)b->n_q * FOT_N_STATS, n_cat);
     const int blocks = (int)std::min<size_t>(1024, (work + 255) / 256);
     const bool planes = !use_items;
     fot_init_kernel<<<blocks, 256, 0, st>>>(r->stats, b->n_q * FOT_N_STATS,
                                             planes && has_dyn ? (double*)h->obs_max2.p : nullptr, planes && has_dyn ? b->n_q : 0,
                                             planes && b->n_static > 0 ? (double*)h->stat_max2.p : nullptr,
-                                            planes && b->n_static > 0 ? nq_s : 0, r->cand_cat, n_cat,
-                                            need_bad ? (unsigned*)h->dyn_bad.p : nullptr, n_badw);
+                                            planes && b->n_static > 0 ? nq_s : 0, r->cand_cat, n_cat);
   }
   CK(cudaEventRecord(ring[0], st));
   if (!use_items) {
@@ -412,11 +407,11 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
       fot_static_prepass<<<(total + 255) / 256, 256, 0, st>>>((const double2*)b->static_obs, (double*)h->stat_tm.p,
                                                               (double*)h->stat_max2.p, nq_s, b->n_static);
     }
-  } else if (need_bad) {
+  } else if (need_box) {
     const long long warps = (long long)b->n_q * SP;
     const long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0x7fffffffll) return fail(FOT_ERR_ARG, "obstacle field too large for one launch");
-    fot_bad_prepass<<<(unsigned)blocks, 256, 0, st>>>((const double2*)b->dyn, (unsigned*)h->dyn_bad.p, b->n_q, SP, b->T_obs, ig.n_bad);
+    fot_aabb_prepass<<<(unsigned)blocks, 256, 0, st>>>((const double2*)b->dyn, (float4*)h->dyn_bad.p, warps, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
   if (use_items) fot_sweep_items<<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);

@@ -36,7 +36,7 @@ struct Batch {
   // fot_sweep_items reads the caller's tensors directly:
   const double* dyn_raw;      // [n_q][S][P][T_obs][2] (reference layout) or null
   const double* static_raw;   // [n_q or 1][M][2] or null
-  const unsigned* dyn_bad;    // [n_q][ceil(S*P/32)] NaN-trajectory bitmap (only when the field is not staged in smem)
+  const float4* dyn_box;      // [n_q][S*P] trajectory boxes (xmin, xmax, ymin, ymax) from fot_aabb_prepass
 };
 
 struct Out {

@@ -47,13 +47,12 @@ __device__ __forceinline__ void atomic_max_pos(double* addr, double v) {   // v 
 // Per-launch initialisation (kept off the copy engines, which cudaMemsetAsync may use and which are
 // busy with the next chunk's upload in the pipelined host path).
 __global__ void fot_init_kernel(int32_t* stats, int n_stats, double* max2_a, int n_a, double* max2_b, int n_b,
-                                uint8_t* cand_cat, size_t n_cat, unsigned* bad, size_t n_bad) {
+                                uint8_t* cand_cat, size_t n_cat) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (size_t j = i; j < (size_t)n_stats; j += stride) stats[j] = 0;
   for (size_t j = i; j < (size_t)n_a; j += stride) max2_a[j] = 0.0;
   for (size_t j = i; j < (size_t)n_b; j += stride) max2_b[j] = 0.0;
   for (size_t j = i; j < n_cat; j += stride) cand_cat[j] = FOT_CAT_DROP + 1;
-  for (size_t j = i; j < n_bad; j += stride) bad[j] = 0u;
 }
 
 // ----------------------------------------------------------------------------------------

@@ -8,9 +8,14 @@
 //   thread = one (terminal speed v_k, sample t_n) "item": everything that depends on the
 //            longitudinal profile only -- s(t_n), the spline reference point, heading, curvature,
 //            1/s_dot -- is computed ONCE per item and lives in registers;
-//   loop   = the lateral targets d_i.  The quintic solve is linear in the target, so
-//            d_i(t_n) = A(t_n) + d_i * B(t_n)  (and likewise the two time derivatives): three FMAs
-//            per candidate sample from six per-thread constants, no table, no per-candidate Horner.
+//   loop   = the lateral targets d_i.  The quintic solve is linear in the target, so at a fixed
+//            sample  d_i(t_n) = A + d_i * B, and with it every first-order quantity of the
+//            Frenet->Cartesian map (q = 1 - kappa_r d, d', d'', kappa_r' d + kappa_r d', the step
+//            vector to the previous sample) is AFFINE in d_i: one FMA each from per-thread constants.
+//            The limit checks are evaluated in squared, division-free form
+//              kappa = w / h^3,  a = Z / (h q),  v^2 = s_dot^2 h^2   (h^2 = q^2 + d'^2)
+//              |kappa| > k_max  <=>  w^2 > k_max^2 h^6       (no sqrt, no reciprocal, no atan2)
+//            so the inner loop is ~45 FP64 instructions per candidate sample.
 //
 // A candidate's validity flags (priority chain fp.py:964-991, silent drops :933-956) are an OR over
 // its samples, i.e. over the threads of one speed: warp `redux.or` over the lanes of that speed,
@@ -20,25 +25,29 @@
 // Collision (fp.py:1035-1233): a clean candidate's sample lies exactly on the normal of the
 // reference line through the item's reference point at lateral offset |d| <= road half-width, so an
 // obstacle sample can only touch it when it is within r along the tangent and W + r across it.
-// Each item tests the obstacles of its own time step against that window (the obstacle tensor is
-// read in the reference's own [S][P][T][2] layout: consecutive lanes are consecutive time steps,
-// so the 16-byte loads coalesce; small fields are staged in shared memory by ONE bulk copy,
-// cp.async.bulk + mbarrier) and pushes the few survivors into a block-wide queue; the queue is then
-// drained by all threads, one entry each, with the reference's exact un-fused
-// `dx*dx + dy*dy <= r^2` against every still-alive clean candidate of that speed.
+//   1. fot_aabb_prepass (one warp per predicted trajectory) boxes every trajectory once per launch;
+//      a block keeps only the trajectories whose box meets the box of its own reference points --
+//      the reference's own AABB prefilter (fp.py:1211-1222) including its NaN-trajectory rule;
+//   2. each item tests the listed obstacles at its own time step against the tangent-frame window
+//      (the obstacle tensor is read in the reference's [S][P][T][2] layout: consecutive lanes are
+//      consecutive time steps, so the 16-byte loads coalesce; small fields are staged in shared memory
+//      by ONE bulk copy, cp.async.bulk + mbarrier) and remembers the few survivors in a bit mask;
+//   3. survivors go to a block-wide queue that all threads drain, one entry each, with the exact
+//      `dx*dx + dy*dy <= r^2` against every still-alive clean candidate of that speed.
 //
 // Numerics: costs are bit-identical to the reference (same arithmetic order, NumPy pairwise
 // sums); the validity chain uses algebraically equal forms that differ by a few ulp (see
 // DESIGN.md section 7); the winner's sequences are regenerated in reference order by fot_winner.
+// The squared forms assume non-negative limits (a negative limit rejects everything, as in the
+// reference).
 #pragma once
+#include <type_traits>
 #include "fot_kernels.cuh"
 
 namespace fot {
 
 constexpr int kItemThreads = 320;   // largest block of fot_sweep_items
-constexpr int kRefW = 8;            // reference row: rx ry cos sin | kappa s 1/s_dot kappa'
-constexpr int kLabW = 6;            // lateral basis row: A B A' B' A'' B''
-constexpr int kLabC = 10;           // lateral basis coefficients: a0 a1 a2 c3 c4 c5 | b3 b4 b5 | pad
+constexpr int kRowW = 12;           // item row: rx ry cos sin | kappa s 1/s_dot s_dot | A0 B0 A1 B1
 constexpr unsigned F_DROP = 32u;    // silent drop (singular / non-finite / teleport), fp.py:826-833, :944-956
 
 struct ItemGeom {
@@ -50,18 +59,18 @@ struct ItemGeom {
   int32_t blocks_per_query;
   int32_t threads;           // block size (multiple of 32, >= items of the largest block)
   int32_t pcap;              // max(ppc, ppb): per-pair table slots
-  int32_t nlat_cap;          // lateral-basis slots: 1 for grid blocks, ppb for brake blocks
   int32_t jcap;              // max(n_d, ppb): lateral jerk-sum slots
   int32_t qcap;              // collision queue capacity (entries)
-  int32_t ochunk;            // obstacles culled per queue round
+  int32_t ochunk;            // list entries culled per queue round
+  int32_t lcap;              // obstacle list capacity (static + dynamic entries)
   int32_t stage_dyn;         // 1: the query's obstacle block is staged in shared memory by one bulk copy
   int32_t spline_smem;       // 1: spline tables copied to shared memory
   int32_t vwords;            // u32 words per candidate of the chance-constraint violation bitmap (0: no budget)
   int32_t nw4, nwc;          // flag words (4 candidates each) / bit-mask words (32 candidates each) per pair
-  int32_t n_bad;             // words of the NaN-trajectory bitmap
+  int32_t n_zero;            // u32 words of the zero-initialised region starting at o_flags
   // byte offsets into dynamic shared memory
-  int32_t o_tt, o_ref, o_lab, o_labc, o_lonc, o_js, o_jp, o_dend, o_dgrid, o_vlast, o_spl, o_dyn;
-  int32_t o_pi, o_flags, o_clean, o_hit, o_viol, o_queue, o_kobs, o_bad;
+  int32_t o_row, o_js, o_sdl, o_jp, o_dend, o_dgrid, o_vlast, o_spl, o_dyn;
+  int32_t o_fn, o_flags, o_hit, o_viol, o_queue, o_list, o_slow;
 };
 
 struct SplineView {
@@ -111,15 +120,15 @@ __device__ __forceinline__ RefFast spline_ref_fast(const SplineView& V, double s
   return o;
 }
 
-// 1/sqrt(x) to fp64 accuracy from the fp32 MUFU seed and two Newton steps (branch-free; the
-// argument is q^2 + d'^2 of a sample that is either well inside the normal range or belongs to a
-// candidate that is dropped / speed-rejected anyway).
-__device__ __forceinline__ double rsqrt_nr(double x) {
-  double y = (double)rsqrtf((float)x);
-  const double hx = 0.5 * x;
-  y = fma(y, fma(-hx * y, y, 0.5), y);
-  y = fma(y, fma(-hx * y, y, 0.5), y);
-  return y;
+// Time powers of one sample, built as the reference's TimeCache does (fp.py:594-598).
+struct TPow {
+  double t, t2, t3, t4, t5;
+};
+__device__ __forceinline__ TPow tpow(int n, double dt) {
+  TPow r;
+  r.t = (double)n * dt;
+  r.t2 = r.t * r.t; r.t3 = r.t2 * r.t; r.t4 = r.t2 * r.t2; r.t5 = r.t4 * r.t;
+  return r;
 }
 
 // NumPy pairwise sum (see np_pairwise_sum) of f(0..n-1) computed by the 8 lanes of an aligned lane
@@ -145,32 +154,64 @@ __device__ __forceinline__ double np_sum_8lanes(const F& f, int n, int sub, unsi
   return res;
 }
 
+// Order-preserving float <-> unsigned map for atomicMin / atomicMax on floats.
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+
+// flag |= bit when a > b / when |a| > b: one DSETP and one predicated LOP3 (the compiler's own
+// `cond ? bit : 0` idiom costs a SEL and a LOP3 per flag)
+__device__ __forceinline__ void flag_gt(unsigned& f, double a, double b, unsigned bit) {
+  asm("{\n .reg .pred p;\n setp.gt.f64 p, %1, %2;\n @p or.b32 %0, %0, %3;\n}" : "+r"(f) : "d"(a), "d"(b), "r"(bit));
+}
+__device__ __forceinline__ void flag_abs_gt(unsigned& f, double a, double b, unsigned bit) {
+  asm("{\n .reg .pred p;\n .reg .f64 t;\n abs.f64 t, %1;\n setp.gt.f64 p, t, %2;\n @p or.b32 %0, %0, %3;\n}" : "+r"(f) : "d"(a), "d"(b), "r"(bit));
+}
+
+// Bit i of the result: candidate 32*w + i of pair `pp` has no validity flag (4 flag bytes per word).
+__device__ __forceinline__ unsigned clean_word(const unsigned* flags_pp, int nw4, int n_dl, int w) {
+  unsigned m = 0u;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int w4 = 8 * w + k;
+    if (w4 < nw4) {
+      const unsigned x = flags_pp[w4];
+      const unsigned t = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // bit 7 of every zero byte
+      m |= ((((t >> 7) * 0x00204081u) >> 21) & 0xfu) << (4 * k);
+    }
+  }
+  const int rem = n_dl - 32 * w;
+  return rem >= 32 ? m : (m & ((1u << rem) - 1u));
+}
+
 __global__ void __launch_bounds__(kItemThreads, 2)
 fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   extern __shared__ __align__(16) unsigned char smb[];
-  double* tt = reinterpret_cast<double*>(smb + G.o_tt);        // [NT][kTT]
-  double* ref = reinterpret_cast<double*>(smb + G.o_ref);      // [pcap][NT][kRefW]
-  double* lab = reinterpret_cast<double*>(smb + G.o_lab);      // [nlat_cap][NT][kLabW]
-  double* labc = reinterpret_cast<double*>(smb + G.o_labc);    // [nlat_cap][kLabC]
-  double* lonc = reinterpret_cast<double*>(smb + G.o_lonc);    // [pcap][6]  a0..a4, s_dot at the last sample
-  double* js = reinterpret_cast<double*>(smb + G.o_js);        // [pcap]
-  double* jp = reinterpret_cast<double*>(smb + G.o_jp);        // [jcap]
-  double* dend = reinterpret_cast<double*>(smb + G.o_dend);    // [jcap]
+  double* row = reinterpret_cast<double*>(smb + G.o_row);      // [pcap][NT][kRowW]
+  double* js = reinterpret_cast<double*>(smb + G.o_js);        // [pcap] longitudinal jerk sums
+  double* sdl = reinterpret_cast<double*>(smb + G.o_sdl);      // [pcap] s_dot at the last sample
+  double* jp = reinterpret_cast<double*>(smb + G.o_jp);        // [jcap] lateral jerk sums
+  double* dend = reinterpret_cast<double*>(smb + G.o_dend);    // [jcap] terminal lateral offsets
   double* dgrid = reinterpret_cast<double*>(smb + G.o_dgrid);  // [n_d]
   double* vlast = reinterpret_cast<double*>(smb + G.o_vlast);  // [pcap][n_d]  v^2 at the last kept sample
   double* spl = reinterpret_cast<double*>(smb + G.o_spl);      // [9][nx] when spline_smem
   const double2* dynst = reinterpret_cast<const double2*>(smb + G.o_dyn);   // [SP][T_obs] when stage_dyn
-  int* pi_hold = reinterpret_cast<int*>(smb + G.o_pi);         // [pcap]
-  int* pi_fn = pi_hold + G.pcap;                               // [pcap] first NaN sample (INT_MAX: none)
+  int* pi_fn = reinterpret_cast<int*>(smb + G.o_fn);                // [pcap] first NaN sample (INT_MAX: none)
   unsigned* flags = reinterpret_cast<unsigned*>(smb + G.o_flags);   // [pcap][nw4]
-  unsigned* cleanw = reinterpret_cast<unsigned*>(smb + G.o_clean);  // [pcap][nwc] kinematically clean
   unsigned* hitw = reinterpret_cast<unsigned*>(smb + G.o_hit);      // [pcap][nwc] decisive collision
   unsigned* viol = reinterpret_cast<unsigned*>(smb + G.o_viol);     // [pcap][n_d][vwords]
   unsigned* queue = reinterpret_cast<unsigned*>(smb + G.o_queue);   // [qcap]
-  int* kobs = reinterpret_cast<int*>(smb + G.o_kobs);               // [NT]
-  unsigned* bad = reinterpret_cast<unsigned*>(smb + G.o_bad);       // [n_bad]
+  unsigned short* olist = reinterpret_cast<unsigned short*>(smb + G.o_list);   // [lcap] static entries first
+  unsigned short* slowq = reinterpret_cast<unsigned short*>(smb + G.o_slow);   // [threads] items with a low-speed sample
   __shared__ int s_qcount[2];
-  __shared__ int s_anybad;
+  __shared__ int s_nlist[2];            // static / dynamic list lengths
+  __shared__ int s_nslow;               // items in the low-speed queue
+  __shared__ unsigned s_box[4];         // xmin xmax ymin ymax of the block's reference points (ordered-uint floats)
   __shared__ int s_stats[FOT_N_STATS];
   __shared__ double s_cost[kItemThreads / 32];
   __shared__ int s_idx[kItemThreads / 32];
@@ -178,11 +219,12 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
 
   const int NT = P.n_t_max;
   const int q = blockIdx.x / G.blocks_per_query;
-  const int b = blockIdx.x % G.blocks_per_query;
+  const int b = blockIdx.x - q * G.blocks_per_query;
   const int tid = threadIdx.x, lane = tid & 31, bd = blockDim.x;
   const double* fs = B.frenet + 6 * (size_t)q;
   const int n_v = B.n_v[q];
   const int n_d = P.cfg.n_d;
+  const double dt = P.cfg.dt;
   const bool brake_blk = b >= G.grid_blocks;
   const size_t part = (size_t)q * G.blocks_per_query + b;
 
@@ -223,11 +265,14 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
 
   const bool has_dyn = B.dyn_raw != nullptr;
   const int SP = has_dyn ? B.S * B.P : 0;
+  const int M = B.static_raw ? B.n_static : 0;
   const double2* dyn_q = has_dyn ? reinterpret_cast<const double2*>(B.dyn_raw) + (size_t)q * SP * B.T_obs : nullptr;
+  const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
 
-  // ---- phase 0: tables ------------------------------------------------------------------------
+  // ---- phase A: shared-memory set-up ------------------------------------------------------------
   if (tid == 0) {
-    s_qcount[0] = 0; s_qcount[1] = 0; s_anybad = 0;
+    s_qcount[0] = 0; s_qcount[1] = 0; s_nlist[0] = 0; s_nlist[1] = 0; s_nslow = 0;
+    s_box[0] = 0xffffffffu; s_box[1] = 0u; s_box[2] = 0xffffffffu; s_box[3] = 0u;
     if (G.stage_dyn) {
       mbar_init(&s_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -237,18 +282,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     }
   }
   if (tid < FOT_N_STATS) s_stats[tid] = 0;
-  for (int n = tid; n < NT; n += bd) {
-    tt_fill(tt, n, P.cfg.dt);
-    const double kf = rint(((double)n * P.cfg.dt) / P.cfg.dt);                 // fp.py:1226-1227
-    const int kmax_i = B.T_obs > 0 ? B.T_obs - 1 : 0;
-    kobs[n] = kf < 0.0 ? 0 : (kf > (double)kmax_i ? kmax_i : (int)kf);
-  }
+  if (tid < G.pcap) pi_fn[tid] = 0x7fffffff;
+  for (int i = tid; i < G.n_zero; i += bd) flags[i] = 0u;          // flags | hit words | violation bitmaps
   for (int i = tid; i < n_d; i += bd) dgrid[i] = P.d_grid[i];
-  for (int i = tid; i < G.pcap; i += bd) pi_fn[i] = 0x7fffffff;
-  for (int i = tid; i < G.pcap * G.nw4; i += bd) flags[i] = 0u;
-  for (int i = tid; i < G.pcap * G.nwc; i += bd) { cleanw[i] = 0u; hitw[i] = 0u; }
-  for (int i = tid; i < G.pcap * n_d * G.vwords; i += bd) viol[i] = 0u;
-  for (int i = tid; i < G.n_bad; i += bd) bad[i] = (!G.stage_dyn && B.dyn_bad) ? B.dyn_bad[(size_t)q * G.n_bad + i] : 0u;
   SplineView V;
   V.nx = P.cfg.nx;
   if (G.spline_smem) {
@@ -270,313 +306,82 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   }
   __syncthreads();
 
-  // quartic solve per pair (fp.py:619-647); lateral basis coefficients
-  if (tid < n_k) {
-    Lon L;
-    if (!brake_blk)
-      L = lon_solve(fs, B.v_grid[(size_t)q * B.n_v_max + k_lo + tid], P.T[jT], P.inv4 + 4 * jT, n_v == 1, N - 1);
-    else
-      L = lon_solve(fs, 0.0, P.Tb[k_lo + tid], P.inv4b + 4 * (k_lo + tid), true, P.n_steps_b[k_lo + tid]);
-    double* lc = lonc + 6 * tid;
-    lc[0] = L.a0; lc[1] = L.a1; lc[2] = L.a2; lc[3] = L.a3; lc[4] = L.a4;
-    lc[5] = lon_p1(L, tt, N - 1);                                              // terminal speed of the cost (fp.py:724)
-    pi_hold[tid] = L.hold;
-    if (brake_blk) {                                                           // one lateral profile per brake horizon (fp.py:480-482)
-      const Lat Lb = lat_solve(fs, fs[3], P.Tb[k_lo + tid], P.inv5b + 9 * (k_lo + tid), true, P.n_steps_b[k_lo + tid]);
-      double* c = labc + kLabC * tid;
-      c[0] = Lb.a0; c[1] = Lb.a1; c[2] = Lb.a2; c[3] = Lb.a3; c[4] = Lb.a4; c[5] = Lb.a5;
-      c[6] = 0.0; c[7] = 0.0; c[8] = 0.0;
-    }
-  }
-  if (!brake_blk && tid == bd - 1) {
-    // d_i(t) = A(t) + d_i * B(t): the quintic's right-hand side is linear in the target (fp.py:676-683)
-    const double T = P.T[jT];
-    const double* Ai = P.inv5 + 9 * jT;
-    const double a0 = fs[3], a1 = fs[4], a2 = fs[5] / 2.0;
-    const double r0 = -a0 - a1 * T - a2 * T * T, r1 = -a1 - 2.0 * a2 * T, r2 = -2.0 * a2;
-    double* c = labc;
-    c[0] = a0; c[1] = a1; c[2] = a2;
-    c[3] = fma(r2, Ai[2], fma(r1, Ai[1], r0 * Ai[0]));
-    c[4] = fma(r2, Ai[5], fma(r1, Ai[4], r0 * Ai[3]));
-    c[5] = fma(r2, Ai[8], fma(r1, Ai[7], r0 * Ai[6]));
-    c[6] = Ai[0]; c[7] = Ai[3]; c[8] = Ai[6];
-  }
-  __syncthreads();
-
-  // lateral basis table and the items' reference points
-  const int n_lat = brake_blk ? n_k : 1;
-  for (int idx = tid; idx < n_lat * N; idx += bd) {
-    const int lt = idx / N, n = idx - lt * N;
-    const int hold = brake_blk ? P.n_steps_b[k_lo + lt] : N - 1;
-    const double t = tt[kTT * min(n, hold)];
-    const double* c = labc + kLabC * lt;
-    // Horner with running derivatives, A: a0..c5, B: b3..b5 (B has no terms below t^3)
-    double pA = fma(c[5], t, c[4]), dA = c[5], ddA;
-    ddA = dA;               dA = fma(dA, t, pA);  pA = fma(pA, t, c[3]);
-    ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c[2]);
-    ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c[1]);
-    ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c[0]);
-    double pB = fma(c[8], t, c[7]), dB = c[8], ddB;
-    ddB = dB;               dB = fma(dB, t, pB);  pB = fma(pB, t, c[6]);
-    ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
-    ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
-    ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
-    const bool held = n > hold;                                                // fp.py:487-499 brake padding
-    double* r = lab + ((size_t)lt * NT + n) * kLabW;
-    r[0] = pA; r[1] = pB;
-    r[2] = held ? 0.0 : dA;        r[3] = held ? 0.0 : dB;
-    r[4] = held ? 0.0 : 2.0 * ddA; r[5] = held ? 0.0 : 2.0 * ddB;
-  }
+  // ---- phase B: one item per thread ---------------------------------------------------------------
   const int n_items = n_k * N;
   const bool active = tid < n_items;
   const int p = active ? tid / N : -1;                                         // pair slot of this item
   const int n = active ? tid - p * N : 0;                                      // its sample
   double i_rx = 0, i_ry = 0, i_cth = 0, i_sth = 0, i_rk = 0, i_rdk = 0, i_sd = 0, i_sdd = 0, i_isd = 0;
+  double A0 = 0, B0 = 0, A1 = 0, B1 = 0, A2 = 0, B2 = 0;
   if (active) {
+    // quartic solve of the item's own pair (fp.py:619-647) -- a dozen flops, cheaper than a barrier
     Lon L;
-    const double* lc = lonc + 6 * p;
-    L.a0 = lc[0]; L.a1 = lc[1]; L.a2 = lc[2]; L.a3 = lc[3]; L.a4 = lc[4]; L.hold = pi_hold[p];
-    const double s = lon_p0(L, tt, n);
-    i_sd = lon_p1(L, tt, n);
-    i_sdd = lon_p2(L, tt, n);
+    if (!brake_blk)
+      L = lon_solve(fs, B.v_grid[(size_t)q * B.n_v_max + k_lo + p], P.T[jT], P.inv4 + 4 * jT, n_v == 1, N - 1);
+    else
+      L = lon_solve(fs, 0.0, P.Tb[k_lo + p], P.inv4b + 4 * (k_lo + p), true, P.n_steps_b[k_lo + p]);
+    const bool held = n > L.hold;                                              // fp.py:487-499 brake padding
+    const TPow tp = tpow(held ? L.hold : n, dt);
+    const double s = L.a0 + L.a1 * tp.t + L.a2 * tp.t2 + L.a3 * tp.t3 + L.a4 * tp.t4;             // fp.py:644
+    i_sd = held ? 0.0 : L.a1 + 2.0 * L.a2 * tp.t + 3.0 * L.a3 * tp.t2 + 4.0 * L.a4 * tp.t3;      // fp.py:645
+    i_sdd = held ? 0.0 : 2.0 * L.a2 + 6.0 * L.a3 * tp.t + 12.0 * L.a4 * tp.t2;                    // fp.py:646
     const RefFast rp = spline_ref_fast(V, s);
     i_rx = rp.rx; i_ry = rp.ry; i_cth = rp.cth; i_sth = rp.sth; i_rk = rp.rk; i_rdk = rp.rdk;
     i_isd = fabs(i_sd) > 1e-3 ? 1.0 / i_sd : 0.0;                              // fp.py:792 EPS_S_DOT
-    double* r = ref + ((size_t)p * NT + n) * kRefW;
-    r[0] = i_rx; r[1] = i_ry; r[2] = i_cth; r[3] = i_sth; r[4] = i_rk; r[5] = s; r[6] = i_isd; r[7] = i_rdk;
+    // lateral basis at this sample: d_i(t) = A(t) + d_i * B(t) (the quintic's right-hand side is linear
+    // in the target, fp.py:676-683); Horner with running derivatives
+    double c0, c1, c2, c3, c4, c5, b3, b4, b5;
+    if (!brake_blk) {
+      const double T = P.T[jT];
+      const double* Ai = P.inv5 + 9 * jT;
+      c0 = fs[3]; c1 = fs[4]; c2 = fs[5] / 2.0;
+      const double r0 = -c0 - c1 * T - c2 * T * T, r1 = -c1 - 2.0 * c2 * T, r2 = -2.0 * c2;
+      c3 = fma(r2, Ai[2], fma(r1, Ai[1], r0 * Ai[0]));
+      c4 = fma(r2, Ai[5], fma(r1, Ai[4], r0 * Ai[3]));
+      c5 = fma(r2, Ai[8], fma(r1, Ai[7], r0 * Ai[6]));
+      b3 = Ai[0]; b4 = Ai[3]; b5 = Ai[6];
+    } else {                                                                   // one lateral profile per brake horizon (fp.py:480-482)
+      const Lat Lb = lat_solve(fs, fs[3], P.Tb[k_lo + p], P.inv5b + 9 * (k_lo + p), true, P.n_steps_b[k_lo + p]);
+      c0 = Lb.a0; c1 = Lb.a1; c2 = Lb.a2; c3 = Lb.a3; c4 = Lb.a4; c5 = Lb.a5;
+      b3 = b4 = b5 = 0.0;
+    }
+    {
+      const double t = tp.t;
+      double pA = fma(c5, t, c4), dA = c5, ddA;
+      ddA = dA;               dA = fma(dA, t, pA);  pA = fma(pA, t, c3);
+      ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c2);
+      ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c1);
+      ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c0);
+      double pB = fma(b5, t, b4), dB = b5, ddB;
+      ddB = dB;               dB = fma(dB, t, pB);  pB = fma(pB, t, b3);
+      ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
+      ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
+      ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
+      A0 = pA; B0 = pB;
+      A1 = held ? 0.0 : dA;        B1 = held ? 0.0 : dB;
+      A2 = held ? 0.0 : 2.0 * ddA; B2 = held ? 0.0 : 2.0 * ddB;
+    }
+    double* r = row + ((size_t)p * NT + n) * kRowW;
+    r[0] = i_rx; r[1] = i_ry; r[2] = i_cth; r[3] = i_sth; r[4] = i_rk; r[5] = s; r[6] = i_isd; r[7] = i_sd;
+    r[8] = A0; r[9] = B0; r[10] = A1; r[11] = B1;
     if (i_rx != i_rx || i_ry != i_ry) atomicMin(&pi_fn[p], n);                 // fp.py:851-866
+    if (n == N - 1) sdl[p] = i_sd;                                             // terminal speed of the cost (fp.py:724)
   }
-  __syncthreads();
-
-  // ---- phase 1: validity chain, thread = item, loop = lateral targets --------------------------
-  const int fn = active ? pi_fn[p] : 0;
-  const int keep = fn == 0x7fffffff ? N : (fn >= 2 ? fn : 0);                  // fp.py:866
-  const bool valid = active && n < keep;
-  const bool chk = valid && n >= 1;                                            // limits skip index 0 (fp.py:964-983)
-  const double* lim = B.limits + 4 * (size_t)q;
-  const double vmax = lim[0], amax = lim[1], kmax = lim[2], latmax = lim[3];
-  const double vmax2 = vmax * vmax;
-  const double road_thr = P.cfg.max_road_width + 1e-9;                         // fp.py:982
-  const double tele_thr = fmax(vmax, P.cfg.max_speed) * P.cfg.dt * 3.0;        // fp.py:955
-  const double tele2 = tele_thr * tele_thr;
-  const double stop_dist = B.stop_dist[q];
-  const bool want_vlast = (stop_dist == stop_dist) && valid && n == keep - 1;
-  const int lt_own = brake_blk ? (active ? p : 0) : 0;
-  const double* labr = lab + ((size_t)lt_own * NT + n) * kLabW;
-  const double A0 = labr[0], B0 = labr[1], A1 = labr[2], B1 = labr[3], A2 = labr[4], B2 = labr[5];
-  const double* labp = n >= 1 ? labr - kLabW : labr;
-  const double Ap = labp[0], Bp = labp[1];
-  const double* refp = ref + ((size_t)(active ? p : 0) * NT + (n >= 1 ? n - 1 : n)) * kRefW;
-  const double rxp = chk ? refp[0] : i_rx, ryp = chk ? refp[1] : i_ry, cthp = chk ? refp[2] : i_cth, sthp = chk ? refp[3] : i_sth;
-  const double sd2 = i_sd * i_sd, isd2 = i_isd * i_isd;
-  const unsigned keepmask = chk ? 0xffu : F_DROP;                              // at n = 0 only the drop guards apply
-  const unsigned segmask = __match_any_sync(0xffffffffu, p);
-  const bool seg_leader = (__ffs(segmask) - 1) == lane;
-  const double kTan01Sq = 0.010067046422495888;                                // tan(0.1)^2
-  unsigned* flags_p = flags + (size_t)(active ? p : 0) * G.nw4;
-
-  for (int i0 = 0; i0 < n_dl; i0 += 4) {
-    unsigned acc = 0u;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u;
-      if (i < n_dl && valid) {
-        const double di = brake_blk ? 0.0 : dgrid[i];
-        const double d = fma(di, B0, A0), d1 = fma(di, B1, A1), d2 = fma(di, B2, A2);
-        const double dprev = fma(di, Bp, Ap);
-        const double qq = fma(-i_rk, d, 1.0);                                  // 1 - kappa_r d
-        const double x = fma(-i_sth, d, i_rx), y = fma(i_cth, d, i_ry);        // cc.py:131-132
-        const double xp = fma(-sthp, dprev, rxp), yp = fma(cthp, dprev, ryp);
-        const double ex = x - xp, ey = y - yp;
-        const double step2 = fma(ex, ex, ey * ey);                             // fp.py:954 (squared)
-        const double dpr = d1 * i_isd;                                         // d' (fp.py:792-799)
-        const double dpp = (d2 - dpr * i_sdd) * isd2;                          // d''
-        const double h2 = fma(qq, qq, dpr * dpr);
-        const double rh = rsqrt_nr(h2);
-        const double h = h2 * rh;                                              // hypot(q, d') = q / cos(delta)
-        const double m = fma(i_rdk, d, i_rk * dpr);                            // kappa_r' d + kappa_r d'
-        const double kap = fma(fma(dpp, qq, m * dpr) * rh, rh, i_rk) * rh;     // cc.py:144-147
-        const double v2 = sd2 * h2;                                            // v^2 (cc.py:150-152)
-        const double t2 = fma(dpr, fma(h, kap, -i_rk), -m);
-        const double aq = h * fma(sd2, t2, i_sdd * qq);                        // a * q (cc.py:155-157)
-        const bool fast = v2 > 0.25;                                           // v > 0.5 (fp.py:1019)
-        const double akap = fabs(kap);
-        unsigned f = 0u;
-        f |= ((qq <= 0.05) & (fabs(qq) < INFINITY)) ? F_DROP : 0u;             // fp.py:826-833
-        f |= !(fabs(v2) + fabs(aq) + akap < INFINITY) ? F_DROP : 0u;           // fp.py:944-946
-        f |= (step2 > tele2) ? F_DROP : 0u;                                    // fp.py:953-956
-        f |= (v2 > vmax2) ? F_SPEED : 0u;                                      // fp.py:964
-        f |= (fabs(aq) > amax * qq) ? F_ACCEL : 0u;                            // fp.py:966
-        f |= (fast & (akap > kmax)) ? F_CURV : 0u;                             // fp.py:1020
-        f |= (v2 * akap > latmax) ? F_LAT : 0u;                                // fp.py:975
-        f |= (fabs(d) > road_thr) ? F_ROAD : 0u;                               // fp.py:982
-        if (chk & !fast & !(f & F_CURV)) {                                     // low-speed regime fp.py:1022-1032
-          const double* rp1 = ref + ((size_t)p * NT + n - 1) * kRefW;
-          const double s_now = rp1[kRefW + 5], s_prev = rp1[5];
-          if (fabs(d - dprev) > fmax(1.5 * fabs(s_now - s_prev), 0.02)) {
-            f |= F_CURV;
-          } else {
-            // |wrap(yaw_n - yaw_{n-1})| is the angle between the heading vectors u = R(theta_r)(q, d')
-            const double q_prev = fma(-rp1[4], dprev, 1.0);
-            const double dp_prev = fma(di, labr[3 - kLabW], labr[2 - kLabW]) * rp1[6];
-            const double ux = i_cth * qq - i_sth * dpr, uy = i_sth * qq + i_cth * dpr;
-            const double uxp = cthp * q_prev - sthp * dp_prev, uyp = sthp * q_prev + cthp * dp_prev;
-            const double cr = uxp * uy - uyp * ux, dt_ = uxp * ux + uyp * uy;
-            if (kmax * kmax * step2 <= 0.01) {
-              // the threshold is the 0.1 rad floor: angle > 0.1 <=> dot <= 0 or cross^2 > tan(0.1)^2 dot^2
-              if (dt_ <= 0.0 || cr * cr > kTan01Sq * dt_ * dt_) f |= F_CURV;
-            } else if (fabs(atan2(cr, dt_)) > kmax * sqrt(step2)) {
-              f |= F_CURV;
-            }
-          }
-        }
-        acc |= (f & keepmask) << (8 * u);
-        if (want_vlast) vlast[(size_t)p * n_d + i] = v2;
-      }
+  // box of the block's reference points (for the obstacle lists), fp32 rounded outward
+  if (has_dyn || M > 0) {
+    const bool ok = active && i_rx == i_rx && i_ry == i_ry;
+    float xlo = ok ? __double2float_rd(i_rx) : INFINITY, xhi = ok ? __double2float_ru(i_rx) : -INFINITY;
+    float ylo = ok ? __double2float_rd(i_ry) : INFINITY, yhi = ok ? __double2float_ru(i_ry) : -INFINITY;
+    for (int off = 16; off > 0; off >>= 1) {
+      xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, off)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, off));
+      ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, off)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, off));
     }
-    const unsigned red = __reduce_or_sync(segmask, acc);
-    if (seg_leader && active && red) atomicOr(&flags_p[i0 >> 2], red);
-  }
-  // Samples beyond the NaN prefix that are inside the spline domain again still count for the
-  // candidate-wide singularity guard (fp.py:826-833 runs before the truncation).  Essentially never.
-  if (active && !valid && i_rx == i_rx && keep > 0) {
-    for (int i = 0; i < n_dl; ++i) {
-      const double qq = fma(-i_rk, fma(brake_blk ? 0.0 : dgrid[i], B0, A0), 1.0);
-      if ((qq <= 0.05) & (fabs(qq) < INFINITY)) atomicOr(&flags_p[i >> 2], F_DROP << (8 * (i & 3)));
+    if (lane == 0 && xlo <= xhi) {
+      atomicMin(&s_box[0], f2ord(xlo)); atomicMax(&s_box[1], f2ord(xhi));
+      atomicMin(&s_box[2], f2ord(ylo)); atomicMax(&s_box[3], f2ord(yhi));
     }
   }
-  __syncthreads();
-
-  // ---- phase 2: collision (fp.py:1035-1233) -------------------------------------------------
-  for (int c = tid; c < n_cand; c += bd) {
-    const int cp = c / n_dl, ci = c - cp * n_dl;
-    const unsigned byte = (flags[(size_t)cp * G.nw4 + (ci >> 2)] >> (8 * (ci & 3))) & 0xffu;
-    const int cfn = pi_fn[cp];
-    if (byte == 0u && (cfn == 0x7fffffff || cfn >= 2)) atomicOr(&cleanw[(size_t)cp * G.nwc + (ci >> 5)], 1u << (ci & 31));
-  }
-  __syncthreads();
-  const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
-  const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
-  const int n_circ = P.cfg.n_circles;
-  double max_off = 0.0;                                  // footprint circles sit within max|offset| of the path point
-  for (int i = 0; i < n_circ; ++i) max_off = fmax(max_off, fabs(P.cfg.circle_offsets[i]));
-  bool pair_clean = false;
-  if (valid)
-    for (int w = 0; w < G.nwc; ++w) pair_clean |= cleanw[(size_t)p * G.nwc + w] != 0u;
-  int qsel = 0;
-
-  // exact test of queue entry (item, obstacle) against every live clean candidate of the item's pair
-  auto process = [&](int it, double ox, double oy, int oj, double r2, bool budget) {
-    const int ep = it / N, en = it - ep * N;
-    const double* r = ref + ((size_t)ep * NT + en) * kRefW;
-    const double* l = lab + ((size_t)(brake_blk ? ep : 0) * NT + en) * kLabW;
-    const double rx = r[0], ry = r[1], cth = r[2], sth = r[3];
-    const double a0 = l[0], b0 = l[1];
-    for (int w = 0; w < G.nwc; ++w) {
-      unsigned mbits = cleanw[(size_t)ep * G.nwc + w];
-      if (!budget) mbits &= ~hitw[(size_t)ep * G.nwc + w];
-      while (mbits) {
-        const int bit = __ffs(mbits) - 1;
-        mbits &= mbits - 1u;
-        const int i = w * 32 + bit;
-        const double di = brake_blk ? 0.0 : dgrid[i];
-        const double d = fma(di, b0, a0);
-        const double x = fma(-sth, d, rx), y = fma(cth, d, ry);
-        bool hit = false;
-        if (n_circ == 0) {
-          const double dx = x - ox, dy = y - oy;
-          hit = dx * dx + dy * dy <= r2;                                       // fp.py:1196-1198, :1231-1233
-        } else {                                                               // fp.py:1158-1167
-          const double dpr = fma(di, l[3], l[2]) * r[6];
-          const double qq = fma(-r[4], d, 1.0);
-          const double rh = 1.0 / sqrt(fma(qq, qq, dpr * dpr));
-          const double hx = (cth * qq - sth * dpr) * rh, hy = (sth * qq + cth * dpr) * rh;   // (cos yaw, sin yaw)
-          for (int ci = 0; ci < n_circ && !hit; ++ci) {
-            const double dx = (x + P.cfg.circle_offsets[ci] * hx) - ox, dy = (y + P.cfg.circle_offsets[ci] * hy) - oy;
-            hit = dx * dx + dy * dy <= r2;
-          }
-        }
-        if (hit) {
-          if (!budget) atomicOr(&hitw[(size_t)ep * G.nwc + w], 1u << bit);
-          else { const int sidx = oj / B.P; atomicOr(&viol[((size_t)ep * n_d + i) * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
-        }
-      }
-    }
-  };
-
-  // one obstacle set: `n_obs` obstacles, obstacle j of item (pair, n) at src[j * stride + koff(n)]
-  auto run_set = [&](const double2* src, int n_obs, int stride, bool timed, bool check_bad, double r2, bool budget) {
-    const double rc = sqrt(r2) * (1.0 + 1e-9) + 1e-9 + max_off;
-    const double wc = fmax(P.cfg.max_road_width + 1e-9, fabs(fs[3])) + rc;
-    const int koff = timed ? kobs[n] : 0;
-    const bool cull = valid && pair_clean;
-    for (int j0 = 0; j0 < n_obs; j0 += G.ochunk) {
-      const int j1 = min(n_obs, j0 + G.ochunk);
-      if (cull) {
-        const double2* sp = src + (size_t)j0 * stride + koff;
-#pragma unroll 4
-        for (int j = j0; j < j1; ++j, sp += stride) {
-          const double2 o = *sp;
-          const double ex = o.x - i_rx, ey = o.y - i_ry;
-          const double al = fma(ex, i_cth, ey * i_sth), ac = fma(ey, i_cth, -(ex * i_sth));
-          if ((fabs(al) <= rc) & (fabs(ac) <= wc)) {                           // NaN -> false
-            if (check_bad && ((bad[j >> 5] >> (j & 31)) & 1u)) continue;       // fp.py:1211-1222 NaN trajectory
-            const int slot = atomicAdd(&s_qcount[qsel], 1);
-            if (slot < G.qcap) queue[slot] = ((unsigned)tid << 16) | (unsigned)(j - j0);
-            else process(tid, o.x, o.y, j, r2, budget);                        // queue full: test right here
-          }
-        }
-      }
-      __syncthreads();
-      const int cnt = min(s_qcount[qsel], G.qcap);
-      if (tid == 0) s_qcount[qsel ^ 1] = 0;
-      for (int e = tid; e < cnt; e += bd) {
-        const unsigned ent = queue[e];
-        const int it = (int)(ent >> 16), j = j0 + (int)(ent & 0xffffu);
-        const int en = it % N;
-        const double2 o = src[(size_t)j * stride + (timed ? kobs[en] : 0)];
-        process(it, o.x, o.y, j, r2, budget);
-      }
-      qsel ^= 1;
-      if (j1 < n_obs && !budget) {
-        // leave early once every clean candidate of the block has its decisive hit
-        bool alive = false;
-        if (tid < n_k * G.nwc) alive = (cleanw[tid] & ~hitw[tid]) != 0u;
-        if (!__syncthreads_or(alive ? 1 : 0)) break;
-      } else {
-        __syncthreads();
-      }
-    }
-  };
-
-  if (B.n_static > 0 && B.static_raw) {
-    const int qs = B.static_per_query ? q : 0;
-    run_set(reinterpret_cast<const double2*>(B.static_raw) + (size_t)qs * B.n_static, B.n_static, 1, false, false,
-            P.cfg.collide_r2, false);
-  }
-  if (has_dyn) {
-    if (G.stage_dyn) {
-      mbar_wait(&s_bar, 0u);
-      // NaN-trajectory rule (fp.py:1211-1222): np.min/np.max over a trajectory with a NaN anywhere is
-      // NaN, the AABB overlap test is then False and that pedestrian never collides.
-      for (int e = tid; e < SP * B.T_obs; e += bd) {
-        const double2 o = dynst[e];
-        if (o.x != o.x || o.y != o.y) { const int j = e / B.T_obs; atomicOr(&bad[j >> 5], 1u << (j & 31)); s_anybad = 1; }
-      }
-      __syncthreads();
-    } else if (tid == 0) {
-      int any = 0;
-      for (int i = 0; i < G.n_bad; ++i) any |= bad[i] != 0u;
-      s_anybad = any;
-    }
-    if (!G.stage_dyn) __syncthreads();
-    const bool check_bad = s_anybad != 0;
-    const bool budget = dist_mode && max_viol > 0;
-    run_set(G.stage_dyn ? dynst : dyn_q, SP, B.T_obs, true, check_bad,
-            dist_mode ? P.cfg.collide_r2 : P.cfg.collide_r2_single, budget);   // fp.py:1099-1104
-  }
-
-  // ---- cost pieces: jerk sums in NumPy's pairwise order, 8 lanes per profile (fp.py:718-722) ----
+  // cost pieces: jerk sums in NumPy's pairwise order, 8 lanes per profile (fp.py:718-722)
   {
     const int n_prof = n_k + (brake_blk ? n_k : n_d);
     const int sub = tid & 7;
@@ -585,9 +390,14 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       const int pr = pr0 + (tid >> 3);
       if (pr < n_k) {                                    // longitudinal
         Lon L;
-        const double* lc = lonc + 6 * pr;
-        L.a0 = lc[0]; L.a1 = lc[1]; L.a2 = lc[2]; L.a3 = lc[3]; L.a4 = lc[4]; L.hold = pi_hold[pr];
-        auto jerk2 = [&](int k) { const double j = lon_p3(L, tt, k); return j * j; };
+        if (!brake_blk)
+          L = lon_solve(fs, B.v_grid[(size_t)q * B.n_v_max + k_lo + pr], P.T[jT], P.inv4 + 4 * jT, n_v == 1, N - 1);
+        else
+          L = lon_solve(fs, 0.0, P.Tb[k_lo + pr], P.inv4b + 4 * (k_lo + pr), true, P.n_steps_b[k_lo + pr]);
+        auto jerk2 = [&](int k) {                        // fp.py:647, :722
+          const double j = k > L.hold ? 0.0 : 6.0 * L.a3 + 24.0 * L.a4 * ((double)k * dt);
+          return j * j;
+        };
         const double sres = np_sum_8lanes(jerk2, N, sub, gmask);
         if (sub == 0) js[pr] = sres;
       } else if (pr < n_prof) {                          // lateral
@@ -595,15 +405,319 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
         Lat L;
         if (brake_blk) L = lat_solve(fs, fs[3], P.Tb[k_lo + li], P.inv5b + 9 * (k_lo + li), true, P.n_steps_b[k_lo + li]);
         else L = lat_solve(fs, dgrid[li], P.T[jT], P.inv5 + 9 * jT, n_d == 1, N - 1);
-        auto jerk2 = [&](int k) { const double j = lat_p3(L, tt, k); return j * j; };
+        auto jerk2 = [&](int k) {                        // fp.py:691, :718
+          const double t = (double)k * dt;
+          const double j = k > L.hold ? 0.0 : 6.0 * L.a3 + 24.0 * L.a4 * t + 60.0 * L.a5 * (t * t);
+          return j * j;
+        };
         const double sres = np_sum_8lanes(jerk2, N, sub, gmask);
-        if (sub == 0) { jp[li] = sres; dend[li] = lat_p0(L, tt, N - 1); }
+        if (sub == 0) {
+          jp[li] = sres;
+          const TPow te = tpow(min(N - 1, L.hold), dt);
+          dend[li] = L.a0 + L.a1 * te.t + L.a2 * te.t2 + L.a3 * te.t3 + L.a4 * te.t4 + L.a5 * te.t5;   // fp.py:688, :719
+        }
       }
     }
   }
   __syncthreads();
 
-  // ---- phase 3: category, cost, block arg-min, histogram ----------------------------------------
+  // ---- phase C: obstacle lists; validity chain, thread = item, loop = lateral targets -------------
+  const int fn = active ? pi_fn[p] : 0;
+  const int keep = fn == 0x7fffffff ? N : (fn >= 2 ? fn : 0);                  // fp.py:866
+  const bool valid = active && n < keep;
+  const bool chk = valid && n >= 1;                                            // limits skip index 0 (fp.py:964-983)
+  const int n_circ = P.cfg.n_circles;
+  double max_off = 0.0;                                  // footprint circles sit within max|offset| of the path point
+  for (int i = 0; i < n_circ; ++i) max_off = fmax(max_off, fabs(P.cfg.circle_offsets[i]));
+  const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
+  const double r2_dyn = dist_mode ? P.cfg.collide_r2 : P.cfg.collide_r2_single;   // fp.py:1099-1104, :1173
+  const double rc_s = sqrt(P.cfg.collide_r2) * (1.0 + 1e-9) + 1e-9 + max_off;
+  const double rc_d = sqrt(r2_dyn) * (1.0 + 1e-9) + 1e-9 + max_off;
+  const double wroad = fmax(P.cfg.max_road_width + 1e-9, fabs(fs[3]));
+  if (has_dyn || M > 0) {
+    // keep the obstacles whose (trajectory) box meets the box of the reference points padded by the
+    // widest reach of a clean candidate; a NaN box (fp.py:1211-1222) fails every comparison
+    const float pad = __double2float_ru(wroad + fmax(rc_s, rc_d));
+    const float bx0 = __fsub_rd(ord2f(s_box[0]), pad), bx1 = __fadd_ru(ord2f(s_box[1]), pad);
+    const float by0 = __fsub_rd(ord2f(s_box[2]), pad), by1 = __fadd_ru(ord2f(s_box[3]), pad);
+    if (s_box[0] != 0xffffffffu) {
+      for (int j = tid; j < M; j += bd) {
+        const double2 o = stat_q[j];
+        if (o.x >= (double)bx0 && o.x <= (double)bx1 && o.y >= (double)by0 && o.y <= (double)by1) {
+          const int slot = atomicAdd(&s_nlist[0], 1);
+          olist[slot] = (unsigned short)j;
+        }
+      }
+      const float4* boxes = B.dyn_box + (size_t)q * SP;
+      for (int j = tid; j < SP; j += bd) {
+        const float4 ob = boxes[j];                       // xmin xmax ymin ymax
+        if (ob.x <= bx1 && ob.y >= bx0 && ob.z <= by1 && ob.w >= by0) {
+          const int slot = atomicAdd(&s_nlist[1], 1);
+          olist[M + slot] = (unsigned short)j;
+        }
+      }
+    }
+  }
+  const double* lim = B.limits + 4 * (size_t)q;
+  const double inf = INFINITY;
+  // squared limits; a negative limit rejects every checked sample, as `x > negative` does in the reference
+  double vmax2 = lim[0] < 0.0 ? -inf : lim[0] * lim[0];
+  double amax2 = lim[1] < 0.0 ? -inf : lim[1] * lim[1];
+  double kmax2 = lim[2] < 0.0 ? -inf : lim[2] * lim[2];
+  double latmax2 = lim[3] < 0.0 ? -inf : lim[3] * lim[3];
+  double road_thr = P.cfg.max_road_width + 1e-9;                               // fp.py:982
+  const double tele_thr = fmax(lim[0], P.cfg.max_speed) * dt * 3.0;            // fp.py:955
+  double tele2 = tele_thr * tele_thr;
+  double fast2 = 0.25;                                                         // v > 0.5 (fp.py:1019)
+  if (!chk) { vmax2 = amax2 = kmax2 = latmax2 = road_thr = tele2 = inf; fast2 = -inf; }   // n = 0: only the drop guards apply
+  const double stop_dist = B.stop_dist[q];
+  // per-item affine coefficients in d_i
+  const double* rown = row + ((size_t)(active ? p : 0) * NT + n) * kRowW;
+  const double* rowp = chk ? rown - kRowW : rown;
+  const double sd2 = i_sd * i_sd, isd2 = i_isd * i_isd;
+  const double Q0 = fma(-i_rk, A0, 1.0), Q1 = -(i_rk * B0);                    // q = 1 - kappa_r d
+  const double P0 = A1 * i_isd, P1 = B1 * i_isd;                               // d' (fp.py:792-799)
+  const double R0 = (A2 - P0 * i_sdd) * isd2, R1 = (B2 - P1 * i_sdd) * isd2;   // d''
+  const double M0 = fma(i_rdk, A0, i_rk * P0), M1 = fma(i_rdk, B0, i_rk * P1); // kappa_r' d + kappa_r d'
+  const double S0 = i_sdd * Q0, S1 = i_sdd * Q1;                               // s_ddot q
+  // step vector to the previous sample (x = rx - sin d, y = ry + cos d; cc.py:131-132)
+  const double E0x = (i_rx - rowp[0]) - (i_sth * A0 - rowp[3] * rowp[8]), E1x = -(i_sth * B0 - rowp[3] * rowp[9]);
+  const double E0y = (i_ry - rowp[1]) + (i_cth * A0 - rowp[2] * rowp[8]), E1y = i_cth * B0 - rowp[2] * rowp[9];
+  const unsigned segmask = __match_any_sync(0xffffffffu, p);
+  const bool seg_leader = (__ffs(segmask) - 1) == lane;
+  const double kTan01Sq = 0.010067046422495888;                                // tan(0.1)^2
+  unsigned* flags_p = flags + (size_t)(active ? p : 0) * G.nw4;
+
+  const double sd4 = sd2 * sd2;
+  unsigned anyslow = 0u;
+  // one candidate sample, straight-line: flags of candidate i0 + U into byte U of acc
+  auto sample = [&](double di, unsigned& acc, unsigned sh) {
+    const double d = fma(di, B0, A0), qq = fma(di, Q1, Q0), dpr = fma(di, P1, P0), dpp = fma(di, R1, R0);
+    const double m = fma(di, M1, M0), sq = fma(di, S1, S0), ex = fma(di, E1x, E0x), ey = fma(di, E1y, E0y);
+    const double h2 = fma(qq, qq, dpr * dpr);                                  // hypot(q, d')^2 = (q / cos delta)^2
+    const double w = fma(i_rk, h2, fma(dpp, qq, m * dpr));                     // kappa h^3   (cc.py:144-147)
+    const double h6 = h2 * h2 * h2;
+    const double w2 = w * w;
+    const double v2 = sd2 * h2;                                                // v^2         (cc.py:150-152)
+    const double T = fma(dpr, fma(-i_rk, h2, w), -(m * h2));
+    const double Z = fma(sd2, T, sq * h2);                                     // a h q       (cc.py:155-157)
+    const double step2 = fma(ex, ex, ey * ey);                                 // fp.py:954 (squared)
+    const double fin = fabs(Z) + fabs(w) + h6;
+    const double acc_rhs = amax2 * (qq * qq * h2), curv_rhs = kmax2 * h6, lat_lhs = sd4 * w2, lat_rhs = latmax2 * h2;
+    const double Z2 = Z * Z;
+    asm("{\n .reg .pred p, f;\n .reg .f64 t;\n"
+        " abs.f64 t, %2;\n setp.lt.f64 p, t, 0d7FF0000000000000;\n setp.le.and.f64 p, %2, 0d3FA999999999999A, p;\n"   // q <= 0.05 and finite (fp.py:826-833)
+        " setp.geu.or.f64 p, %3, 0d7FF0000000000000, p;\n"                      // non-finite v / a / kappa (fp.py:944-946)
+        " setp.gt.or.f64 p, %4, %5, p;\n"                                       // teleport (fp.py:953-956)
+        " @p or.b32 %0, %0, %6;\n"
+        " setp.gt.f64 f, %7, %8;\n"                                             // v > 0.5 (fp.py:1019)
+        " @!f or.b32 %1, %1, 1;\n"
+        " setp.gt.and.f64 p, %9, %10, f;\n"                                     // |kappa| > k_max when fast (fp.py:1020)
+        " @p or.b32 %0, %0, %11;\n"
+        "}"
+        : "+r"(acc), "+r"(anyslow)
+        : "d"(qq), "d"(fin), "d"(step2), "d"(tele2), "r"(F_DROP << sh), "d"(v2), "d"(fast2), "d"(w2), "d"(curv_rhs), "r"(F_CURV << sh));
+    flag_gt(acc, v2, vmax2, F_SPEED << sh);                                    // fp.py:964
+    flag_gt(acc, Z2, acc_rhs, F_ACCEL << sh);                                  // fp.py:966
+    flag_gt(acc, lat_lhs, lat_rhs, F_LAT << sh);                               // fp.py:975  v^2 |kappa| > a_lat
+    flag_abs_gt(acc, d, road_thr, F_ROAD << sh);                               // fp.py:982
+  };
+  for (int i0 = 0; i0 < n_dl; i0 += 4) {
+    unsigned acc = 0u;
+    if (valid) {
+      if (brake_blk) {
+        sample(0.0, acc, 0u);
+      } else if (i0 + 4 <= n_dl) {
+        const double g0 = dgrid[i0], g1 = dgrid[i0 + 1], g2 = dgrid[i0 + 2], g3 = dgrid[i0 + 3];
+        sample(g0, acc, 0u); sample(g1, acc, 8u); sample(g2, acc, 16u); sample(g3, acc, 24u);
+      } else {
+        for (int u = 0; i0 + u < n_dl; ++u) sample(dgrid[i0 + u], acc, 8u * u);
+      }
+    }
+    const unsigned red = __reduce_or_sync(segmask, acc);
+    if (seg_leader && active && red) atomicOr(&flags_p[i0 >> 2], red);
+  }
+  // Low-speed regime (fp.py:1022-1032): items that saw a candidate with v <= 0.5 queue up; the block
+  // redoes the two low-speed tests for them in phase D, one (item, candidate) unit per thread.
+  if (anyslow) slowq[atomicAdd(&s_nslow, 1)] = (unsigned short)tid;
+  // Samples beyond the NaN prefix that are inside the spline domain again still count for the
+  // candidate-wide singularity guard (fp.py:826-833 runs before the truncation).  Essentially never.
+  if (active && !valid && i_rx == i_rx && keep > 0) {
+    for (int i = 0; i < n_dl; ++i) {
+      const double qq = fma(brake_blk ? 0.0 : dgrid[i], Q1, Q0);
+      if ((qq <= 0.05) & (fabs(qq) < inf)) atomicOr(&flags_p[i >> 2], F_DROP << (8 * (i & 3)));
+    }
+  }
+  // stop-distance directive (fp.py:307-324) needs v at the last kept sample
+  if (stop_dist == stop_dist && valid && n == keep - 1) {
+    for (int i = 0; i < n_dl; ++i) {
+      const double di = brake_blk ? 0.0 : dgrid[i];
+      const double qq = fma(di, Q1, Q0), dpr = fma(di, P1, P0);
+      vlast[(size_t)p * n_d + i] = sd2 * fma(qq, qq, dpr * dpr);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase D: collision (fp.py:1035-1233) --------------------------------------------------------
+  const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
+  const bool budget = dist_mode && max_viol > 0;
+  const int n_ls = s_nlist[0], n_ld = s_nlist[1];
+  if (G.stage_dyn) mbar_wait(&s_bar, 0u);             // always: the copy must have landed before the block can exit
+  {
+    const double2* dsrc = G.stage_dyn ? dynst : dyn_q;
+    // low-speed tests of unit (queued item, candidate i): lateral step vs longitudinal step, heading
+    // change vs the 0.1 rad / kappa_max * step floor (fp.py:1022-1032), from the item rows
+    auto slow_unit = [&](int it, int i) {
+      const int sp = it / N, sn = it - sp * N;
+      const double* r1 = row + ((size_t)sp * NT + sn) * kRowW;                 // sample n
+      const double* r0 = r1 - kRowW;                                           // sample n - 1 (only checked samples queue)
+      const double di = brake_blk ? 0.0 : dgrid[i];
+      const double d = fma(di, r1[9], r1[8]), dprev = fma(di, r0[9], r0[8]);
+      const double qq = fma(-r1[4], d, 1.0), dpr = fma(di, r1[11], r1[10]) * r1[6];
+      const double ssd = r1[7];
+      if (ssd * ssd * fma(qq, qq, dpr * dpr) > 0.25) return;                   // this candidate is in the fast regime here
+      bool badc;
+      if (fabs(d - dprev) > fmax(1.5 * fabs(r1[5] - r0[5]), 0.02)) {
+        badc = true;
+      } else {
+        // |wrap(yaw_n - yaw_{n-1})| is the angle between the heading vectors u = R(theta_r)(q, d')
+        const double kmax = lim[2];
+        const double q_prev = fma(-r0[4], dprev, 1.0);
+        const double dp_prev = fma(di, r0[11], r0[10]) * r0[6];
+        const double ux = r1[2] * qq - r1[3] * dpr, uy = r1[3] * qq + r1[2] * dpr;
+        const double uxp = r0[2] * q_prev - r0[3] * dp_prev, uyp = r0[3] * q_prev + r0[2] * dp_prev;
+        const double cr = uxp * uy - uyp * ux, dt_ = uxp * ux + uyp * uy;
+        const double ex = fma(-r1[3], d, r1[0]) - fma(-r0[3], dprev, r0[0]);
+        const double ey = fma(r1[2], d, r1[1]) - fma(r0[2], dprev, r0[1]);
+        const double step2 = fma(ex, ex, ey * ey);
+        if (kmax * kmax * step2 <= 0.01)
+          // the threshold is the 0.1 rad floor: angle > 0.1 <=> dot <= 0 or cross^2 > tan(0.1)^2 dot^2
+          badc = dt_ <= 0.0 || cr * cr > kTan01Sq * dt_ * dt_;
+        else
+          badc = fabs(atan2(cr, dt_)) > kmax * sqrt(step2);
+      }
+      if (badc) atomicOr(&flags[(size_t)sp * G.nw4 + (i >> 2)], F_CURV << (8 * (i & 3)));
+    };
+
+    bool pair_clean = false;
+    if (valid && n_ls + n_ld > 0)
+      for (int w = 0; w < G.nwc; ++w) pair_clean |= clean_word(flags_p, G.nw4, n_dl, w) != 0u;
+    const bool cull = valid && pair_clean;
+    const int kob = B.T_obs > 0 ? min(n, B.T_obs - 1) : 0;                     // clip(round(t/dt)) = n (fp.py:1226-1227)
+    // tangent-frame window: along = (o - ref).t, across = (o - ref).n
+    const double ca = fma(i_rx, i_cth, i_ry * i_sth), cn = fma(i_ry, i_cth, -(i_rx * i_sth));
+    const double wc_s = wroad + rc_s, wc_d = wroad + rc_d;
+    int qsel = 0;
+
+    // exact test of entry (item, obstacle) against every live clean candidate of the item's pair.
+    // (Candidates the low-speed pass rejects in the same round may still be tested: harmless, the
+    // curvature category outranks the collision category.)
+    auto process = [&](int it, int e) {
+      const int ep = it / N, en = it - ep * N;
+      const bool is_dyn = e >= n_ls;
+      const int j = is_dyn ? olist[M + e - n_ls] : olist[e];
+      const double2 o = is_dyn ? dsrc[(size_t)j * B.T_obs + (B.T_obs > 0 ? min(en, B.T_obs - 1) : 0)] : stat_q[j];
+      const double r2 = is_dyn ? r2_dyn : P.cfg.collide_r2;
+      const bool use_budget = budget && is_dyn;
+      const double* r = row + ((size_t)ep * NT + en) * kRowW;
+      const double cth = r[2], sth = r[3];
+      const double X0 = fma(-sth, r[8], r[0]) - o.x, X1 = -(sth * r[9]);       // x - ox = X0 + d_i X1
+      const double Y0 = fma(cth, r[8], r[1]) - o.y, Y1 = cth * r[9];
+      const unsigned* fl = flags + (size_t)ep * G.nw4;
+      for (int w = 0; w < G.nwc; ++w) {
+        unsigned mbits = clean_word(fl, G.nw4, n_dl, w);
+        if (!use_budget) mbits &= ~hitw[(size_t)ep * G.nwc + w];
+        while (mbits) {
+          const int bit = __ffs(mbits) - 1;
+          mbits &= mbits - 1u;
+          const int i = w * 32 + bit;
+          const double di = brake_blk ? 0.0 : dgrid[i];
+          bool hit = false;
+          if (n_circ == 0) {
+            const double dx = fma(di, X1, X0), dy = fma(di, Y1, Y0);
+            hit = dx * dx + dy * dy <= r2;                                     // fp.py:1196-1198, :1231-1233
+          } else {                                                             // fp.py:1158-1167
+            const double d = fma(di, r[9], r[8]);
+            const double dpr = fma(di, r[11], r[10]) * r[6];
+            const double qq = fma(-r[4], d, 1.0);
+            const double rh = 1.0 / sqrt(fma(qq, qq, dpr * dpr));
+            const double hx = (cth * qq - sth * dpr) * rh, hy = (sth * qq + cth * dpr) * rh;   // (cos yaw, sin yaw)
+            for (int ci = 0; ci < n_circ && !hit; ++ci) {
+              const double dx = fma(di, X1, X0) + P.cfg.circle_offsets[ci] * hx, dy = fma(di, Y1, Y0) + P.cfg.circle_offsets[ci] * hy;
+              hit = dx * dx + dy * dy <= r2;
+            }
+          }
+          if (hit) {
+            if (!use_budget) atomicOr(&hitw[(size_t)ep * G.nwc + w], 1u << bit);
+            else { const int sidx = j / B.P; atomicOr(&viol[((size_t)ep * n_d + i) * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
+          }
+        }
+      }
+    };
+
+    // window test of this item against list entries [ea, eb) of one kind; survivors -> queue
+    auto cull_range = [&](auto dyn_tag, int ea, int eb, int e0) {
+      constexpr bool kDyn = decltype(dyn_tag)::value;
+      const double rc = kDyn ? rc_d : rc_s, wc = kDyn ? wc_d : wc_s;
+      const unsigned short* lst = kDyn ? olist + M - n_ls : olist;             // entry e -> lst[e]
+      for (int e32 = ea; e32 < eb; e32 += 32) {
+        const int ee = min(eb, e32 + 32);
+        unsigned rel = 0u, bit = 1u;
+#pragma unroll 4
+        for (int e = e32; e < ee; ++e, bit <<= 1) {
+          const int j = lst[e];
+          const double2 o = kDyn ? dsrc[(size_t)j * B.T_obs + kob] : stat_q[j];
+          const double al = fma(o.x, i_cth, fma(o.y, i_sth, -ca));
+          const double ac = fma(o.y, i_cth, fma(-o.x, i_sth, -cn));
+          if ((fabs(al) <= rc) & (fabs(ac) <= wc)) rel |= bit;                 // NaN -> false
+        }
+        while (rel) {
+          const int e = e32 + __ffs(rel) - 1;
+          rel &= rel - 1u;
+          const int slot = atomicAdd(&s_qcount[qsel], 1);
+          if (slot < G.qcap) queue[slot] = ((unsigned)tid << 16) | (unsigned)(e - e0);
+          else process(tid, e);                                                // queue full: test right here
+        }
+      }
+    };
+
+    const int n_l = n_ls + n_ld;
+    int e0 = 0;
+    do {                                                 // at least one round: it also drains the low-speed queue
+      const int e1 = min(n_l, e0 + G.ochunk);
+      if (cull) {
+        if (e0 < n_ls) cull_range(std::false_type{}, e0, min(e1, n_ls), e0);
+        if (e1 > n_ls) cull_range(std::true_type{}, max(e0, n_ls), e1, e0);
+      }
+      __syncthreads();
+      const int cnt = min(s_qcount[qsel], G.qcap);
+      if (tid == 0) s_qcount[qsel ^ 1] = 0;
+      if (e0 == 0) {
+        const int n_units = s_nslow * n_dl;
+        for (int u = tid; u < n_units; u += bd) { const int k = u / n_dl; slow_unit(slowq[k], u - k * n_dl); }
+      }
+      for (int k = tid; k < cnt; k += bd) {
+        const unsigned ent = queue[k];
+        process((int)(ent >> 16), e0 + (int)(ent & 0xffffu));
+      }
+      qsel ^= 1;
+      e0 = e1;
+      if (e1 < n_l && !budget) {
+        // leave early once every clean candidate of the block has its decisive hit
+        bool alive = false;
+        if (tid < n_k * G.nwc) {
+          const int ap = tid / G.nwc, aw = tid - ap * G.nwc;
+          const int afn = pi_fn[ap];
+          alive = (afn == 0x7fffffff || afn >= 2) && (clean_word(flags + (size_t)ap * G.nw4, G.nw4, n_dl, aw) & ~hitw[tid]) != 0u;
+        }
+        if (!__syncthreads_or(alive ? 1 : 0)) break;
+      } else {
+        __syncthreads();
+      }
+    } while (e0 < n_l);
+  }
+
+  // ---- phase E: category, cost, block arg-min, histogram ----------------------------------------
   double my_cost = INFINITY;
   int my_idx = 0x7fffffff;
   for (int c = tid; c < n_cand; c += bd) {
@@ -613,9 +727,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     const double Jp = jp[li], d_end = dend[li];
     const double Jd = d_end * d_end;
     const double Js = js[cp];
-    const double dv = B.target[q] - lonc[6 * cp + 5];
+    const double dv = B.target[q] - sdl[cp];
     const double Jv = dv * dv;
-    const double Jt = tt[kTT * (N - 1)];
+    const double Jt = (double)(N - 1) * dt;
     const double lat_cost = P.cfg.k_j * Jp + P.cfg.k_t * Jt + P.cfg.k_d * Jd;
     const double lon_cost = P.cfg.k_j * Js + P.cfg.k_t * Jt + P.cfg.k_s_dot * Jv;
     const double cost = P.cfg.k_lat * lat_cost + P.cfg.k_lon * lon_cost;
@@ -642,7 +756,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
         cat = FOT_CAT_OK;
         if (stop_dist == stop_dist) {                                          // fp.py:307-324
           const double v_last = sqrt(vlast[(size_t)cp * n_d + ci]);
-          const double s_span = ref[((size_t)cp * NT + ckeep - 1) * kRefW + 5] - ref[(size_t)cp * NT * kRefW + 5];
+          const double s_span = row[((size_t)cp * NT + ckeep - 1) * kRowW + 5] - row[(size_t)cp * NT * kRowW + 5];
           if (!(v_last <= 0.15 && s_span <= stop_dist + 1e-6)) cat = FOT_CAT_STOP;
         }
       }
@@ -668,22 +782,32 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   if (tid < FOT_N_STATS && s_stats[tid] != 0) atomicAdd(&O.stats[(size_t)q * FOT_N_STATS + tid], s_stats[tid]);
 }
 
-// NaN-trajectory bitmap for obstacle fields too large to stage in shared memory: one warp per
-// predicted trajectory, bit j of bad[q] set when any of its samples is NaN (fp.py:1211-1222).
-__global__ void fot_bad_prepass(const double2* __restrict__ dyn, unsigned* __restrict__ bad, int n_q, int SP,
-                                int T_obs, int n_bad) {
+// Boxes of the predicted trajectories, once per launch: one warp per trajectory (q, sample, ped),
+// (xmin, xmax, ymin, ymax) over all its steps rounded outward to fp32.  A NaN anywhere makes the
+// whole box NaN, which fails every overlap test: exactly the reference's prefilter, whose np.min /
+// np.max propagate the NaN and thereby remove that pedestrian from the test (fp.py:1211-1222).
+__global__ void fot_aabb_prepass(const double2* __restrict__ dyn, float4* __restrict__ box, long long n_traj, int T_obs) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= (long long)n_q * SP) return;
-  const int q = (int)(warp / SP), j = (int)(warp % SP);
+  if (warp >= n_traj) return;
   const double2* src = dyn + (size_t)warp * T_obs;
-  bool b = false;
+  double xlo = INFINITY, xhi = -INFINITY, ylo = INFINITY, yhi = -INFINITY;
+  bool bad = false;
   for (int k = lane; k < T_obs; k += 32) {
     const double2 o = src[k];
-    b |= (o.x != o.x) || (o.y != o.y);
+    bad |= (o.x != o.x) || (o.y != o.y);
+    xlo = fmin(xlo, o.x); xhi = fmax(xhi, o.x); ylo = fmin(ylo, o.y); yhi = fmax(yhi, o.y);
   }
-  b = __any_sync(0xffffffffu, b);
-  if (lane == 0 && b) atomicOr(&bad[(size_t)q * n_bad + (j >> 5)], 1u << (j & 31));
+  for (int off = 16; off > 0; off >>= 1) {
+    xlo = fmin(xlo, __shfl_xor_sync(0xffffffffu, xlo, off)); xhi = fmax(xhi, __shfl_xor_sync(0xffffffffu, xhi, off));
+    ylo = fmin(ylo, __shfl_xor_sync(0xffffffffu, ylo, off)); yhi = fmax(yhi, __shfl_xor_sync(0xffffffffu, yhi, off));
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    const float nanf_ = __int_as_float(0x7fc00000);
+    box[warp] = bad ? make_float4(nanf_, nanf_, nanf_, nanf_)
+                    : make_float4(__double2float_rd(xlo), __double2float_ru(xhi), __double2float_rd(ylo), __double2float_ru(yhi));
+  }
 }
 
 }  // namespace fot
