@@ -248,7 +248,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B, nx = h->plan.cfg.nx;
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const long long SPl = has_dyn ? (long long)b->S * b->P : 0;
-  if (NT > kItemThreads || nd > 8192 || SPl > 32768 || b->n_static > 32768) return false;
+  if (NT > 128 || nd > 8192 || SPl > 32768 || b->n_static > 32768) return false;   // 128: one NumPy pairwise block
   const int SP = (int)SPl;
   const int ppc_max = kItemThreads / NT;
   ItemGeom G{};
@@ -258,6 +258,18 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   G.ppb = nB > 0 ? std::min(nB, ppc_max) : 0;
   G.brake_blocks = nB > 0 ? (nB + G.ppb - 1) / G.ppb : 0;
   G.blocks_per_query = G.grid_blocks + G.brake_blocks;
+  // blocks per CTA: a whole query per CTA once the batch alone fills the GPU several times over,
+  // one block per CTA for single plan() calls
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const long long total = (long long)b->n_q * G.blocks_per_query;
+    long long bpc = total / ((long long)sms * 2 * 4);
+    bpc = std::max<long long>(1, std::min<long long>(bpc, G.blocks_per_query));
+    if (const char* env = getenv("FOT_BPC")) bpc = std::max(1, std::min(atoi(env), (int)G.blocks_per_query));
+    G.ctas_per_query = (int)((G.blocks_per_query + bpc - 1) / bpc);
+    G.bpc = (G.blocks_per_query + G.ctas_per_query - 1) / G.ctas_per_query;
+  }
   G.pcap = std::max(G.ppc, std::max(G.ppb, 1));
   G.threads = (G.pcap * NT + 31) / 32 * 32;
   G.jcap = std::max(nd, G.ppb);
@@ -340,7 +352,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
     int rc = sweep_geometry(h, b, &g, &smem);
     if (rc != FOT_OK) return rc;
   } else {
-    g.blocks_per_query = ig.blocks_per_query;   // fot_winner reads the partials
+    g.blocks_per_query = ig.ctas_per_query;     // fot_winner reads one partial per CTA
   }
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const size_t n_part = (size_t)b->n_q * g.blocks_per_query;

@@ -4,7 +4,9 @@
 // every query, per-block arg-min partials out, no trajectory written to HBM.  The work is laid out
 // the other way round:
 //
-//   block  = (query, horizon T_j, chunk of terminal speeds)  -- or the query's brake ladder
+//   block  = (query, horizon T_j, chunk of terminal speeds)  -- or the query's brake ladder;
+//            a CTA sweeps `bpc` consecutive blocks of one query (all of them in large batches), so
+//            the obstacle staging, the spline tables and the arg-min / histogram are per CTA
 //   thread = one (terminal speed v_k, sample t_n) "item": everything that depends on the
 //            longitudinal profile only -- s(t_n), the spline reference point, heading, curvature,
 //            1/s_dot -- is computed ONCE per item and lives in registers;
@@ -57,6 +59,8 @@ struct ItemGeom {
   int32_t ppb;               // brake horizons per brake block
   int32_t brake_blocks;
   int32_t blocks_per_query;
+  int32_t bpc;               // blocks swept by one CTA (consecutive blocks of one query)
+  int32_t ctas_per_query;    // ceil(blocks_per_query / bpc)
   int32_t threads;           // block size (multiple of 32, >= items of the largest block)
   int32_t pcap;              // max(ppc, ppb): per-pair table slots
   int32_t jcap;              // max(n_d, ppb): lateral jerk-sum slots
@@ -135,10 +139,8 @@ __device__ __forceinline__ TPow tpow(int n, double dt) {
 // group: lane a owns accumulator r_a, the combine tree and the sequential tail are NumPy's.
 template <class F>
 __device__ __forceinline__ double np_sum_8lanes(const F& f, int n, int sub, unsigned gmask) {
-  double res;
-  if (n > 128) {
-    res = np_pairwise_sum(f, 0, n);          // rare: long time grids, every lane does the serial sum
-  } else if (n < 8) {
+  double res;                                // n <= 128 (item_geometry sends longer time grids to fot_sweep)
+  if (n < 8) {
     res = 0.0;
     for (int i = 0; i < n; ++i) res += f(i);
   } else {
@@ -218,16 +220,52 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   __shared__ __align__(8) uint64_t s_bar;
 
   const int NT = P.n_t_max;
-  const int q = blockIdx.x / G.blocks_per_query;
-  const int b = blockIdx.x - q * G.blocks_per_query;
+  const int q = blockIdx.x / G.ctas_per_query;
+  const int cta = blockIdx.x - q * G.ctas_per_query;
   const int tid = threadIdx.x, lane = tid & 31, bd = blockDim.x;
   const double* fs = B.frenet + 6 * (size_t)q;
   const int n_v = B.n_v[q];
   const int n_d = P.cfg.n_d;
   const double dt = P.cfg.dt;
-  const bool brake_blk = b >= G.grid_blocks;
-  const size_t part = (size_t)q * G.blocks_per_query + b;
+  const size_t part = (size_t)q * G.ctas_per_query + cta;
+  const int b_first = cta * G.bpc, b_last = min(G.blocks_per_query, b_first + G.bpc);
+  // A non-finite Frenet state makes every sample of every candidate non-finite: the reference drops
+  // them all silently (empty / non-finite guards fp.py:933-946).
+  const bool state_ok = fabs(fs[0]) + fabs(fs[1]) + fabs(fs[2]) + fabs(fs[3]) + fabs(fs[4]) + fabs(fs[5]) < INFINITY;
 
+  const bool has_dyn = B.dyn_raw != nullptr;
+  const int SP = has_dyn ? B.S * B.P : 0;
+  const int M = B.static_raw ? B.n_static : 0;
+  const double2* dyn_q = has_dyn ? reinterpret_cast<const double2*>(B.dyn_raw) + (size_t)q * SP * B.T_obs : nullptr;
+  const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
+
+  // ---- once per CTA: obstacle block in flight, grids and spline tables in shared memory ----------
+  if (tid == 0 && G.stage_dyn && state_ok) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)SP * (uint32_t)B.T_obs * 16u;
+    mbar_expect_tx(&s_bar, bytes);
+    tma_bulk_g2s(smb + G.o_dyn, dyn_q, bytes, &s_bar);
+  }
+  if (tid < FOT_N_STATS) s_stats[tid] = 0;
+  for (int i = tid; i < n_d; i += bd) dgrid[i] = P.d_grid[i];
+  if (G.spline_smem) {
+    const int nx = P.cfg.nx;
+    for (int i = tid; i < nx; i += bd) {
+      spl[i] = P.knots[i];
+      spl[nx + i] = P.xa[i];      spl[3 * nx + i] = P.xc[i];
+      spl[5 * nx + i] = P.ya[i];  spl[7 * nx + i] = P.yc[i];
+      if (i < nx - 1) {
+        spl[2 * nx + i] = P.xb[i]; spl[4 * nx + i] = P.xd[i];
+        spl[6 * nx + i] = P.yb[i]; spl[8 * nx + i] = P.yd[i];
+      }
+    }
+  }
+  double my_cost = INFINITY;            // running arg-min over every block this CTA sweeps
+  int my_idx = 0x7fffffff;
+
+  for (int b = b_first; b < b_last; ++b) {
+  const bool brake_blk = b >= G.grid_blocks;
   // ---- which pairs does this block own? -----------------------------------------------------
   int jT = 0, k_lo = 0, n_k = 0, N = 0, n_dl = 0;
   if (!brake_blk) {
@@ -245,65 +283,24 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     N = P.cfg.n_total;
     n_dl = 1;
   }
-  if (n_k <= 0) {                                        // uniform per block
-    if (tid == 0) { O.part_cost[part] = INFINITY; O.part_idx[part] = -1; }
-    return;
-  }
+  if (n_k <= 0) continue;                                // uniform per block
   const int n_cand = n_k * n_dl;
   const int cand0 = brake_blk ? P.cfg.n_T * n_v * n_d + k_lo : (jT * n_v + k_lo) * n_d;   // generation order (fp.py:398-449)
-  // A non-finite Frenet state makes every sample of every candidate non-finite: the reference drops
-  // them all silently (empty / non-finite guards fp.py:933-946).
-  const bool state_ok = fabs(fs[0]) + fabs(fs[1]) + fabs(fs[2]) + fabs(fs[3]) + fabs(fs[4]) + fabs(fs[5]) < INFINITY;
   if (!state_ok) {
     for (int c = tid; c < n_cand; c += bd) {
       if (O.cand_cat) O.cand_cat[(size_t)q * O.cand_stride + cand0 + c] = (uint8_t)FOT_CAT_DROP;
       if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + cand0 + c] = qnan();
     }
-    if (tid == 0) { O.part_cost[part] = INFINITY; O.part_idx[part] = -1; }
-    return;
+    continue;
   }
 
-  const bool has_dyn = B.dyn_raw != nullptr;
-  const int SP = has_dyn ? B.S * B.P : 0;
-  const int M = B.static_raw ? B.n_static : 0;
-  const double2* dyn_q = has_dyn ? reinterpret_cast<const double2*>(B.dyn_raw) + (size_t)q * SP * B.T_obs : nullptr;
-  const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
-
-  // ---- phase A: shared-memory set-up ------------------------------------------------------------
+  // ---- phase A: per-block shared-memory state ------------------------------------------------------
   if (tid == 0) {
     s_qcount[0] = 0; s_qcount[1] = 0; s_nlist[0] = 0; s_nlist[1] = 0; s_nslow = 0;
     s_box[0] = 0xffffffffu; s_box[1] = 0u; s_box[2] = 0xffffffffu; s_box[3] = 0u;
-    if (G.stage_dyn) {
-      mbar_init(&s_bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      const uint32_t bytes = (uint32_t)SP * (uint32_t)B.T_obs * 16u;
-      mbar_expect_tx(&s_bar, bytes);
-      tma_bulk_g2s(smb + G.o_dyn, dyn_q, bytes, &s_bar);
-    }
   }
-  if (tid < FOT_N_STATS) s_stats[tid] = 0;
   if (tid < G.pcap) pi_fn[tid] = 0x7fffffff;
   for (int i = tid; i < G.n_zero; i += bd) flags[i] = 0u;          // flags | hit words | violation bitmaps
-  for (int i = tid; i < n_d; i += bd) dgrid[i] = P.d_grid[i];
-  SplineView V;
-  V.nx = P.cfg.nx;
-  if (G.spline_smem) {
-    const int nx = V.nx;
-    for (int i = tid; i < nx; i += bd) {
-      spl[i] = P.knots[i];
-      spl[nx + i] = P.xa[i];      spl[3 * nx + i] = P.xc[i];
-      spl[5 * nx + i] = P.ya[i];  spl[7 * nx + i] = P.yc[i];
-      if (i < nx - 1) {
-        spl[2 * nx + i] = P.xb[i]; spl[4 * nx + i] = P.xd[i];
-        spl[6 * nx + i] = P.yb[i]; spl[8 * nx + i] = P.yd[i];
-      }
-    }
-    V.knots = spl; V.xa = spl + nx; V.xb = spl + 2 * nx; V.xc = spl + 3 * nx; V.xd = spl + 4 * nx;
-    V.ya = spl + 5 * nx; V.yb = spl + 6 * nx; V.yc = spl + 7 * nx; V.yd = spl + 8 * nx;
-  } else {
-    V.knots = P.knots; V.xa = P.xa; V.xb = P.xb; V.xc = P.xc; V.xd = P.xd;
-    V.ya = P.ya; V.yb = P.yb; V.yc = P.yc; V.yd = P.yd;
-  }
   __syncthreads();
 
   // ---- phase B: one item per thread ---------------------------------------------------------------
@@ -325,6 +322,16 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     const double s = L.a0 + L.a1 * tp.t + L.a2 * tp.t2 + L.a3 * tp.t3 + L.a4 * tp.t4;             // fp.py:644
     i_sd = held ? 0.0 : L.a1 + 2.0 * L.a2 * tp.t + 3.0 * L.a3 * tp.t2 + 4.0 * L.a4 * tp.t3;      // fp.py:645
     i_sdd = held ? 0.0 : 2.0 * L.a2 + 6.0 * L.a3 * tp.t + 12.0 * L.a4 * tp.t2;                    // fp.py:646
+    SplineView V;
+    V.nx = P.cfg.nx;
+    if (G.spline_smem) {
+      const int nx = V.nx;
+      V.knots = spl; V.xa = spl + nx; V.xb = spl + 2 * nx; V.xc = spl + 3 * nx; V.xd = spl + 4 * nx;
+      V.ya = spl + 5 * nx; V.yb = spl + 6 * nx; V.yc = spl + 7 * nx; V.yd = spl + 8 * nx;
+    } else {
+      V.knots = P.knots; V.xa = P.xa; V.xb = P.xb; V.xc = P.xc; V.xd = P.xd;
+      V.ya = P.ya; V.yb = P.yb; V.yc = P.yc; V.yd = P.yd;
+    }
     const RefFast rp = spline_ref_fast(V, s);
     i_rx = rp.rx; i_ry = rp.ry; i_cth = rp.cth; i_sth = rp.sth; i_rk = rp.rk; i_rdk = rp.rdk;
     i_isd = fabs(i_sd) > 1e-3 ? 1.0 / i_sd : 0.0;                              // fp.py:792 EPS_S_DOT
@@ -361,7 +368,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       A1 = held ? 0.0 : dA;        B1 = held ? 0.0 : dB;
       A2 = held ? 0.0 : 2.0 * ddA; B2 = held ? 0.0 : 2.0 * ddB;
     }
-    double* r = row + ((size_t)p * NT + n) * kRowW;
+    double* r = row + (p * NT + n) * kRowW;
     r[0] = i_rx; r[1] = i_ry; r[2] = i_cth; r[3] = i_sth; r[4] = i_rk; r[5] = s; r[6] = i_isd; r[7] = i_sd;
     r[8] = A0; r[9] = B0; r[10] = A1; r[11] = B1;
     if (i_rx != i_rx || i_ry != i_ry) atomicMin(&pi_fn[p], n);                 // fp.py:851-866
@@ -370,15 +377,14 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   // box of the block's reference points (for the obstacle lists), fp32 rounded outward
   if (has_dyn || M > 0) {
     const bool ok = active && i_rx == i_rx && i_ry == i_ry;
-    float xlo = ok ? __double2float_rd(i_rx) : INFINITY, xhi = ok ? __double2float_ru(i_rx) : -INFINITY;
-    float ylo = ok ? __double2float_rd(i_ry) : INFINITY, yhi = ok ? __double2float_ru(i_ry) : -INFINITY;
-    for (int off = 16; off > 0; off >>= 1) {
-      xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, off)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, off));
-      ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, off)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, off));
-    }
-    if (lane == 0 && xlo <= xhi) {
-      atomicMin(&s_box[0], f2ord(xlo)); atomicMax(&s_box[1], f2ord(xhi));
-      atomicMin(&s_box[2], f2ord(ylo)); atomicMax(&s_box[3], f2ord(yhi));
+    // ordered-uint encoding, warp min / max by redux, one atomic per warp and bound
+    const unsigned xlo = __reduce_min_sync(0xffffffffu, ok ? f2ord(__double2float_rd(i_rx)) : 0xffffffffu);
+    const unsigned xhi = __reduce_max_sync(0xffffffffu, ok ? f2ord(__double2float_ru(i_rx)) : 0u);
+    const unsigned ylo = __reduce_min_sync(0xffffffffu, ok ? f2ord(__double2float_rd(i_ry)) : 0xffffffffu);
+    const unsigned yhi = __reduce_max_sync(0xffffffffu, ok ? f2ord(__double2float_ru(i_ry)) : 0u);
+    if (lane == 0 && xlo != 0xffffffffu) {
+      atomicMin(&s_box[0], xlo); atomicMax(&s_box[1], xhi);
+      atomicMin(&s_box[2], ylo); atomicMax(&s_box[3], yhi);
     }
   }
   // cost pieces: jerk sums in NumPy's pairwise order, 8 lanes per profile (fp.py:718-722)
@@ -472,7 +478,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   if (!chk) { vmax2 = amax2 = kmax2 = latmax2 = road_thr = tele2 = inf; fast2 = -inf; }   // n = 0: only the drop guards apply
   const double stop_dist = B.stop_dist[q];
   // per-item affine coefficients in d_i
-  const double* rown = row + ((size_t)(active ? p : 0) * NT + n) * kRowW;
+  const double* rown = row + ((active ? p : 0) * NT + n) * kRowW;
   const double* rowp = chk ? rown - kRowW : rown;
   const double sd2 = i_sd * i_sd, isd2 = i_isd * i_isd;
   const double Q0 = fma(-i_rk, A0, 1.0), Q1 = -(i_rk * B0);                    // q = 1 - kappa_r d
@@ -486,7 +492,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   const unsigned segmask = __match_any_sync(0xffffffffu, p);
   const bool seg_leader = (__ffs(segmask) - 1) == lane;
   const double kTan01Sq = 0.010067046422495888;                                // tan(0.1)^2
-  unsigned* flags_p = flags + (size_t)(active ? p : 0) * G.nw4;
+  unsigned* flags_p = flags + (active ? p : 0) * G.nw4;
 
   const double sd4 = sd2 * sd2;
   unsigned anyslow = 0u;
@@ -553,7 +559,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     for (int i = 0; i < n_dl; ++i) {
       const double di = brake_blk ? 0.0 : dgrid[i];
       const double qq = fma(di, Q1, Q0), dpr = fma(di, P1, P0);
-      vlast[(size_t)p * n_d + i] = sd2 * fma(qq, qq, dpr * dpr);
+      vlast[p * n_d + i] = sd2 * fma(qq, qq, dpr * dpr);
     }
   }
   __syncthreads();
@@ -564,12 +570,11 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   const int n_ls = s_nlist[0], n_ld = s_nlist[1];
   if (G.stage_dyn) mbar_wait(&s_bar, 0u);             // always: the copy must have landed before the block can exit
   {
-    const double2* dsrc = G.stage_dyn ? dynst : dyn_q;
     // low-speed tests of unit (queued item, candidate i): lateral step vs longitudinal step, heading
     // change vs the 0.1 rad / kappa_max * step floor (fp.py:1022-1032), from the item rows
     auto slow_unit = [&](int it, int i) {
       const int sp = it / N, sn = it - sp * N;
-      const double* r1 = row + ((size_t)sp * NT + sn) * kRowW;                 // sample n
+      const double* r1 = row + (sp * NT + sn) * kRowW;                 // sample n
       const double* r0 = r1 - kRowW;                                           // sample n - 1 (only checked samples queue)
       const double di = brake_blk ? 0.0 : dgrid[i];
       const double d = fma(di, r1[9], r1[8]), dprev = fma(di, r0[9], r0[8]);
@@ -596,7 +601,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
         else
           badc = fabs(atan2(cr, dt_)) > kmax * sqrt(step2);
       }
-      if (badc) atomicOr(&flags[(size_t)sp * G.nw4 + (i >> 2)], F_CURV << (8 * (i & 3)));
+      if (badc) atomicOr(&flags[sp * G.nw4 + (i >> 2)], F_CURV << (8 * (i & 3)));
     };
 
     bool pair_clean = false;
@@ -616,17 +621,18 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       const int ep = it / N, en = it - ep * N;
       const bool is_dyn = e >= n_ls;
       const int j = is_dyn ? olist[M + e - n_ls] : olist[e];
-      const double2 o = is_dyn ? dsrc[(size_t)j * B.T_obs + (B.T_obs > 0 ? min(en, B.T_obs - 1) : 0)] : stat_q[j];
+      const int ok_ = j * B.T_obs + (B.T_obs > 0 ? min(en, B.T_obs - 1) : 0);
+      const double2 o = is_dyn ? (G.stage_dyn ? dynst[ok_] : dyn_q[ok_]) : stat_q[j];
       const double r2 = is_dyn ? r2_dyn : P.cfg.collide_r2;
       const bool use_budget = budget && is_dyn;
-      const double* r = row + ((size_t)ep * NT + en) * kRowW;
+      const double* r = row + (ep * NT + en) * kRowW;
       const double cth = r[2], sth = r[3];
       const double X0 = fma(-sth, r[8], r[0]) - o.x, X1 = -(sth * r[9]);       // x - ox = X0 + d_i X1
       const double Y0 = fma(cth, r[8], r[1]) - o.y, Y1 = cth * r[9];
-      const unsigned* fl = flags + (size_t)ep * G.nw4;
+      const unsigned* fl = flags + ep * G.nw4;
       for (int w = 0; w < G.nwc; ++w) {
         unsigned mbits = clean_word(fl, G.nw4, n_dl, w);
-        if (!use_budget) mbits &= ~hitw[(size_t)ep * G.nwc + w];
+        if (!use_budget) mbits &= ~hitw[ep * G.nwc + w];
         while (mbits) {
           const int bit = __ffs(mbits) - 1;
           mbits &= mbits - 1u;
@@ -648,16 +654,18 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
             }
           }
           if (hit) {
-            if (!use_budget) atomicOr(&hitw[(size_t)ep * G.nwc + w], 1u << bit);
-            else { const int sidx = j / B.P; atomicOr(&viol[((size_t)ep * n_d + i) * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
+            if (!use_budget) atomicOr(&hitw[ep * G.nwc + w], 1u << bit);
+            else { const int sidx = j / B.P; atomicOr(&viol[(ep * n_d + i) * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
           }
         }
       }
     };
 
     // window test of this item against list entries [ea, eb) of one kind; survivors -> queue
-    auto cull_range = [&](auto dyn_tag, int ea, int eb, int e0) {
+    auto cull_range = [&](auto dyn_tag, auto stage_tag, int ea, int eb, int e0) {
       constexpr bool kDyn = decltype(dyn_tag)::value;
+      constexpr bool kStaged = decltype(stage_tag)::value;
+      const double2* obs_k = (kStaged ? dynst : dyn_q) + kob;                  // this item's time step
       const double rc = kDyn ? rc_d : rc_s, wc = kDyn ? wc_d : wc_s;
       const unsigned short* lst = kDyn ? olist + M - n_ls : olist;             // entry e -> lst[e]
       for (int e32 = ea; e32 < eb; e32 += 32) {
@@ -666,7 +674,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
 #pragma unroll 4
         for (int e = e32; e < ee; ++e, bit <<= 1) {
           const int j = lst[e];
-          const double2 o = kDyn ? dsrc[(size_t)j * B.T_obs + kob] : stat_q[j];
+          const double2 o = kDyn ? obs_k[j * B.T_obs] : stat_q[j];
           const double al = fma(o.x, i_cth, fma(o.y, i_sth, -ca));
           const double ac = fma(o.y, i_cth, fma(-o.x, i_sth, -cn));
           if ((fabs(al) <= rc) & (fabs(ac) <= wc)) rel |= bit;                 // NaN -> false
@@ -686,8 +694,11 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     do {                                                 // at least one round: it also drains the low-speed queue
       const int e1 = min(n_l, e0 + G.ochunk);
       if (cull) {
-        if (e0 < n_ls) cull_range(std::false_type{}, e0, min(e1, n_ls), e0);
-        if (e1 > n_ls) cull_range(std::true_type{}, max(e0, n_ls), e1, e0);
+        if (e0 < n_ls) cull_range(std::false_type{}, std::false_type{}, e0, min(e1, n_ls), e0);
+        if (e1 > n_ls) {
+          if (G.stage_dyn) cull_range(std::true_type{}, std::true_type{}, max(e0, n_ls), e1, e0);
+          else cull_range(std::true_type{}, std::false_type{}, max(e0, n_ls), e1, e0);
+        }
       }
       __syncthreads();
       const int cnt = min(s_qcount[qsel], G.qcap);
@@ -708,7 +719,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
         if (tid < n_k * G.nwc) {
           const int ap = tid / G.nwc, aw = tid - ap * G.nwc;
           const int afn = pi_fn[ap];
-          alive = (afn == 0x7fffffff || afn >= 2) && (clean_word(flags + (size_t)ap * G.nw4, G.nw4, n_dl, aw) & ~hitw[tid]) != 0u;
+          alive = (afn == 0x7fffffff || afn >= 2) && (clean_word(flags + ap * G.nw4, G.nw4, n_dl, aw) & ~hitw[tid]) != 0u;
         }
         if (!__syncthreads_or(alive ? 1 : 0)) break;
       } else {
@@ -718,8 +729,6 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   }
 
   // ---- phase E: category, cost, block arg-min, histogram ----------------------------------------
-  double my_cost = INFINITY;
-  int my_idx = 0x7fffffff;
   for (int c = tid; c < n_cand; c += bd) {
     const int cp = c / n_dl, ci = c - cp * n_dl;
     const int li = brake_blk ? cp : ci;
@@ -733,7 +742,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     const double lat_cost = P.cfg.k_j * Jp + P.cfg.k_t * Jt + P.cfg.k_d * Jd;
     const double lon_cost = P.cfg.k_j * Js + P.cfg.k_t * Jt + P.cfg.k_s_dot * Jv;
     const double cost = P.cfg.k_lat * lat_cost + P.cfg.k_lon * lon_cost;
-    const unsigned byte = (flags[(size_t)cp * G.nw4 + (ci >> 2)] >> (8 * (ci & 3))) & 0xffu;
+    const unsigned byte = (flags[cp * G.nw4 + (ci >> 2)] >> (8 * (ci & 3))) & 0xffu;
     const int cfn = pi_fn[cp];
     const int ckeep = cfn == 0x7fffffff ? N : (cfn >= 2 ? cfn : 0);
     int cat;
@@ -744,10 +753,10 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     else if (byte & F_LAT) cat = FOT_CAT_LAT;
     else if (byte & F_ROAD) cat = FOT_CAT_ROAD;
     else {
-      bool hit = (hitw[(size_t)cp * G.nwc + (ci >> 5)] >> (ci & 31)) & 1u;
+      bool hit = (hitw[cp * G.nwc + (ci >> 5)] >> (ci & 31)) & 1u;
       if (G.vwords > 0) {
         int nv = 0;
-        for (int w = 0; w < G.vwords; ++w) nv += __popc(viol[((size_t)cp * n_d + ci) * G.vwords + w]);
+        for (int w = 0; w < G.vwords; ++w) nv += __popc(viol[(cp * n_d + ci) * G.vwords + w]);
         hit = hit || nv > max_viol;                                            // fp.py:1113-1124
       }
       if (hit) {
@@ -755,8 +764,8 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       } else {
         cat = FOT_CAT_OK;
         if (stop_dist == stop_dist) {                                          // fp.py:307-324
-          const double v_last = sqrt(vlast[(size_t)cp * n_d + ci]);
-          const double s_span = row[((size_t)cp * NT + ckeep - 1) * kRowW + 5] - row[(size_t)cp * NT * kRowW + 5];
+          const double v_last = sqrt(vlast[cp * n_d + ci]);
+          const double s_span = row[(cp * NT + ckeep - 1) * kRowW + 5] - row[cp * NT * kRowW + 5];
           if (!(v_last <= 0.15 && s_span <= stop_dist + 1e-6)) cat = FOT_CAT_STOP;
         }
       }
@@ -767,6 +776,10 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + cand_idx] = cost;
     if (cat == FOT_CAT_OK && cost < INFINITY) argmin_merge(my_cost, my_idx, cost, cand_idx);
   }
+  __syncthreads();                                       // this block's tables are dead; the next block may overwrite them
+  }  // blocks of this CTA
+
+  if (G.stage_dyn && state_ok) mbar_wait(&s_bar, 0u);    // the bulk copy must have landed before the CTA can exit
   for (int off = 16; off > 0; off >>= 1) {
     const double oc = __shfl_down_sync(0xffffffffu, my_cost, off);
     const int oi = __shfl_down_sync(0xffffffffu, my_idx, off);
