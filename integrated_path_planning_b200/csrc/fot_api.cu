@@ -101,6 +101,13 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   for (int j = 0; j < nB; ++j)
     if (tb->n_steps_b[j] + 1 > cfg->n_total) { delete h; return fail(FOT_ERR_ARG, "fot_create: brake horizon longer than max_t"); }
   h->plan.n_t_max = n_t_max;
+  h->plan.d_sorted = 1;
+  h->plan.d_min = h->plan.d_max = tb->d_grid[0];
+  for (int i = 0; i < nd; ++i) {
+    if (i > 0 && !(tb->d_grid[i] >= tb->d_grid[i - 1])) h->plan.d_sorted = 0;
+    h->plan.d_min = std::min(h->plan.d_min, tb->d_grid[i]);
+    h->plan.d_max = std::max(h->plan.d_max, tb->d_grid[i]);
+  }
 
   // one device blob: doubles first, then the int tables
   std::vector<double> dbl;
@@ -250,7 +257,9 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   const long long SPl = has_dyn ? (long long)b->S * b->P : 0;
   if (NT > 128 || nd > 8192 || SPl > 32768 || b->n_static > 32768) return false;   // 128: one NumPy pairwise block
   const int SP = (int)SPl;
-  const int ppc_max = kItemThreads / NT;
+  int max_threads = kItemThreads;
+  if (const char* env = getenv("FOT_ITEM_THREADS")) max_threads = std::max(NT, std::min(kItemThreads, atoi(env)));
+  const int ppc_max = max_threads / NT;
   ItemGeom G{};
   G.chunks = (b->n_v_max + ppc_max - 1) / ppc_max;
   G.ppc = (b->n_v_max + G.chunks - 1) / G.chunks;
@@ -300,7 +309,8 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
     G.o_viol = take((size_t)G.pcap * nd * G.vwords * 4);
     G.n_zero = (int32_t)((off - (size_t)G.o_flags) / 4);
     G.o_queue = take((size_t)G.qcap * 4);
-    G.o_list = take((size_t)G.lcap * 2);
+    G.o_list = take((size_t)G.lcap * 4);
+    G.o_clean = take((size_t)G.pcap * G.nwc * 4);
     G.o_slow = take((size_t)G.threads * 2);
     G.stage_dyn = stage ? 1 : 0;
     return off;
@@ -632,3 +642,14 @@ extern "C" int fot_probe_fma_tflops(int device, int kind, double* tflops_out) {
   *tflops_out = best;
   return FOT_OK;
 }
+
+#ifdef FOT_PHASE_CLOCKS
+// tuning aid: read and reset the per-phase clock accumulators of fot_sweep_items
+extern "C" int fot_debug_phase_clocks(unsigned long long out[16]) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out, fot::g_phase_clk, sizeof(unsigned long long) * 16));
+  unsigned long long z[16] = {};
+  CK(cudaMemcpyToSymbol(fot::g_phase_clk, z, sizeof z));
+  return FOT_OK;
+}
+#endif

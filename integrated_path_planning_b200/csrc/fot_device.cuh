@@ -20,6 +20,8 @@ struct Plan {
   const int32_t *n_steps, *n_steps_b;
   const double *knots, *xa, *xb, *xc, *xd, *ya, *yb, *yc, *yd;
   int32_t n_t_max;
+  int32_t d_sorted;        // d_grid is non-decreasing (the reference's grid always is)
+  double d_min, d_max;     // extreme lateral targets
 };
 
 // One batch, device pointers.

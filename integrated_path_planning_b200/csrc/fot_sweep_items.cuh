@@ -48,6 +48,15 @@
 
 namespace fot {
 
+// Optional phase timeline (tuning only): -DFOT_PHASE_CLOCKS accumulates, per warp, the clock64 span
+// between the kernel's barriers into g_phase_clk[phase] (read back with fot_debug_phase_clocks).
+#ifdef FOT_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define FOT_PHASE_MARK(k) do { const long long t__ = clock64(); if (lane == 0) atomicAdd(&g_phase_clk[k], (unsigned long long)(t__ - t_phase)); t_phase = t__; } while (0)
+#else
+#define FOT_PHASE_MARK(k) do { } while (0)
+#endif
+
 constexpr int kItemThreads = 320;   // largest block of fot_sweep_items
 constexpr int kRowW = 12;           // item row: rx ry cos sin | kappa s 1/s_dot s_dot | A0 B0 A1 B1
 constexpr unsigned F_DROP = 32u;    // silent drop (singular / non-finite / teleport), fp.py:826-833, :944-956
@@ -74,7 +83,7 @@ struct ItemGeom {
   int32_t n_zero;            // u32 words of the zero-initialised region starting at o_flags
   // byte offsets into dynamic shared memory
   int32_t o_row, o_js, o_sdl, o_jp, o_dend, o_dgrid, o_vlast, o_spl, o_dyn;
-  int32_t o_fn, o_flags, o_hit, o_viol, o_queue, o_list, o_slow;
+  int32_t o_fn, o_flags, o_hit, o_viol, o_queue, o_list, o_slow, o_clean;
 };
 
 struct SplineView {
@@ -208,7 +217,8 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   unsigned* hitw = reinterpret_cast<unsigned*>(smb + G.o_hit);      // [pcap][nwc] decisive collision
   unsigned* viol = reinterpret_cast<unsigned*>(smb + G.o_viol);     // [pcap][n_d][vwords]
   unsigned* queue = reinterpret_cast<unsigned*>(smb + G.o_queue);   // [qcap]
-  unsigned short* olist = reinterpret_cast<unsigned short*>(smb + G.o_list);   // [lcap] static entries first
+  unsigned* olist = reinterpret_cast<unsigned*>(smb + G.o_list);   // [lcap] element offsets: static j (first M slots), dynamic j * T_obs
+  unsigned* cleanw = reinterpret_cast<unsigned*>(smb + G.o_clean);  // [pcap][nwc] kinematically clean (phase D)
   unsigned short* slowq = reinterpret_cast<unsigned short*>(smb + G.o_slow);   // [threads] items with a low-speed sample
   __shared__ int s_qcount[2];
   __shared__ int s_nlist[2];            // static / dynamic list lengths
@@ -263,6 +273,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   }
   double my_cost = INFINITY;            // running arg-min over every block this CTA sweeps
   int my_idx = 0x7fffffff;
+#ifdef FOT_PHASE_CLOCKS
+  long long t_phase = clock64();
+#endif
 
   for (int b = b_first; b < b_last; ++b) {
   const bool brake_blk = b >= G.grid_blocks;
@@ -301,7 +314,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   }
   if (tid < G.pcap) pi_fn[tid] = 0x7fffffff;
   for (int i = tid; i < G.n_zero; i += bd) flags[i] = 0u;          // flags | hit words | violation bitmaps
+  FOT_PHASE_MARK(0);
   __syncthreads();
+  FOT_PHASE_MARK(1);
 
   // ---- phase B: one item per thread ---------------------------------------------------------------
   const int n_items = n_k * N;
@@ -425,7 +440,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       }
     }
   }
+  FOT_PHASE_MARK(2);
   __syncthreads();
+  FOT_PHASE_MARK(3);
 
   // ---- phase C: obstacle lists; validity chain, thread = item, loop = lateral targets -------------
   const int fn = active ? pi_fn[p] : 0;
@@ -451,7 +468,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
         const double2 o = stat_q[j];
         if (o.x >= (double)bx0 && o.x <= (double)bx1 && o.y >= (double)by0 && o.y <= (double)by1) {
           const int slot = atomicAdd(&s_nlist[0], 1);
-          olist[slot] = (unsigned short)j;
+          olist[slot] = (unsigned)j;
         }
       }
       const float4* boxes = B.dyn_box + (size_t)q * SP;
@@ -459,7 +476,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
         const float4 ob = boxes[j];                       // xmin xmax ymin ymax
         if (ob.x <= bx1 && ob.y >= bx0 && ob.z <= by1 && ob.w >= by0) {
           const int slot = atomicAdd(&s_nlist[1], 1);
-          olist[M + slot] = (unsigned short)j;
+          olist[M + slot] = (unsigned)(j * B.T_obs);
         }
       }
     }
@@ -467,15 +484,22 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   const double* lim = B.limits + 4 * (size_t)q;
   const double inf = INFINITY;
   // squared limits; a negative limit rejects every checked sample, as `x > negative` does in the reference
-  double vmax2 = lim[0] < 0.0 ? -inf : lim[0] * lim[0];
-  double amax2 = lim[1] < 0.0 ? -inf : lim[1] * lim[1];
-  double kmax2 = lim[2] < 0.0 ? -inf : lim[2] * lim[2];
-  double latmax2 = lim[3] < 0.0 ? -inf : lim[3] * lim[3];
-  double road_thr = P.cfg.max_road_width + 1e-9;                               // fp.py:982
+  // (warp-uniform: pushed through redux so that they live in uniform registers, not in the 96 vector
+  // registers the loop below is short of)
+  auto uni = [&](double x) {
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)__double2loint(x));
+    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)__double2hiint(x));
+    return __hiloint2double((int)hi, (int)lo);
+  };
+  const double vmax2 = uni(lim[0] < 0.0 ? -inf : lim[0] * lim[0]);
+  const double amax2 = uni(lim[1] < 0.0 ? -inf : lim[1] * lim[1]);
+  const double kmax2 = uni(lim[2] < 0.0 ? -inf : lim[2] * lim[2]);
+  const double latmax2 = uni(lim[3] < 0.0 ? -inf : lim[3] * lim[3]);
+  const double road_thr = P.cfg.max_road_width + 1e-9;                         // fp.py:982
   const double tele_thr = fmax(lim[0], P.cfg.max_speed) * dt * 3.0;            // fp.py:955
-  double tele2 = tele_thr * tele_thr;
-  double fast2 = 0.25;                                                         // v > 0.5 (fp.py:1019)
-  if (!chk) { vmax2 = amax2 = kmax2 = latmax2 = road_thr = tele2 = inf; fast2 = -inf; }   // n = 0: only the drop guards apply
+  const double tele2 = uni(tele_thr * tele_thr);
+  const double fast2 = 0.25;                                                   // v > 0.5 (fp.py:1019)
+  const unsigned keep4 = chk ? 0xffffffffu : F_DROP * 0x01010101u;             // n = 0: only the drop guards apply
   const double stop_dist = B.stop_dist[q];
   // per-item affine coefficients in d_i
   const double* rown = row + ((active ? p : 0) * NT + n) * kRowW;
@@ -540,12 +564,12 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
         for (int u = 0; i0 + u < n_dl; ++u) sample(dgrid[i0 + u], acc, 8u * u);
       }
     }
-    const unsigned red = __reduce_or_sync(segmask, acc);
+    const unsigned red = __reduce_or_sync(segmask, acc & keep4);
     if (seg_leader && active && red) atomicOr(&flags_p[i0 >> 2], red);
   }
   // Low-speed regime (fp.py:1022-1032): items that saw a candidate with v <= 0.5 queue up; the block
   // redoes the two low-speed tests for them in phase D, one (item, candidate) unit per thread.
-  if (anyslow) slowq[atomicAdd(&s_nslow, 1)] = (unsigned short)tid;
+  if (anyslow && chk) slowq[atomicAdd(&s_nslow, 1)] = (unsigned short)tid;
   // Samples beyond the NaN prefix that are inside the spline domain again still count for the
   // candidate-wide singularity guard (fp.py:826-833 runs before the truncation).  Essentially never.
   if (active && !valid && i_rx == i_rx && keep > 0) {
@@ -562,7 +586,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       vlast[p * n_d + i] = sd2 * fma(qq, qq, dpr * dpr);
     }
   }
+  FOT_PHASE_MARK(4);
   __syncthreads();
+  FOT_PHASE_MARK(5);
 
   // ---- phase D: collision (fp.py:1035-1233) --------------------------------------------------------
   const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
@@ -574,6 +600,8 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     // change vs the 0.1 rad / kappa_max * step floor (fp.py:1022-1032), from the item rows
     auto slow_unit = [&](int it, int i) {
       const int sp = it / N, sn = it - sp * N;
+      // a candidate that already carries a flag of curvature priority or higher cannot change category
+      if ((flags[sp * G.nw4 + (i >> 2)] >> (8 * (i & 3))) & (F_DROP | F_SPEED | F_ACCEL | F_CURV)) return;
       const double* r1 = row + (sp * NT + sn) * kRowW;                 // sample n
       const double* r0 = r1 - kRowW;                                           // sample n - 1 (only checked samples queue)
       const double di = brake_blk ? 0.0 : dgrid[i];
@@ -604,14 +632,32 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       if (badc) atomicOr(&flags[sp * G.nw4 + (i >> 2)], F_CURV << (8 * (i & 3)));
     };
 
-    bool pair_clean = false;
+    // clean masks: every thread needs its own pair's (cull decision + lateral window); the exact
+    // tests read them from shared memory after the round's barrier
+    unsigned cw_lo = 0u;
+    int i_lo = -1, i_hi = -1;                            // lowest / highest clean candidate of the pair
     if (valid && n_ls + n_ld > 0)
-      for (int w = 0; w < G.nwc; ++w) pair_clean |= clean_word(flags_p, G.nw4, n_dl, w) != 0u;
-    const bool cull = valid && pair_clean;
+      for (int w = 0; w < G.nwc; ++w) {
+        const unsigned cwd = clean_word(flags_p, G.nw4, n_dl, w);
+        if (cwd) { if (i_lo < 0) i_lo = 32 * w + __ffs(cwd) - 1; i_hi = 32 * w + 31 - __clz(cwd); }
+        cw_lo |= cwd;
+      }
+    if (tid < n_k * G.nwc) {
+      const int ap = tid / G.nwc, aw = tid - ap * G.nwc;
+      const int afn = pi_fn[ap];
+      cleanw[tid] = (afn == 0x7fffffff || afn >= 2) ? clean_word(flags + ap * G.nw4, G.nw4, n_dl, aw) : 0u;
+    }
+    const bool cull = valid && cw_lo != 0u;
     const int kob = B.T_obs > 0 ? min(n, B.T_obs - 1) : 0;                     // clip(round(t/dt)) = n (fp.py:1226-1227)
-    // tangent-frame window: along = (o - ref).t, across = (o - ref).n
+    // tangent-frame window: along = (o - ref).t within the collision radius, across = (o - ref).n within
+    // the radius of the lateral offsets the pair's clean candidates take at this sample
     const double ca = fma(i_rx, i_cth, i_ry * i_sth), cn = fma(i_ry, i_cth, -(i_rx * i_sth));
-    const double wc_s = wroad + rc_s, wc_d = wroad + rc_d;
+    double d_lo = A0, d_hi = A0;
+    if (cull && !brake_blk) {
+      const double ga = P.d_sorted ? dgrid[i_lo] : P.d_min, gb = P.d_sorted ? dgrid[i_hi] : P.d_max;
+      d_lo = A0 + fmin(ga * B0, gb * B0) - 1e-9;
+      d_hi = A0 + fmax(ga * B0, gb * B0) + 1e-9;
+    }
     int qsel = 0;
 
     // exact test of entry (item, obstacle) against every live clean candidate of the item's pair.
@@ -620,18 +666,17 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     auto process = [&](int it, int e) {
       const int ep = it / N, en = it - ep * N;
       const bool is_dyn = e >= n_ls;
-      const int j = is_dyn ? olist[M + e - n_ls] : olist[e];
-      const int ok_ = j * B.T_obs + (B.T_obs > 0 ? min(en, B.T_obs - 1) : 0);
-      const double2 o = is_dyn ? (G.stage_dyn ? dynst[ok_] : dyn_q[ok_]) : stat_q[j];
+      const unsigned off = is_dyn ? olist[M + e - n_ls] : olist[e];
+      const unsigned ok_ = off + (unsigned)(B.T_obs > 0 ? min(en, B.T_obs - 1) : 0);
+      const double2 o = is_dyn ? (G.stage_dyn ? dynst[ok_] : dyn_q[ok_]) : stat_q[off];
       const double r2 = is_dyn ? r2_dyn : P.cfg.collide_r2;
       const bool use_budget = budget && is_dyn;
       const double* r = row + (ep * NT + en) * kRowW;
       const double cth = r[2], sth = r[3];
       const double X0 = fma(-sth, r[8], r[0]) - o.x, X1 = -(sth * r[9]);       // x - ox = X0 + d_i X1
       const double Y0 = fma(cth, r[8], r[1]) - o.y, Y1 = cth * r[9];
-      const unsigned* fl = flags + ep * G.nw4;
       for (int w = 0; w < G.nwc; ++w) {
-        unsigned mbits = clean_word(fl, G.nw4, n_dl, w);
+        unsigned mbits = cleanw[ep * G.nwc + w];
         if (!use_budget) mbits &= ~hitw[ep * G.nwc + w];
         while (mbits) {
           const int bit = __ffs(mbits) - 1;
@@ -655,7 +700,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
           }
           if (hit) {
             if (!use_budget) atomicOr(&hitw[ep * G.nwc + w], 1u << bit);
-            else { const int sidx = j / B.P; atomicOr(&viol[(ep * n_d + i) * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
+            else { const int sidx = (int)(off / (unsigned)B.T_obs) / B.P; atomicOr(&viol[(ep * n_d + i) * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
           }
         }
       }
@@ -666,18 +711,18 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       constexpr bool kDyn = decltype(dyn_tag)::value;
       constexpr bool kStaged = decltype(stage_tag)::value;
       const double2* obs_k = (kStaged ? dynst : dyn_q) + kob;                  // this item's time step
-      const double rc = kDyn ? rc_d : rc_s, wc = kDyn ? wc_d : wc_s;
-      const unsigned short* lst = kDyn ? olist + M - n_ls : olist;             // entry e -> lst[e]
+      const double rc = kDyn ? rc_d : rc_s;
+      const double w_lo = d_lo - rc, w_hi = d_hi + rc;
+      const unsigned* lst = kDyn ? olist + M - n_ls : olist;                   // entry e -> lst[e]
       for (int e32 = ea; e32 < eb; e32 += 32) {
         const int ee = min(eb, e32 + 32);
         unsigned rel = 0u, bit = 1u;
 #pragma unroll 4
         for (int e = e32; e < ee; ++e, bit <<= 1) {
-          const int j = lst[e];
-          const double2 o = kDyn ? obs_k[j * B.T_obs] : stat_q[j];
+          const double2 o = kDyn ? obs_k[lst[e]] : stat_q[lst[e]];
           const double al = fma(o.x, i_cth, fma(o.y, i_sth, -ca));
           const double ac = fma(o.y, i_cth, fma(-o.x, i_sth, -cn));
-          if ((fabs(al) <= rc) & (fabs(ac) <= wc)) rel |= bit;                 // NaN -> false
+          if ((fabs(al) <= rc) & (ac >= w_lo) & (ac <= w_hi)) rel |= bit;      // NaN -> false
         }
         while (rel) {
           const int e = e32 + __ffs(rel) - 1;
@@ -700,7 +745,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
           else cull_range(std::true_type{}, std::false_type{}, max(e0, n_ls), e1, e0);
         }
       }
+      FOT_PHASE_MARK(6);
       __syncthreads();
+      FOT_PHASE_MARK(7);
       const int cnt = min(s_qcount[qsel], G.qcap);
       if (tid == 0) s_qcount[qsel ^ 1] = 0;
       if (e0 == 0) {
@@ -717,13 +764,13 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
         // leave early once every clean candidate of the block has its decisive hit
         bool alive = false;
         if (tid < n_k * G.nwc) {
-          const int ap = tid / G.nwc, aw = tid - ap * G.nwc;
-          const int afn = pi_fn[ap];
-          alive = (afn == 0x7fffffff || afn >= 2) && (clean_word(flags + ap * G.nw4, G.nw4, n_dl, aw) & ~hitw[tid]) != 0u;
+          alive = (cleanw[tid] & ~hitw[tid]) != 0u;
         }
         if (!__syncthreads_or(alive ? 1 : 0)) break;
       } else {
+        FOT_PHASE_MARK(8);
         __syncthreads();
+        FOT_PHASE_MARK(9);
       }
     } while (e0 < n_l);
   }
@@ -776,7 +823,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + cand_idx] = cost;
     if (cat == FOT_CAT_OK && cost < INFINITY) argmin_merge(my_cost, my_idx, cost, cand_idx);
   }
+  FOT_PHASE_MARK(10);
   __syncthreads();                                       // this block's tables are dead; the next block may overwrite them
+  FOT_PHASE_MARK(11);
   }  // blocks of this CTA
 
   if (G.stage_dyn && state_ok) mbar_wait(&s_bar, 0u);    // the bulk copy must have landed before the CTA can exit
