@@ -508,11 +508,22 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   CK(h->out_d.reserve(ro));
   char* od = (char*)h->out_d.p;
 
-  // chunking: only worth it when the obstacle upload is large
+  // chunking: only worth it when the obstacle upload is large.  The kernels are the longer leg of the
+  // pipeline (the upload runs at PCIe speed), so the first chunks are small -- the sweep starts after
+  // 1/16 of the upload -- and the rest are large enough to keep the wave tail short.
   int n_chunks = 1;
-  if ((size_t)nq * dyn_q_bytes > ((size_t)8 << 20)) n_chunks = std::min(8, std::max(1, nq / 1024));
-  if (const char* env = getenv("FOT_HOST_CHUNKS")) n_chunks = std::max(1, std::min(8, atoi(env)));
-  const int per = (nq + n_chunks - 1) / n_chunks;
+  int bounds[9] = {0, nq, nq, nq, nq, nq, nq, nq, nq};
+  if ((size_t)nq * dyn_q_bytes > ((size_t)8 << 20) && nq >= 1024) {
+    const int unit = nq / 16;
+    const int cuts[] = {unit, 3 * unit, 6 * unit, 11 * unit, nq};     // 1/16, 1/8, 3/16, 5/16, 5/16
+    n_chunks = 5;
+    for (int c = 0; c < n_chunks; ++c) bounds[c + 1] = cuts[c];
+  }
+  if (const char* env = getenv("FOT_HOST_CHUNKS")) {
+    n_chunks = std::max(1, std::min(8, atoi(env)));
+    const int per_ = (nq + n_chunks - 1) / n_chunks;
+    for (int c = 0; c <= n_chunks; ++c) bounds[c] = std::min(nq, c * per_);
+  }
   static const bool dbg = getenv("FOT_DEBUG_TIMING") != nullptr;
   cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr, d3 = nullptr, d4 = nullptr;
   if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventCreate(&d2); cudaEventCreate(&d3); cudaEventCreate(&d4);
@@ -520,8 +531,8 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   // every obstacle upload is queued first (they depend on nothing), one event per chunk
   if (has_dyn)
     for (int c = 0; c < n_chunks; ++c) {
-      const int q0 = c * per, cq = std::min(per, nq - q0);
-      if (cq <= 0) break;
+      const int q0 = bounds[c], cq = bounds[c + 1] - q0;
+      if (cq <= 0) continue;
       char* dst = (char*)h->dyn_d.p + (size_t)q0 * dyn_q_bytes;
       const char* src = (const char*)b->dyn + (size_t)q0 * dyn_q_bytes;
       CK(cudaMemcpyAsync(dst, src, (size_t)cq * dyn_q_bytes, cudaMemcpyHostToDevice, h->copy_stream));
@@ -536,8 +547,8 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     fprintf(stderr, "[fot] dyn pointer attr: err=%d type=%d (0 unregistered, 1 host, 2 device, 3 managed)\n", (int)pe, (int)pa.type);
   }
   for (int c = 0; c < n_chunks; ++c) {
-    const int q0 = c * per, cq = std::min(per, nq - q0);
-    if (cq <= 0) break;
+    const int q0 = bounds[c], cq = bounds[c + 1] - q0;
+    if (cq <= 0) continue;
     if (has_dyn || c == 0) CK(cudaStreamWaitEvent(st, h->ev_copy[c], 0));
     if (dbg && c == 0) cudaEventRecord(d2, st);
     fot_batch_t db = *b;
