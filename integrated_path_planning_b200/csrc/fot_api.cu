@@ -352,7 +352,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   // FOT_SWEEP=generic asks for the candidate-major kernel, which the tests use as a cross-check)
   ItemGeom ig{};
   size_t ismem = 0;
-  static const char* force = getenv("FOT_SWEEP");
+  const char* force = getenv("FOT_SWEEP");            // read per launch: the tests switch kernels in-process
   bool use_items = item_geometry(h, b, &ig, &ismem);
   if (force && !strcmp(force, "generic")) use_items = false;
   if (force && !strcmp(force, "items") && !use_items) return fail(FOT_ERR_ARG, "FOT_SWEEP=items: shape not supported by fot_sweep_items");

@@ -1,0 +1,111 @@
+"""GPU: the two sweep kernels are independent implementations of the same contract -- the
+sample-major `fot_sweep_items` (default) and the candidate-major `fot_sweep` (FOT_SWEEP=generic,
+also the fallback for very long time grids).  They must agree bit for bit on every candidate's
+category and cost, on the winner and on the histogram, at sizes the NumPy oracle cannot reach."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(kernel, fn):
+    old = os.environ.get("FOT_SWEEP")
+    os.environ["FOT_SWEEP"] = kernel
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("FOT_SWEEP", None)
+        else:
+            os.environ["FOT_SWEEP"] = old
+
+
+def _assert_same(a, b):
+    assert np.array_equal(a.n_cand, b.n_cand)
+    assert np.array_equal(a.cand_cat, b.cand_cat)
+    n = int(a.n_cand.max())
+    assert np.array_equal(a.cand_cost[:, :n].view(np.uint64), b.cand_cost[:, :n].view(np.uint64))
+    assert np.array_equal(a.best_idx, b.best_idx)
+    assert np.array_equal(a.best_cost.view(np.uint64), b.best_cost.view(np.uint64))
+    assert np.array_equal(a.stats, b.stats)
+    assert np.array_equal(a.winner_len, b.winner_len)
+
+
+def _planner(knobs, wp):
+    from integrated_path_planning_b200 import BatchFrenetPlanner, CubicSpline2D
+    return BatchFrenetPlanner(CubicSpline2D(*wp), **knobs)
+
+
+def test_config4_batch_both_kernels():
+    """512 queries of BASELINE config 4 (1261 candidates x 50 pedestrians each)."""
+    import bench
+    _, frenet, dyn = bench.make_queries(1000, 512)
+    pl = _planner(scenarios.S1_KNOBS, scenarios.STRAIGHT_60)
+    run = lambda: pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn[:, 0], want_candidates=True)
+    a, b = _run("items", run), _run("generic", run)
+    _assert_same(a, b)
+    assert (a.stats[:, 6] > 0).any() and (a.best_idx >= 0).any()
+
+
+def test_curved_path_state_machine_knobs_both_kernels():
+    """S-curve reference line, per-query target speeds / limits / stop distances (the state machine's
+    three knob sets), static wall and dynamic field together."""
+    rng = np.random.default_rng(3)
+    n = 96
+    wp = scenarios.s_curve_waypoints()
+    frenet = np.stack([rng.uniform(2, 30, n), rng.uniform(0, 8, n), rng.uniform(-1, 1, n),
+                       rng.uniform(-1.5, 1.5, n), rng.normal(0, 0.3, n), rng.normal(0, 0.05, n)], axis=1)
+    k = scenarios.S1_KNOBS
+    target = np.tile([6.0, 3.6, 0.0], n // 3)
+    limits = np.tile([[k["max_speed"], k["max_accel"], k["max_curvature"], k["max_lat_accel"]],
+                      [k["max_speed"] * 0.6, k["max_accel"] * 1.5, k["max_curvature"], k["max_lat_accel"]],
+                      [k["max_speed"], k["max_accel"] * 3.0, k["max_curvature"], k["max_lat_accel"] * 2.0]], (n // 3, 1))
+    msd = np.where(target == 0.0, 5.0, np.nan)
+    dyn = np.stack([scenarios.pedestrian_field(np.random.default_rng(50 + i), 30, x_range=(0.0, 70.0), y_range=(-8.0, 8.0))
+                    for i in range(n)])
+    wall = scenarios.wall(x=45.0, half=1.0, n=9)
+    pl = _planner(k, wp)
+    run = lambda: pl.plan_batch(frenet, target, dynamic_obstacles=dyn, static_obstacles=wall, limits=limits,
+                                max_stop_distance=msd, want_candidates=True)
+    _assert_same(_run("items", run), _run("generic", run))
+
+
+def test_dense_grid_distribution_both_kernels():
+    """BASELINE config 3: 65 d x 32 T x 32 v (+ brake ladder) = 66.5k candidates against 200 pedestrians
+    x 20 samples (chance-constrained, epsilon = 0) -- 9.4e9 dense evaluations in one plan() call."""
+    rng = np.random.default_rng(33)
+    knobs = dict(scenarios.S1_KNOBS, d_road_w=0.1, max_road_width=3.2, min_t=1.9, max_t=5.0, d_t_s=0.2)
+    wp = (np.linspace(0.0, 80.0, 9).tolist(), [0.0] * 9)
+    base = scenarios.pedestrian_field(rng, 200, x_range=(5.0, 65.0), vel_clip=2.5)
+    dist = scenarios.sample_distribution(rng, base, 20)
+    pl = _planner(knobs, wp)
+    fs = np.array([[5.0, 5.0, 0.0, 0.0, 0.0, 0.0]])
+    run = lambda: pl.plan_batch(fs, 6.2, distribution=dist[None], want_candidates=True)
+    a, b = _run("items", run), _run("generic", run)
+    _assert_same(a, b)
+    assert int(a.n_cand[0]) > 60000
+
+
+def test_budgeted_distribution_and_footprint_both_kernels():
+    """chance_epsilon > 0 (violation budget per candidate) and a 3-circle footprint on an arc."""
+    rng = np.random.default_rng(5)
+    n = 24
+    knobs = dict(scenarios.S1_KNOBS, chance_epsilon=0.25)
+    wp = scenarios.arc_waypoints()
+    frenet = np.stack([rng.uniform(1, 10, n), rng.uniform(1, 7, n), rng.uniform(-1, 1, n),
+                       rng.uniform(-1, 1, n), rng.normal(0, 0.2, n), rng.normal(0, 0.05, n)], axis=1)
+    dists = []
+    for i in range(n):
+        r = np.random.default_rng(200 + i)
+        base = scenarios.pedestrian_field(r, 14, x_range=(0.0, 20.0), y_range=(-5.0, 25.0))
+        dists.append(scenarios.sample_distribution(r, base, 12, sigma=0.08))
+    dist = np.stack(dists)
+    from integrated_path_planning_b200 import BatchFrenetPlanner, CubicSpline2D
+    from tests import runners
+    pl = BatchFrenetPlanner(CubicSpline2D(*wp), footprint=runners.make_footprint((4.5, 2.0, 3)), **knobs)
+    run = lambda: pl.plan_batch(frenet, 6.0, distribution=dist, want_candidates=True)
+    _assert_same(_run("items", run), _run("generic", run))
