@@ -39,6 +39,7 @@ UNIT = "evals/s"
 FLOP_PER_EVAL = 5.0      # 2 SUB + 1 MUL + 1 FMA
 N_PEDS, T_OBS = 50, 51
 TARGET_SPEED = 6.0
+NCU_DRAM_READ, NCU_DRAM_WRITE = 171.250432e6, 5.416192e6   # bytes per 4096-query launch (ncu --set full)
 
 
 # ------------------------------------------------------------------------------------------
@@ -92,6 +93,20 @@ def cpu_leg(frenet, dyn, n_sample, cores, steps, warmup):
 # ------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------
+def oracle_plan_latency(calls=3):
+    """config 2 plan() on one host core with the NumPy oracle (the reference port): p50 in ms."""
+    from oracle import frenet_oracle as O
+    opl = O.OraclePlanner(O.Spline2D(*scenarios.STRAIGHT_60), O.Knobs(**scenarios.S1_KNOBS))
+    dyn2 = scenarios.pedestrian_field(np.random.default_rng(1), N_PEDS, T_OBS, scenarios.S1_KNOBS["dt"])
+    lat = []
+    for _ in range(calls + 1):
+        opl.reset_ego_curvature()
+        t0 = time.perf_counter()
+        opl.plan((5.0, 0.0, 0.0, 5.0, 0.0), np.empty((0, 2)), dyn2, TARGET_SPEED)
+        lat.append(1e3 * (time.perf_counter() - t0))
+    return float(np.median(lat[1:]))
+
+
 class ClockSampler(threading.Thread):
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -166,7 +181,9 @@ def main():
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{n_sample} of the {args.queries} queries per step "
                                            f"({evals:.3g} dense evals), NumPy oracle over a {cores}-process pool; "
-                                           f"timed steps capped at 5"},
+                                           f"timed steps capped at 5",
+                                 "plan_p50_ms": oracle_plan_latency(),
+                                 "plan_sample": "config2 plan() on one core, 3 calls after 1 warm-up"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -264,17 +281,36 @@ def main():
     peak = C.c_double()
     _lib.check(eng.lib.fot_probe_fma_tflops(local_rank, 0, C.byref(peak)), "probe")
     achieved_tf = FLOP_PER_EVAL * evals_step / (sweep_ms * 1e-3) / 1e12
-    # DRAM traffic of one fot_sweep launch from the committed ncu --set full capture
-    # (profiles/r1/sweep_ncu_full_summary.txt: 142.2 MB read + 6.0 MB written for 4096 queries), per query
-    traffic = (142.210816e6 + 5.962752e6) / 4096 * Q
+    # DRAM traffic of one fot_sweep_items launch from the committed ncu --set full capture
+    # (profiles/r1/sweep_items_ncu_full_summary.txt: read + written bytes for 4096 queries), per query
+    traffic = (NCU_DRAM_READ + NCU_DRAM_WRITE) / 4096 * Q
     roofline = {"bound": "fp64_pipe", "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak.value, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/r1)",
-                "kernel": "fot_sweep", "kernel_ms": sweep_ms,
+                "kernel": "fot_sweep_items", "kernel_ms": sweep_ms,
                 "stage_ms": {"prepass": float(stage[:, 0].mean()), "sweep": sweep_ms, "winner": float(stage[:, 2].mean())},
                 "peak_source": "fot_probe_fma_tflops on this GPU (dependent-chain DFMA, 2 FLOP/FMA); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "note": "algorithmic 5 FLOP per dense evaluation; point generation (about 58041 points per query) "
                         "is extra work not credited here"}
+
+    # plan() latency (BASELINE config 2: one call, default grid, 50 pedestrians x 1 sample), measured the
+    # way the reference's simulator measures it: time.perf_counter around FrenetPlanner.plan()
+    # (integrated_simulator.py:575-585) -- ego->Frenet on the host, H2D, kernels, D2H, FrenetPath rebuilt
+    from integrated_path_planning_b200 import FrenetPlanner
+    from integrated_path_planning_b200.types import EgoVehicleState
+    single = FrenetPlanner(spline, device=local_rank, **scenarios.S1_KNOBS)
+    ego2 = EgoVehicleState(x=5.0, y=0.0, yaw=0.0, v=5.0, a=0.0)
+    dyn2 = scenarios.pedestrian_field(np.random.default_rng(1), N_PEDS, T_OBS, scenarios.S1_KNOBS["dt"])
+    lat, kms = [], []
+    for i in range(103):
+        single.reset_ego_curvature()
+        t0 = time.perf_counter()
+        single.plan(ego2, np.empty((0, 2)), dyn2, TARGET_SPEED)
+        lat.append(1e3 * (time.perf_counter() - t0))
+        kms.append(single.last_result.kernel_ms)
+    plan_latency = {"p50_ms": float(np.median(lat[3:])), "p95_ms": float(np.percentile(lat[3:], 95)),
+                    "kernels_p50_ms": float(np.median(kms[3:])), "calls": 100,
+                    "config": "config2: one plan() call, 1261 candidates x 50 pedestrians x 1 sample"}
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -282,7 +318,9 @@ def main():
         val, ms, ev = cpu_leg(frenet, dyn, n_sample, cores, 2, 1)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_sample} of the {Q} queries ({ev:.3g} dense evals), NumPy oracle over a "
-                         f"{cores}-process pool, mean of 2 passes, {ms:.0f} ms per pass"}
+                         f"{cores}-process pool, mean of 2 passes, {ms:.0f} ms per pass",
+               "plan_p50_ms": oracle_plan_latency(),
+               "plan_sample": "config2 plan() on one core, 3 calls after 1 warm-up"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -290,7 +328,8 @@ def main():
             "e2e": {"value": evals_step * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "winners_match_resident": same},
-            "gpu_launches": 3 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "plan_latency": plan_latency,
             "candidates_per_s": float(res.n_cand.sum()) * world / (ms_step * 1e-3),
             "evals_per_step_per_gpu": evals_step}
     print(json.dumps(line))

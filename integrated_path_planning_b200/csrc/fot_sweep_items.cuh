@@ -57,6 +57,9 @@ __device__ unsigned long long g_phase_clk[16];
 #define FOT_PHASE_MARK(k) do { } while (0)
 #endif
 
+#ifndef FOT_ITEM_MIN_CTAS
+#define FOT_ITEM_MIN_CTAS 2
+#endif
 constexpr int kItemThreads = 320;   // largest block of fot_sweep_items
 constexpr int kRowW = 12;           // item row: rx ry cos sin | kappa s 1/s_dot s_dot | A0 B0 A1 B1
 constexpr unsigned F_DROP = 32u;    // silent drop (singular / non-finite / teleport), fp.py:826-833, :944-956
@@ -200,7 +203,7 @@ __device__ __forceinline__ unsigned clean_word(const unsigned* flags_pp, int nw4
   return rem >= 32 ? m : (m & ((1u << rem) - 1u));
 }
 
-__global__ void __launch_bounds__(kItemThreads, 2)
+__global__ void __launch_bounds__(kItemThreads, FOT_ITEM_MIN_CTAS)
 fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   extern __shared__ __align__(16) unsigned char smb[];
   double* row = reinterpret_cast<double*>(smb + G.o_row);      // [pcap][NT][kRowW]
