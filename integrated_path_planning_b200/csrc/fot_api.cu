@@ -514,10 +514,14 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   int n_chunks = 1;
   int bounds[9] = {0, nq, nq, nq, nq, nq, nq, nq, nq};
   if ((size_t)nq * dyn_q_bytes > ((size_t)8 << 20) && nq >= 1024) {
-    const int unit = nq / 16;
-    const int cuts[] = {unit, 3 * unit, 6 * unit, 11 * unit, nq};     // 1/16, 1/8, 3/16, 5/16, 5/16
+    // chunk sizes in whole waves of the sweep (one CTA per query, two CTAs per SM) where possible
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int wave = 2 * sms;
+    auto waves = [&](int frac16) { const int w = std::max(1, (int)((long long)nq * frac16 / 16 / wave)); return w * wave; };
+    const int cuts[] = {waves(1), waves(3), waves(6), waves(11), nq};  // about 1/16, 1/8, 3/16, 5/16, 5/16 of the queries
     n_chunks = 5;
-    for (int c = 0; c < n_chunks; ++c) bounds[c + 1] = cuts[c];
+    for (int c = 0; c < n_chunks; ++c) bounds[c + 1] = std::min(nq, std::max(cuts[c], bounds[c]));
   }
   if (const char* env = getenv("FOT_HOST_CHUNKS")) {
     n_chunks = std::max(1, std::min(8, atoi(env)));

@@ -33,6 +33,16 @@ class CoordinateConverter:
         # the same inner loops (including its vectorised pow), so the values are bit-identical to the
         # reference's point-by-point calls; only the per-call overhead goes (10 ms -> ~1 ms per plan()).
         self._batched = True
+        # Paths that expose their coefficient arrays (ours and the reference's CubicSpline2D) get a lean
+        # evaluator: the same element-wise NumPy expression as CubicSpline1D.calc_position
+        # (a + b dx + c dx**2.0 + d dx**3.0), with the segment search and the powers shared by x and y.
+        self._tab = None
+        try:
+            from .spline import spline_tables
+            t = spline_tables(reference_path)
+            self._tab = tuple(t[k] for k in ("knots", "xa", "xb", "xc", "xd", "ya", "yb", "yc", "yd"))
+        except Exception:
+            self._tab = None
 
     # -- search --------------------------------------------------------------------------
     def _xy(self, s):
@@ -44,8 +54,52 @@ class CoordinateConverter:
         if not self._batched:
             pts = [self._xy(s) for s in s_values]
             return [p[0] for p in pts], [p[1] for p in pts]
-        px, py = self.reference_path.calc_position(np.asarray(s_values, dtype=np.float64))
-        return np.atleast_1d(px), np.atleast_1d(py)
+        sv = np.asarray(s_values, dtype=np.float64).reshape(-1)
+        if self._tab is None:
+            px, py = self.reference_path.calc_position(sv)
+            return np.atleast_1d(px), np.atleast_1d(py)
+        knots, xa, xb, xc, xd, ya, yb, yc, yd = self._tab
+        inside = (sv >= knots[0]) & (sv <= knots[-1])                 # cubic_spline.py:62
+        i = np.searchsorted(knots, sv, side="right") - 1               # cubic_spline.py:162-165
+        i = np.minimum(np.maximum(i, 0), knots.shape[0] - 2)
+        dx = sv - knots[i]
+        dx2, dx3 = dx ** 2.0, dx ** 3.0
+        px = xa[i] + xb[i] * dx + xc[i] * dx2 + xd[i] * dx3            # cubic_spline.py:73-74
+        py = ya[i] + yb[i] * dx + yc[i] * dx2 + yd[i] * dx3
+        if not inside.all():
+            px = np.where(inside, px, np.nan)
+            py = np.where(inside, py, np.nan)
+        return px, py
+
+    def _heading_curvature(self, rs):
+        """yaw, curvature, curvature rate at rs: CubicSpline2D.calc_yaw / calc_curvature /
+        calc_curvature_rate (cubic_spline.py:228-288) with the segment search done once.  The
+        derivatives are one-element array expressions and the combinations scalar expressions,
+        exactly as those methods evaluate them for a scalar argument."""
+        if self._tab is None:
+            return (_f(self.reference_path.calc_yaw(rs)), _f(self.reference_path.calc_curvature(rs)),
+                    _f(self.reference_path.calc_curvature_rate(rs)))
+        knots, xa, xb, xc, xd, ya, yb, yc, yd = self._tab
+        sv = np.atleast_1d(np.asarray(rs, dtype=np.float64))
+        if not ((sv >= knots[0]) & (sv <= knots[-1])).all():
+            return np.nan, np.nan, np.nan
+        i = np.searchsorted(knots, sv, side="right") - 1
+        i = np.minimum(np.maximum(i, 0), knots.shape[0] - 2)
+        h = sv - knots[i]
+        h2 = h ** 2.0
+        dx = (xb[i] + 2.0 * xc[i] * h + 3.0 * xd[i] * h2)[0]          # cubic_spline.py:100
+        dy = (yb[i] + 2.0 * yc[i] * h + 3.0 * yd[i] * h2)[0]
+        ddx = (2.0 * xc[i] + 6.0 * xd[i] * h)[0]                       # cubic_spline.py:125
+        ddy = (2.0 * yc[i] + 6.0 * yd[i] * h)[0]
+        dddx = (6.0 * xd[i])[0]                                        # cubic_spline.py:149
+        dddy = (6.0 * yd[i])[0]
+        yaw = np.arctan2(dy, dx)                                       # :287
+        kappa = (ddy * dx - ddx * dy) / ((dx ** 2 + dy ** 2) ** (3 / 2))   # :246
+        a = dx * ddy - dy * ddx
+        b = dx * dddy - dy * dddx
+        c = dx * ddx + dy * ddy
+        d = dx * dx + dy * dy
+        return yaw, kappa, b / d ** 1.5 - 3.0 * a * c / d ** 2.5      # :273
 
     def _global_search(self, x, y):
         length = self.reference_path.s[-1]
@@ -97,9 +151,7 @@ class CoordinateConverter:
             rx, ry = self._xy(rs)
             if np.any(np.isnan([rx, ry])):
                 raise ValueError(f"Failed to find valid reference point for position ({x:.2f}, {y:.2f})")
-        rtheta = _f(self.reference_path.calc_yaw(rs))
-        rkappa = _f(self.reference_path.calc_curvature(rs))
-        rdkappa = _f(self.reference_path.calc_curvature_rate(rs))
+        rtheta, rkappa, rdkappa = self._heading_curvature(rs)
         if np.any(np.isnan([rtheta, rkappa, rdkappa])):
             raise ValueError(f"Failed to calculate reference path properties at s={rs:.2f}")
         return rs, rx, ry, rtheta, rkappa, rdkappa
