@@ -68,7 +68,7 @@ struct fot_handle {
   std::vector<cudaEvent_t> ring;     // kRing x 4 events: start, after prepass, after sweep, after winner
   long long n_launch = 0;
   int smem_optin = 0;
-  Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_bad;   // device scratch
+  Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_bad, cost_tab;   // device scratch
   int last_sweep_kind = 0;           // 1: fot_sweep_items, 2: fot_sweep (generic)
   Buf stage_h, stage_d, out_d, dyn_d, stat_d;   // host-API staging
   fot_handle() { stage_h.host = true; }
@@ -157,7 +157,7 @@ extern "C" int fot_destroy(fot_handle_t* h) {
   if (!h) return FOT_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->dyn_bad, &h->stage_h, &h->stage_d, &h->out_d,
+  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->dyn_bad, &h->cost_tab, &h->stage_h, &h->stage_d, &h->out_d,
                  &h->dyn_d, &h->stat_d})
     b->release();
   if (h->tables_dev) cudaFree(h->tables_dev);
@@ -281,7 +281,6 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   }
   G.pcap = std::max(G.ppc, std::max(G.ppb, 1));
   G.threads = (G.pcap * NT + 31) / 32 * 32;
-  G.jcap = std::max(nd, G.ppb);
   G.nw4 = (nd + 3) / 4;
   G.nwc = (nd + 31) / 32;
   const int max_viol = b->dyn_mode == FOT_DYN_DISTRIBUTION ? (int)std::floor(h->plan.cfg.chance_epsilon * (double)b->S) : 0;
@@ -295,10 +294,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
     G.o_row = take((size_t)G.pcap * NT * kRowW * 8);
-    G.o_js = take((size_t)G.pcap * 8);
     G.o_sdl = take((size_t)G.pcap * 8);
-    G.o_jp = take((size_t)G.jcap * 8);
-    G.o_dend = take((size_t)G.jcap * 8);
     G.o_dgrid = take((size_t)nd * 8);
     G.o_vlast = take((size_t)G.pcap * nd * 8);
     G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);
@@ -382,8 +378,10 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
       CK(h->stat_tm.reserve((size_t)nq_s * 3 * Mp * sizeof(double)));
       CK(h->stat_max2.reserve((size_t)nq_s * sizeof(double)));
     }
-  } else if (need_box) {
-    CK(h->dyn_bad.reserve((size_t)b->n_q * SP * sizeof(float4)));
+  } else {
+    if (need_box) CK(h->dyn_bad.reserve((size_t)b->n_q * SP * sizeof(float4)));
+    const size_t stride = (size_t)h->plan.cfg.n_T * (b->n_v_max + 2 * h->plan.cfg.n_d) + 3 * (size_t)h->plan.cfg.n_B;
+    CK(h->cost_tab.reserve((size_t)b->n_q * stride * sizeof(double)));
   }
 
   Batch B{};
@@ -399,6 +397,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   B.dyn_raw = has_dyn ? b->dyn : nullptr;
   B.static_raw = b->n_static > 0 ? b->static_obs : nullptr;
   B.dyn_box = need_box ? (const float4*)h->dyn_bad.p : nullptr;
+  B.cost_tab = use_items ? (const double*)h->cost_tab.p : nullptr;
   Out O{};
   O.best_idx = r->best_idx; O.best_cost = r->best_cost; O.stats = r->stats; O.winner_len = r->winner_len;
   O.winner = r->winner; O.cand_cat = r->cand_cat; O.cand_cost = r->cand_cost; O.cand_stride = r->cand_stride;
@@ -429,11 +428,15 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
       fot_static_prepass<<<(total + 255) / 256, 256, 0, st>>>((const double2*)b->static_obs, (double*)h->stat_tm.p,
                                                               (double*)h->stat_max2.p, nq_s, b->n_static);
     }
-  } else if (need_box) {
-    const long long warps = (long long)b->n_q * SP;
-    const long long blocks = (warps * 32 + 255) / 256;
-    if (blocks > 0x7fffffffll) return fail(FOT_ERR_ARG, "obstacle field too large for one launch");
-    fot_aabb_prepass<<<(unsigned)blocks, 256, 0, st>>>((const double2*)b->dyn, (float4*)h->dyn_bad.p, warps, b->T_obs);
+  } else {
+    // cost tables (one thread per polynomial profile) and trajectory boxes (one warp per trajectory), one launch
+    const long long n_prof = (long long)h->plan.cfg.n_T * (b->n_v_max + h->plan.cfg.n_d) + 2 * h->plan.cfg.n_B;
+    const long long cblocks = ((long long)b->n_q * n_prof + 255) / 256;
+    const long long n_traj = need_box ? (long long)b->n_q * SP : 0;
+    const long long ablocks = (n_traj * 32 + 255) / 256;
+    if (cblocks + ablocks > 0x7fffffffll) return fail(FOT_ERR_ARG, "batch too large for one launch");
+    fot_prepass<<<(unsigned)(cblocks + ablocks), 256, 0, st>>>(h->plan, B, (double*)h->cost_tab.p, (unsigned)cblocks,
+                                                               (const double2*)b->dyn, (float4*)h->dyn_bad.p, n_traj, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
   if (use_items) fot_sweep_items<<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);

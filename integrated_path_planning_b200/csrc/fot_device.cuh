@@ -39,6 +39,7 @@ struct Batch {
   const double* dyn_raw;      // [n_q][S][P][T_obs][2] (reference layout) or null
   const double* static_raw;   // [n_q or 1][M][2] or null
   const float4* dyn_box;      // [n_q][S*P] trajectory boxes (xmin, xmax, ymin, ymax) from fot_aabb_prepass
+  const double* cost_tab;     // [n_q][n_T*(n_v_max + 2 n_d) + 3 n_B] jerk sums / terminal offsets from fot_cost_prepass
 };
 
 struct Out {

@@ -75,7 +75,6 @@ struct ItemGeom {
   int32_t ctas_per_query;    // ceil(blocks_per_query / bpc)
   int32_t threads;           // block size (multiple of 32, >= items of the largest block)
   int32_t pcap;              // max(ppc, ppb): per-pair table slots
-  int32_t jcap;              // max(n_d, ppb): lateral jerk-sum slots
   int32_t qcap;              // collision queue capacity (entries)
   int32_t ochunk;            // list entries culled per queue round
   int32_t lcap;              // obstacle list capacity (static + dynamic entries)
@@ -85,7 +84,7 @@ struct ItemGeom {
   int32_t nw4, nwc;          // flag words (4 candidates each) / bit-mask words (32 candidates each) per pair
   int32_t n_zero;            // u32 words of the zero-initialised region starting at o_flags
   // byte offsets into dynamic shared memory
-  int32_t o_row, o_js, o_sdl, o_jp, o_dend, o_dgrid, o_vlast, o_spl, o_dyn;
+  int32_t o_row, o_sdl, o_dgrid, o_vlast, o_spl, o_dyn;
   int32_t o_fn, o_flags, o_hit, o_viol, o_queue, o_list, o_slow, o_clean;
 };
 
@@ -147,27 +146,6 @@ __device__ __forceinline__ TPow tpow(int n, double dt) {
   return r;
 }
 
-// NumPy pairwise sum (see np_pairwise_sum) of f(0..n-1) computed by the 8 lanes of an aligned lane
-// group: lane a owns accumulator r_a, the combine tree and the sequential tail are NumPy's.
-template <class F>
-__device__ __forceinline__ double np_sum_8lanes(const F& f, int n, int sub, unsigned gmask) {
-  double res;                                // n <= 128 (item_geometry sends longer time grids to fot_sweep)
-  if (n < 8) {
-    res = 0.0;
-    for (int i = 0; i < n; ++i) res += f(i);
-  } else {
-    const int stop = n - (n % 8);
-    double r = f(sub);
-    for (int i = 8 + sub; i < stop; i += 8) r += f(i);
-    r = r + __shfl_xor_sync(gmask, r, 1);    // (r0+r1), (r2+r3), ...
-    r = r + __shfl_xor_sync(gmask, r, 2);    // (r0+r1)+(r2+r3), (r4+r5)+(r6+r7)
-    r = r + __shfl_xor_sync(gmask, r, 4);
-    res = r;
-    for (int i = stop; i < n; ++i) res += f(i);
-  }
-  return res;
-}
-
 // Order-preserving float <-> unsigned map for atomicMin / atomicMax on floats.
 __device__ __forceinline__ unsigned f2ord(float f) {
   const unsigned u = __float_as_uint(f);
@@ -207,10 +185,7 @@ __global__ void __launch_bounds__(kItemThreads, FOT_ITEM_MIN_CTAS)
 fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   extern __shared__ __align__(16) unsigned char smb[];
   double* row = reinterpret_cast<double*>(smb + G.o_row);      // [pcap][NT][kRowW]
-  double* js = reinterpret_cast<double*>(smb + G.o_js);        // [pcap] longitudinal jerk sums
   double* sdl = reinterpret_cast<double*>(smb + G.o_sdl);      // [pcap] s_dot at the last sample
-  double* jp = reinterpret_cast<double*>(smb + G.o_jp);        // [jcap] lateral jerk sums
-  double* dend = reinterpret_cast<double*>(smb + G.o_dend);    // [jcap] terminal lateral offsets
   double* dgrid = reinterpret_cast<double*>(smb + G.o_dgrid);  // [n_d]
   double* vlast = reinterpret_cast<double*>(smb + G.o_vlast);  // [pcap][n_d]  v^2 at the last kept sample
   double* spl = reinterpret_cast<double*>(smb + G.o_spl);      // [9][nx] when spline_smem
@@ -403,44 +378,6 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     if (lane == 0 && xlo != 0xffffffffu) {
       atomicMin(&s_box[0], xlo); atomicMax(&s_box[1], xhi);
       atomicMin(&s_box[2], ylo); atomicMax(&s_box[3], yhi);
-    }
-  }
-  // cost pieces: jerk sums in NumPy's pairwise order, 8 lanes per profile (fp.py:718-722)
-  {
-    const int n_prof = n_k + (brake_blk ? n_k : n_d);
-    const int sub = tid & 7;
-    const unsigned gmask = 0xffu << (lane & 24);
-    for (int pr0 = 0; pr0 < n_prof; pr0 += bd / 8) {
-      const int pr = pr0 + (tid >> 3);
-      if (pr < n_k) {                                    // longitudinal
-        Lon L;
-        if (!brake_blk)
-          L = lon_solve(fs, B.v_grid[(size_t)q * B.n_v_max + k_lo + pr], P.T[jT], P.inv4 + 4 * jT, n_v == 1, N - 1);
-        else
-          L = lon_solve(fs, 0.0, P.Tb[k_lo + pr], P.inv4b + 4 * (k_lo + pr), true, P.n_steps_b[k_lo + pr]);
-        auto jerk2 = [&](int k) {                        // fp.py:647, :722
-          const double j = k > L.hold ? 0.0 : 6.0 * L.a3 + 24.0 * L.a4 * ((double)k * dt);
-          return j * j;
-        };
-        const double sres = np_sum_8lanes(jerk2, N, sub, gmask);
-        if (sub == 0) js[pr] = sres;
-      } else if (pr < n_prof) {                          // lateral
-        const int li = pr - n_k;
-        Lat L;
-        if (brake_blk) L = lat_solve(fs, fs[3], P.Tb[k_lo + li], P.inv5b + 9 * (k_lo + li), true, P.n_steps_b[k_lo + li]);
-        else L = lat_solve(fs, dgrid[li], P.T[jT], P.inv5 + 9 * jT, n_d == 1, N - 1);
-        auto jerk2 = [&](int k) {                        // fp.py:691, :718
-          const double t = (double)k * dt;
-          const double j = k > L.hold ? 0.0 : 6.0 * L.a3 + 24.0 * L.a4 * t + 60.0 * L.a5 * (t * t);
-          return j * j;
-        };
-        const double sres = np_sum_8lanes(jerk2, N, sub, gmask);
-        if (sub == 0) {
-          jp[li] = sres;
-          const TPow te = tpow(min(N - 1, L.hold), dt);
-          dend[li] = L.a0 + L.a1 * te.t + L.a2 * te.t2 + L.a3 * te.t3 + L.a4 * te.t4 + L.a5 * te.t5;   // fp.py:688, :719
-        }
-      }
     }
   }
   FOT_PHASE_MARK(2);
@@ -783,9 +720,13 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     const int cp = c / n_dl, ci = c - cp * n_dl;
     const int li = brake_blk ? cp : ci;
     // cost on the un-truncated profile (fp.py:703-734)
-    const double Jp = jp[li], d_end = dend[li];
+    // jerk sums and terminal offsets come from fot_cost_prepass (profile numbering: see there)
+    const int nTv = P.cfg.n_T * B.n_v_max, nTd = P.cfg.n_T * n_d;
+    const double* ct = B.cost_tab + (size_t)q * (nTv + 2 * nTd + 3 * P.cfg.n_B);
+    const double Js = brake_blk ? ct[nTv + 2 * nTd + k_lo + cp] : ct[jT * B.n_v_max + k_lo + cp];
+    const double Jp = brake_blk ? ct[nTv + 2 * nTd + P.cfg.n_B + k_lo + li] : ct[nTv + jT * n_d + li];
+    const double d_end = brake_blk ? ct[nTv + 2 * nTd + 2 * P.cfg.n_B + k_lo + li] : ct[nTv + nTd + jT * n_d + li];
     const double Jd = d_end * d_end;
-    const double Js = js[cp];
     const double dv = B.target[q] - sdl[cp];
     const double Jv = dv * dv;
     const double Jt = (double)(N - 1) * dt;
@@ -847,12 +788,78 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   if (tid < FOT_N_STATS && s_stats[tid] != 0) atomicAdd(&O.stats[(size_t)q * FOT_N_STATS + tid], s_stats[tid]);
 }
 
+// Cost pieces that depend on one polynomial profile only (fp.py:703-734): the jerk sums  sum_n s'''(t_n)^2,
+// sum_n d'''(t_n)^2  in NumPy's pairwise-summation order (so that costs are bit-identical to the
+// reference) and the terminal lateral offset d(t_end).  One thread per profile; per query the table holds
+//   [n_T][n_v_max] Js | [n_T][n_d] Jp | [n_T][n_d] d_end | [n_B] Js brake | [n_B] Jp brake | [n_B] d_end brake.
+__device__ __forceinline__ void cost_prepass_body(const Plan& P, const Batch& B, double* __restrict__ tab, unsigned block) {
+  const int n_d = P.cfg.n_d, n_T = P.cfg.n_T, n_B = P.cfg.n_B;
+  const int nTv = n_T * B.n_v_max, nTd = n_T * n_d;
+  const int n_prof = nTv + nTd + 2 * n_B;                // profiles with a sum
+  const int stride = nTv + 2 * nTd + 3 * n_B;
+  const long long g = (long long)block * blockDim.x + threadIdx.x;    // one thread per profile
+  if (g >= (long long)B.n_q * n_prof) return;
+  const int q = (int)(g / n_prof), pr = (int)(g - (long long)q * n_prof);
+  const double* fs = B.frenet + 6 * (size_t)q;
+  const double dt = P.cfg.dt;
+  double* out = tab + (size_t)q * stride;
+  const int n_v = B.n_v[q];
+  if (pr < nTv || (pr >= nTv + nTd && pr < nTv + nTd + n_B)) {             // longitudinal
+    Lon L;
+    int N, slot;
+    if (pr < nTv) {
+      const int jT = pr / B.n_v_max, kv = pr - jT * B.n_v_max;
+      if (kv >= n_v) return;
+      N = P.n_steps[jT] + 1;
+      L = lon_solve(fs, B.v_grid[(size_t)q * B.n_v_max + kv], P.T[jT], P.inv4 + 4 * jT, n_v == 1, N - 1);
+      slot = pr;
+    } else {
+      const int b = pr - nTv - nTd;
+      N = P.cfg.n_total;
+      L = lon_solve(fs, 0.0, P.Tb[b], P.inv4b + 4 * b, true, P.n_steps_b[b]);
+      slot = nTv + 2 * nTd + b;
+    }
+    const double a3 = L.a3, a4 = L.a4;
+    const int hold = L.hold;
+    auto jerk2 = [=](int k) {                            // fp.py:647, :722
+      const double j = k > hold ? 0.0 : 6.0 * a3 + 24.0 * a4 * ((double)k * dt);
+      return j * j;
+    };
+    out[slot] = np_block_sum(jerk2, 0, N);               // N <= 128: one pairwise block
+  } else {                                               // lateral
+    Lat L;
+    int N, slot_j, slot_d;
+    if (pr < nTv + nTd) {
+      const int li = pr - nTv, jT = li / n_d, id = li - jT * n_d;
+      N = P.n_steps[jT] + 1;
+      L = lat_solve(fs, P.d_grid[id], P.T[jT], P.inv5 + 9 * jT, n_d == 1, N - 1);
+      slot_j = nTv + li; slot_d = nTv + nTd + li;
+    } else {
+      const int b = pr - nTv - nTd - n_B;
+      N = P.cfg.n_total;
+      L = lat_solve(fs, fs[3], P.Tb[b], P.inv5b + 9 * b, true, P.n_steps_b[b]);
+      slot_j = nTv + 2 * nTd + n_B + b; slot_d = nTv + 2 * nTd + 2 * n_B + b;
+    }
+    const double a3 = L.a3, a4 = L.a4, a5 = L.a5;
+    const int hold = L.hold;
+    auto jerk2 = [=](int k) {                            // fp.py:691, :718
+      const double t = (double)k * dt;
+      const double j = k > hold ? 0.0 : 6.0 * a3 + 24.0 * a4 * t + 60.0 * a5 * (t * t);
+      return j * j;
+    };
+    out[slot_j] = np_block_sum(jerk2, 0, N);
+    const TPow te = tpow(min(N - 1, hold), dt);
+    out[slot_d] = L.a0 + L.a1 * te.t + L.a2 * te.t2 + L.a3 * te.t3 + L.a4 * te.t4 + L.a5 * te.t5;     // fp.py:688, :719
+  }
+}
+
 // Boxes of the predicted trajectories, once per launch: one warp per trajectory (q, sample, ped),
 // (xmin, xmax, ymin, ymax) over all its steps rounded outward to fp32.  A NaN anywhere makes the
 // whole box NaN, which fails every overlap test: exactly the reference's prefilter, whose np.min /
 // np.max propagate the NaN and thereby remove that pedestrian from the test (fp.py:1211-1222).
-__global__ void fot_aabb_prepass(const double2* __restrict__ dyn, float4* __restrict__ box, long long n_traj, int T_obs) {
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__device__ __forceinline__ void aabb_prepass_body(const double2* __restrict__ dyn, float4* __restrict__ box, long long n_traj, int T_obs,
+                                                  unsigned block) {
+  const long long warp = ((long long)block * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_traj) return;
   const double2* src = dyn + (size_t)warp * T_obs;
@@ -873,6 +880,15 @@ __global__ void fot_aabb_prepass(const double2* __restrict__ dyn, float4* __rest
     box[warp] = bad ? make_float4(nanf_, nanf_, nanf_, nanf_)
                     : make_float4(__double2float_rd(xlo), __double2float_ru(xhi), __double2float_rd(ylo), __double2float_ru(yhi));
   }
+}
+
+// One launch for both prepasses (they are independent and each too small to fill the GPU for long):
+// blocks [0, n_cost_blocks) build the cost tables, the rest box the predicted trajectories.
+__global__ void __launch_bounds__(256)
+fot_prepass(const Plan P, const Batch B, double* __restrict__ cost_tab, unsigned n_cost_blocks,
+            const double2* __restrict__ dyn, float4* __restrict__ box, long long n_traj, int T_obs) {
+  if (blockIdx.x < n_cost_blocks) cost_prepass_body(P, B, cost_tab, blockIdx.x);
+  else aabb_prepass_body(dyn, box, n_traj, T_obs, blockIdx.x - n_cost_blocks);
 }
 
 }  // namespace fot
