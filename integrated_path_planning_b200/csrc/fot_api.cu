@@ -281,6 +281,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   }
   G.pcap = std::max(G.ppc, std::max(G.ppb, 1));
   G.threads = (G.pcap * NT + 31) / 32 * 32;
+  G.ct_lcap = std::max(nd, std::max(G.ppb, 1));
   G.nw4 = (nd + 3) / 4;
   G.nwc = (nd + 31) / 32;
   const int max_viol = b->dyn_mode == FOT_DYN_DISTRIBUTION ? (int)std::floor(h->plan.cfg.chance_epsilon * (double)b->S) : 0;
@@ -295,6 +296,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
     G.o_row = take((size_t)G.pcap * NT * kRowW * 8);
     G.o_sdl = take((size_t)G.pcap * 8);
+    G.o_ct = take((size_t)(G.pcap + 2 * G.ct_lcap) * 8);
     G.o_dgrid = take((size_t)nd * 8);
     G.o_vlast = take((size_t)G.pcap * nd * 8);
     G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);

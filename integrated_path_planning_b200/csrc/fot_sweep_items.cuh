@@ -75,6 +75,7 @@ struct ItemGeom {
   int32_t ctas_per_query;    // ceil(blocks_per_query / bpc)
   int32_t threads;           // block size (multiple of 32, >= items of the largest block)
   int32_t pcap;              // max(ppc, ppb): per-pair table slots
+  int32_t ct_lcap;           // max(n_d, ppb): lateral slots of the staged cost-table entries
   int32_t qcap;              // collision queue capacity (entries)
   int32_t ochunk;            // list entries culled per queue round
   int32_t lcap;              // obstacle list capacity (static + dynamic entries)
@@ -84,7 +85,7 @@ struct ItemGeom {
   int32_t nw4, nwc;          // flag words (4 candidates each) / bit-mask words (32 candidates each) per pair
   int32_t n_zero;            // u32 words of the zero-initialised region starting at o_flags
   // byte offsets into dynamic shared memory
-  int32_t o_row, o_sdl, o_dgrid, o_vlast, o_spl, o_dyn;
+  int32_t o_row, o_sdl, o_ct, o_dgrid, o_vlast, o_spl, o_dyn;
   int32_t o_fn, o_flags, o_hit, o_viol, o_queue, o_list, o_slow, o_clean;
 };
 
@@ -186,6 +187,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   extern __shared__ __align__(16) unsigned char smb[];
   double* row = reinterpret_cast<double*>(smb + G.o_row);      // [pcap][NT][kRowW]
   double* sdl = reinterpret_cast<double*>(smb + G.o_sdl);      // [pcap] s_dot at the last sample
+  double* ctb = reinterpret_cast<double*>(smb + G.o_ct);       // [pcap + 2 max(n_d, ppb)] this block's cost-table entries: Js | Jp | d_end
   double* dgrid = reinterpret_cast<double*>(smb + G.o_dgrid);  // [n_d]
   double* vlast = reinterpret_cast<double*>(smb + G.o_vlast);  // [pcap][n_d]  v^2 at the last kept sample
   double* spl = reinterpret_cast<double*>(smb + G.o_spl);      // [9][nx] when spline_smem
@@ -292,6 +294,31 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   }
   if (tid < G.pcap) pi_fn[tid] = 0x7fffffff;
   for (int i = tid; i < G.n_zero; i += bd) flags[i] = 0u;          // flags | hit words | violation bitmaps
+  {
+    // this block's jerk sums / terminal offsets (fot_prepass tables) -> shared memory, asynchronously:
+    // phase E reads them four barriers from now
+    const int nTv = P.cfg.n_T * B.n_v_max, nTd = P.cfg.n_T * n_d, nB = P.cfg.n_B;
+    const double* ct = B.cost_tab + (size_t)q * (nTv + 2 * nTd + 3 * nB);
+    const int n_lat = brake_blk ? n_k : n_d, lcap = G.ct_lcap;
+    if (tid < n_k + 2 * n_lat) {
+      const double* src;
+      double* dst;
+      if (tid < n_k) {
+        src = brake_blk ? ct + nTv + 2 * nTd + k_lo + tid : ct + jT * B.n_v_max + k_lo + tid;
+        dst = ctb + tid;
+      } else if (tid < n_k + n_lat) {
+        const int li = tid - n_k;
+        src = brake_blk ? ct + nTv + 2 * nTd + nB + k_lo + li : ct + nTv + jT * n_d + li;
+        dst = ctb + G.pcap + li;
+      } else {
+        const int li = tid - n_k - n_lat;
+        src = brake_blk ? ct + nTv + 2 * nTd + 2 * nB + k_lo + li : ct + nTv + nTd + jT * n_d + li;
+        dst = ctb + G.pcap + lcap + li;
+      }
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   FOT_PHASE_MARK(0);
   __syncthreads();
   FOT_PHASE_MARK(1);
@@ -526,6 +553,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       vlast[p * n_d + i] = sd2 * fma(qq, qq, dpr * dpr);
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");   // cost-table entries of phase A have landed (visible after the barrier)
   FOT_PHASE_MARK(4);
   __syncthreads();
   FOT_PHASE_MARK(5);
@@ -720,12 +748,8 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     const int cp = c / n_dl, ci = c - cp * n_dl;
     const int li = brake_blk ? cp : ci;
     // cost on the un-truncated profile (fp.py:703-734)
-    // jerk sums and terminal offsets come from fot_cost_prepass (profile numbering: see there)
-    const int nTv = P.cfg.n_T * B.n_v_max, nTd = P.cfg.n_T * n_d;
-    const double* ct = B.cost_tab + (size_t)q * (nTv + 2 * nTd + 3 * P.cfg.n_B);
-    const double Js = brake_blk ? ct[nTv + 2 * nTd + k_lo + cp] : ct[jT * B.n_v_max + k_lo + cp];
-    const double Jp = brake_blk ? ct[nTv + 2 * nTd + P.cfg.n_B + k_lo + li] : ct[nTv + jT * n_d + li];
-    const double d_end = brake_blk ? ct[nTv + 2 * nTd + 2 * P.cfg.n_B + k_lo + li] : ct[nTv + nTd + jT * n_d + li];
+    // jerk sums and terminal offsets from fot_prepass (staged in phase A)
+    const double Js = ctb[cp], Jp = ctb[G.pcap + li], d_end = ctb[G.pcap + G.ct_lcap + li];
     const double Jd = d_end * d_end;
     const double dv = B.target[q] - sdl[cp];
     const double Jv = dv * dv;
