@@ -162,6 +162,43 @@ int fot_launch_stage_ms(const fot_handle_t* h, int back, float ms[3]);
  * Writes achieved TFLOP/s (2 flops per FMA). */
 int fot_probe_fma_tflops(int device, int kind, double* tflops_out);
 
+/* ---- next row: the predictor's post-processing on the device ---------
+ * Builds the obstacle tensor fot_batch_t.dyn consumes, so that batched roll-outs never upload it.
+ * All pointers are DEVICE pointers; `stream` is a cudaStream_t (NULL = the default stream, synchronised
+ * before returning).  The time grid `time_target[n_steps]` is the reference's
+ * np.arange(sim_dt, max(plan_horizon, pred_len * sgan_dt) + 1e-9, sim_dt) (trajectory_predictor.py:214-215,
+ * :283-284), built by the caller with NumPy so that its values are bit-identical. */
+
+/* Replaces TrajectoryPredictor.predict_cv (trajectory_predictor.py:188-231).
+ *   p_curr, p_prev [n_q][P][2]  last two observations (p_prev NULL: zero velocity, :201-205)
+ *   staleness      [n_q] or NULL (= 0)
+ *   cur_pos        [n_q][P][2] or NULL: the t = 0 prepend of integrated_simulator.py:503-513 (skipped,
+ *                  last step duplicated, when the first predicted step already equals it for every pedestrian)
+ *   out            [n_q][P][T_out][2], T_out = n_steps + (cur_pos != NULL) */
+int fot_predict_cv_device(int device, void* stream, int n_q, int P, const double* p_curr, const double* p_prev,
+                          const double* staleness, double sgan_dt, const double* time_target, int n_steps,
+                          const double* cur_pos, double* out);
+
+/* Replaces TrajectoryPredictor.process_prediction (:233-313) for S samples per query.
+ *   pred   [n_q][S][pred_len][P][2]  raw predictor output (pred_len <= 64)
+ *   anchor [n_q][P][2] or NULL       last observed positions (:277-279)
+ *   out    [n_q][S][P][n_steps][2] */
+int fot_process_prediction_device(int device, void* stream, int n_q, int S, int P, int pred_len, const double* pred,
+                                  const double* anchor, const double* staleness, double sgan_dt,
+                                  const double* time_target, int n_steps, double* out);
+
+/* Replaces the closest-to-mean selection of TrajectoryPredictor.predict_single_best (:346-351).
+ *   samples [n_q][S][P][T][2];  dist_scratch [n_q][S];  best_idx [n_q] */
+int fot_select_best_sample_device(int device, void* stream, int n_q, int S, int P, int T, const double* samples,
+                                  double* dist_scratch, int32_t* best_idx);
+
+/* The t = 0 prepend of IntegratedSimulator._update_prediction (integrated_simulator.py:503-525).
+ *   in   [n_q][S][P][T][2];  pick [n_q] or NULL (one sample per query: the representative sample)
+ *   out  [n_q][pick ? 1 : S][P][T + 1][2]
+ *   conditional != 0: the single-sample rule (:506-513); 0: the distribution rule (:517-525). */
+int fot_prepend_current_device(int device, void* stream, int n_q, int S, int P, int T, const double* in,
+                               const int32_t* pick, const double* cur_pos, int conditional, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
 
 #include "fot_kernels.cuh"
 #include "fot_sweep_items.cuh"
+#include "fot_predict.cuh"
 
 using namespace fot;
 
@@ -661,6 +662,72 @@ extern "C" int fot_probe_fma_tflops(int device, int kind, double* tflops_out) {
   CK(cudaGetLastError());
   *tflops_out = best;
   return FOT_OK;
+}
+
+// ---- prediction post-processing ------------------------------------------
+static int pred_begin(int device, const char* what) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(FOT_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= n_dev) return fail(FOT_ERR_ARG, what);
+  CK(cudaSetDevice(device));
+  return FOT_OK;
+}
+static int pred_end(void* stream) {
+  CK(cudaGetLastError());
+  if (!stream) CK(cudaStreamSynchronize(nullptr));
+  return FOT_OK;
+}
+
+extern "C" int fot_predict_cv_device(int device, void* stream, int n_q, int P, const double* p_curr, const double* p_prev,
+                                     const double* staleness, double sgan_dt, const double* time_target, int n_steps,
+                                     const double* cur_pos, double* out) {
+  if (n_q < 1 || P < 1 || n_steps < 1 || !p_curr || !time_target || !out || !(sgan_dt > 0.0))
+    return fail(FOT_ERR_ARG, "fot_predict_cv_device: bad argument");
+  int rc = pred_begin(device, "fot_predict_cv_device: bad device ordinal");
+  if (rc != FOT_OK) return rc;
+  const int T_out = n_steps + (cur_pos ? 1 : 0);
+  const size_t smem = (size_t)P * 2 * sizeof(double);
+  if (smem > 48 * 1024) return fail(FOT_ERR_TOO_LARGE, "fot_predict_cv_device: too many pedestrians per query");
+  fot_cv_kernel<<<n_q, 256, smem, (cudaStream_t)stream>>>(p_curr, p_prev, staleness, time_target, cur_pos, out, P, n_steps,
+                                                          T_out, sgan_dt);
+  return pred_end(stream);
+}
+
+extern "C" int fot_process_prediction_device(int device, void* stream, int n_q, int S, int P, int pred_len, const double* pred,
+                                             const double* anchor, const double* staleness, double sgan_dt,
+                                             const double* time_target, int n_steps, double* out) {
+  if (n_q < 1 || S < 1 || P < 1 || pred_len < 1 || pred_len > kPredLenMax || n_steps < 1 || !pred || !time_target || !out ||
+      !(sgan_dt > 0.0))
+    return fail(FOT_ERR_ARG, "fot_process_prediction_device: bad argument (pred_len <= 64)");
+  int rc = pred_begin(device, "fot_process_prediction_device: bad device ordinal");
+  if (rc != FOT_OK) return rc;
+  const int threads = std::min(256, std::max(32, (2 * P + 31) / 32 * 32));
+  fot_resample_kernel<<<(unsigned)((long long)n_q * S), threads, 0, (cudaStream_t)stream>>>(pred, anchor, staleness, time_target, out, S, P,
+                                                                                            pred_len, n_steps, sgan_dt);
+  return pred_end(stream);
+}
+
+extern "C" int fot_select_best_sample_device(int device, void* stream, int n_q, int S, int P, int T, const double* samples,
+                                             double* dist_scratch, int32_t* best_idx) {
+  if (n_q < 1 || S < 1 || P < 1 || T < 1 || !samples || !dist_scratch || !best_idx)
+    return fail(FOT_ERR_ARG, "fot_select_best_sample_device: bad argument");
+  int rc = pred_begin(device, "fot_select_best_sample_device: bad device ordinal");
+  if (rc != FOT_OK) return rc;
+  const long long n = (long long)n_q * S;
+  fot_best_dist_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(samples, dist_scratch, n_q, S, P * T);
+  fot_best_pick_kernel<<<(n_q + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dist_scratch, best_idx, n_q, S);
+  return pred_end(stream);
+}
+
+extern "C" int fot_prepend_current_device(int device, void* stream, int n_q, int S, int P, int T, const double* in,
+                                          const int32_t* pick, const double* cur_pos, int conditional, double* out) {
+  if (n_q < 1 || S < 1 || P < 1 || T < 1 || !in || !cur_pos || !out)
+    return fail(FOT_ERR_ARG, "fot_prepend_current_device: bad argument");
+  int rc = pred_begin(device, "fot_prepend_current_device: bad device ordinal");
+  if (rc != FOT_OK) return rc;
+  const long long blocks = (long long)n_q * (pick ? 1 : S);
+  fot_prepend_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, pick, cur_pos, out, S, P, T, conditional);
+  return pred_end(stream);
 }
 
 #ifdef FOT_PHASE_CLOCKS
