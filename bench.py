@@ -196,7 +196,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the sweep has no CPU path")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only
+    # stdout carries the one JSON line only: anything a library prints meanwhile (NCCL's version banner)
+    # goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -210,15 +214,33 @@ def main():
     batch = DeviceBatch(planner, frenet, TARGET_SPEED, dyn, _lib.FOT_DYN_SINGLE)
     evals_step = batch.dense_evals()
     stream = torch.cuda.Stream(device=local_rank)
-    small = None
+    # The one collective of the path: every step's winners (cost per query) are all-gathered.  The
+    # gather runs on its own stream behind the sweep that produced them, double-buffered, so the next
+    # step's sweep does not wait for the slowest rank of this one; the timed region ends after the
+    # last gather has completed on every rank.
+    gstream = torch.cuda.Stream(device=local_rank) if world > 1 else None
+    stage_buf = [torch.empty_like(batch.out["best_cost"]) for _ in range(2)] if world > 1 else None
+    gathered = [torch.empty((world,) + tuple(batch.out["best_cost"].shape), dtype=torch.float64, device="cuda")
+                for _ in range(2)] if world > 1 else None
+    g_done = [None, None]
+    step_no = [0]
 
     def resident_step():
         batch.launch(stream.cuda_stream)
         if world > 1:
+            k = step_no[0] & 1
+            step_no[0] += 1
             with torch.cuda.stream(stream):
-                nonlocal small
-                small = [torch.empty_like(batch.out["best_cost"]) for _ in range(world)]
-                dist.all_gather(small, batch.out["best_cost"])
+                if g_done[k] is not None:
+                    stream.wait_event(g_done[k])            # the gather that last read this staging buffer
+                stage_buf[k].copy_(batch.out["best_cost"], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(stream)
+            with torch.cuda.stream(gstream):
+                gstream.wait_event(ready)
+                dist.all_gather_into_tensor(gathered[k], stage_buf[k])
+                g_done[k] = torch.cuda.Event()
+                g_done[k].record(gstream)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -237,6 +259,8 @@ def main():
     for _ in range(args.steps):
         resident_step()
     with torch.cuda.stream(stream):
+        if gstream is not None:
+            stream.wait_stream(gstream)                     # the timed region ends after the last gather
         e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
@@ -378,7 +402,10 @@ def main():
             "plan_latency": plan_latency, "e2e_device_prediction": e2e_cv,
             "candidates_per_s": float(res.n_cand.sum()) * world / (ms_step * 1e-3),
             "evals_per_step_per_gpu": evals_step}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
