@@ -199,6 +199,17 @@ int fot_select_best_sample_device(int device, void* stream, int n_q, int S, int 
 int fot_prepend_current_device(int device, void* stream, int n_q, int S, int P, int T, const double* in,
                                const int32_t* pick, const double* cur_pos, int conditional, double* out);
 
+/* ---- next row: the state machine's inputs on the device -------------
+ * Replaces compute_safety_metrics_static (src/core/data_structures.py:301-388) for n_q queries.
+ *   ego      [n_q][5]      x, y, yaw, v, a
+ *   ped_pos  [n_q][P][2], ped_vel [n_q][P][2];  n_peds [n_q] or NULL (= P for every query)
+ *   combined_radius        ego_radius + ped_radius, or footprint.radius + ped_radius (:331-335)
+ *   offsets  [n_circ]      HOST pointer, EgoFootprint.offsets (n_circ = 0: the centre circle)
+ *   out      [n_q][5]      min_distance, collision (0 / 1), ttc, clearance, clearance_ahead (+inf = none) */
+int fot_safety_metrics_device(int device, void* stream, int n_q, int P, const double* ego, const double* ped_pos,
+                              const double* ped_vel, const int32_t* n_peds, double combined_radius,
+                              const double* offsets, int n_circ, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,8 @@ SYMBOLS = (
                                                 C.c_void_p, C.c_void_p)),
     ("fot_prepend_current_device", C.c_int, (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)),
+    ("fot_safety_metrics_device", C.c_int, (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_double, c_double_p, C.c_int, C.c_void_p)),
 )
 
 _lib = None

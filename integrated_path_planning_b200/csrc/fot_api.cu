@@ -730,6 +730,25 @@ extern "C" int fot_prepend_current_device(int device, void* stream, int n_q, int
   return pred_end(stream);
 }
 
+extern "C" int fot_safety_metrics_device(int device, void* stream, int n_q, int P, const double* ego, const double* ped_pos,
+                                         const double* ped_vel, const int32_t* n_peds, double combined_radius,
+                                         const double* offsets, int n_circ, double* out) {
+  if (n_q < 1 || P < 0 || !ego || !out || (P > 0 && (!ped_pos || !ped_vel)) || n_circ < 0 || n_circ > FOT_MAX_CIRCLES ||
+      (n_circ > 0 && !offsets))
+    return fail(FOT_ERR_ARG, "fot_safety_metrics_device: bad argument");
+  int rc = pred_begin(device, "fot_safety_metrics_device: bad device ordinal");
+  if (rc != FOT_OK) return rc;
+  static thread_local double* d_off = nullptr;          // footprint offsets: a few doubles, copied per call
+  if (n_circ > 0) {
+    if (!d_off) CK(cudaMalloc(&d_off, FOT_MAX_CIRCLES * sizeof(double)));
+    CK(cudaMemcpyAsync(d_off, offsets, n_circ * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  }
+  const long long threads = (long long)n_q * 32;
+  fot_safety_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ego, ped_pos, ped_vel, n_peds, out, n_q, P,
+                                                                                         combined_radius, d_off, n_circ);
+  return pred_end(stream);
+}
+
 #ifdef FOT_PHASE_CLOCKS
 // tuning aid: read and reset the per-phase clock accumulators of fot_sweep_items
 extern "C" int fot_debug_phase_clocks(unsigned long long out[16]) {

@@ -211,4 +211,56 @@ __global__ void fot_best_pick_kernel(const double* __restrict__ dist, int32_t* _
   }
 }
 
+// ---- safety metrics -----------------------------------------------------
+// compute_safety_metrics_static (src/core/data_structures.py:301-388): per query the minimum distance from
+// any footprint circle centre to any pedestrian, the collision flag, the time to collision along the line
+// of sight, the clearance and the clearance restricted to pedestrians ahead of the vehicle.  These are the
+// inputs of the fail-safe state machine, needed once per query and step in batched roll-outs.
+// One warp per query; out[q] = {min_distance, collision, ttc, clearance, clearance_ahead}.
+__global__ void fot_safety_kernel(const double* __restrict__ ego, const double* __restrict__ ped_pos,
+                                  const double* __restrict__ ped_vel, const int32_t* __restrict__ n_peds,
+                                  double* __restrict__ out, int n_q, int P, double combined_radius,
+                                  const double* __restrict__ offsets, int n_circ) {
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (q >= n_q) return;
+  const double* e = ego + 5 * (size_t)q;
+  const double x = e[0], y = e[1], yaw = e[2], v = e[3];
+  const double hx = cos(yaw), hy = sin(yaw);                                   // :371-372 / footprint.py:44
+  const double evx = v * hx, evy = v * hy;                                     // :350-351
+  const int np_ = n_peds ? n_peds[q] : P;
+  const double inf = INFINITY;
+  double dmin = inf, ttc = inf, dmin_ahead = inf;
+  for (int p = lane; p < np_; p += 32) {
+    const double px = ped_pos[((size_t)q * P + p) * 2], py = ped_pos[((size_t)q * P + p) * 2 + 1];
+    const double vx = ped_vel[((size_t)q * P + p) * 2], vy = ped_vel[((size_t)q * P + p) * 2 + 1];
+    const bool ahead = (px - x) * hx + (py - y) * hy > 0.0;                    // :373-374
+    for (int c = 0; c < (n_circ > 0 ? n_circ : 1); ++c) {
+      const double cx = n_circ > 0 ? x + offsets[c] * hx : x, cy = n_circ > 0 ? y + offsets[c] * hy : y;   // footprint.py:45
+      const double rx = px - cx, ry = py - cy;
+      const double dist = sqrt(rx * rx + ry * ry);                             // :337-339
+      dmin = fmin(dmin, dist);
+      if (ahead) dmin_ahead = fmin(dmin_ahead, dist);
+      const double rvx = vx - evx, rvy = vy - evy;
+      const double along = -(rx * rvx + ry * rvy) / (dist + 1e-8);             // :358
+      if (along > 1e-5) {
+        const double t = (dist - combined_radius) / along;                     // :360
+        if (t >= 0.0) ttc = fmin(ttc, t);
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, off));
+    ttc = fmin(ttc, __shfl_xor_sync(0xffffffffu, ttc, off));
+    dmin_ahead = fmin(dmin_ahead, __shfl_xor_sync(0xffffffffu, dmin_ahead, off));
+  }
+  if (lane == 0) {
+    double* o = out + 5 * (size_t)q;
+    o[0] = dmin;                                                               // inf without pedestrians (:343)
+    o[1] = dmin < combined_radius ? 1.0 : 0.0;                                 // :345
+    o[2] = ttc;
+    o[3] = dmin - combined_radius;                                             // :385
+    o[4] = dmin_ahead < inf ? dmin_ahead - combined_radius : inf;              // :375-376
+  }
+}
+
 }  // namespace fot

@@ -132,3 +132,32 @@ class DevicePredictionPostprocessor:
         single = self.prepend_current(dense, current_positions, pick=best, conditional=True)
         dist = self.prepend_current(dense, current_positions, pick=None, conditional=False)
         return single, dist, best
+
+
+def safety_metrics(ego, ped_pos, ped_vel, ego_radius: float, ped_radius: float, footprint=None, n_peds=None,
+                   device: int = 0):
+    """compute_safety_metrics_static (src/core/data_structures.py:301-388) for a batch of queries on the
+    device.  ego [n_q, 5] (x, y, yaw, v, a), ped_pos / ped_vel [n_q, P, 2] (host arrays or CUDA tensors),
+    n_peds optional int32 [n_q].  Returns a dict of CUDA tensors [n_q]: min_distance, collision (bool),
+    ttc, clearance, clearance_ahead -- the inputs of FailSafeStateMachine.update / _get_planner_config."""
+    import torch
+    lib = _lib.load()
+    dev = torch.device("cuda", int(device))
+    f64 = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+                     ).to(dev, dtype=torch.float64).contiguous()
+    ego_t, pos_t, vel_t = f64(ego).reshape(-1, 5), f64(ped_pos), f64(ped_vel)
+    n_q, P = ego_t.shape[0], pos_t.shape[1]
+    if tuple(pos_t.shape) != (n_q, P, 2) or tuple(vel_t.shape) != (n_q, P, 2):
+        raise ValueError("ped_pos / ped_vel must be [n_q, P, 2]")
+    np_t = None if n_peds is None else torch.as_tensor(n_peds, dtype=torch.int32).to(dev).contiguous()
+    if footprint is None:
+        combined, offs, n_circ = float(ego_radius) + float(ped_radius), None, 0
+    else:
+        o = np.ascontiguousarray(footprint.offsets, dtype=np.float64).reshape(-1)
+        combined, offs, n_circ = float(footprint.radius) + float(ped_radius), o.ctypes.data_as(_lib.c_double_p), o.size
+    out = torch.empty((n_q, 5), dtype=torch.float64, device=dev)
+    _lib.check(lib.fot_safety_metrics_device(int(device), C.c_void_p(torch.cuda.current_stream().cuda_stream), n_q, P,
+                                             _p(ego_t), _p(pos_t) if P else None, _p(vel_t) if P else None, _p(np_t),
+                                             combined, offs, n_circ, _p(out)), "fot_safety_metrics_device")
+    return {"min_distance": out[:, 0], "collision": out[:, 1] > 0.5, "ttc": out[:, 2], "clearance": out[:, 3],
+            "clearance_ahead": out[:, 4]}

@@ -94,3 +94,43 @@ def prepend_current(dynamic_obstacles: np.ndarray, current_positions: np.ndarray
         cur_dist = np.broadcast_to(cur[None, ...], (distribution.shape[0],) + cur.shape)
         distribution = np.concatenate([cur_dist, distribution], axis=2)
     return dynamic_obstacles, distribution
+
+
+def safety_metrics(ego_xyyva, ped_pos: np.ndarray, ped_vel: np.ndarray, ego_radius: float, ped_radius: float,
+                   footprint_offsets: Optional[np.ndarray] = None, footprint_radius: float = 0.0) -> dict:
+    """compute_safety_metrics_static, src/core/data_structures.py:301-388."""
+    x, y, yaw, v = ego_xyyva[0], ego_xyyva[1], ego_xyyva[2], ego_xyyva[3]
+    if footprint_offsets is None:
+        centers = np.array([[x, y]])
+        combined = ego_radius + ped_radius
+    else:
+        direction = np.array([np.cos(yaw), np.sin(yaw)])                    # footprint.py:44-45
+        centers = np.array([x, y]) + np.asarray(footprint_offsets)[:, None] * direction
+        combined = footprint_radius + ped_radius
+    if len(ped_pos) > 0:
+        dist_matrix = np.linalg.norm(ped_pos[None, :, :] - centers[:, None, :], axis=2)
+        min_distance = float(np.min(dist_matrix))
+    else:
+        dist_matrix = np.empty((len(centers), 0))
+        min_distance = float("inf")
+    collision = min_distance < combined
+    ttc = float("inf")
+    if len(ped_pos) > 0:
+        ego_vel = np.array([v * np.cos(yaw), v * np.sin(yaw)])
+        for ci, center in enumerate(centers):
+            for pi, (pos, vel) in enumerate(zip(ped_pos, ped_vel)):
+                rel_pos = pos - center
+                rel_vel = vel - ego_vel
+                along = -np.dot(rel_pos, rel_vel) / (np.linalg.norm(rel_pos) + 1e-8)
+                if along > 1e-5:
+                    t = (dist_matrix[ci, pi] - combined) / along
+                    if t >= 0:
+                        ttc = min(ttc, t)
+    clearance_ahead = float("inf")
+    if len(ped_pos) > 0:
+        heading = np.array([np.cos(yaw), np.sin(yaw)])
+        ahead = (ped_pos - np.array([x, y])) @ heading > 0.0
+        if np.any(ahead):
+            clearance_ahead = float(np.min(dist_matrix[:, ahead])) - combined
+    return {"min_distance": min_distance, "collision": collision, "ttc": ttc, "clearance": min_distance - combined,
+            "clearance_ahead": clearance_ahead}

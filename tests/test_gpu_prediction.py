@@ -111,3 +111,26 @@ def test_cv_on_device_feeds_the_sweep_like_the_host_path():
     ref = planner.plan_batch(frenet, 6.0, dynamic_obstacles=host[:, 0])
     assert np.array_equal(got_idx, ref.best_idx) and np.array_equal(_bits(got_cost), _bits(ref.best_cost))
     assert (got_idx >= 0).any()
+
+
+def test_safety_metrics_match_reference_golden():
+    """compute_safety_metrics_static on the device against values recorded from the unmodified reference:
+    distances and clearances bit for bit in single-circle mode; the quantities that pass through cos / sin /
+    a dot product (ttc, footprint centres) within 1e-12 relative."""
+    from integrated_path_planning_b200.prediction import safety_metrics
+    from tests import runners
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "safety.npz"))
+    fp = runners.make_footprint((4.5, 2.0, 3))
+    assert np.array_equal(fp.offsets, g["fp_offsets"]) and fp.radius == float(g["fp_radius"][0])
+    for footprint, want in ((None, g["single"]), (fp, g["footprint"])):
+        m = safety_metrics(g["ego"], g["pos"], g["vel"], 1.0, 0.2, footprint, g["n_peds"])
+        got = np.stack([m["min_distance"].cpu().numpy(), m["collision"].cpu().numpy().astype(float), m["ttc"].cpu().numpy(),
+                        m["clearance"].cpu().numpy(), m["clearance_ahead"].cpu().numpy()], axis=1)
+        assert np.array_equal(got[:, 1], want[:, 1])                                   # collision flags
+        assert np.array_equal(np.isinf(got), np.isinf(want))
+        fin = np.isfinite(want)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=1e-12, atol=1e-12)
+        if footprint is None:
+            for col in (0, 3, 4):
+                assert np.array_equal(_bits(got[:, col]), _bits(want[:, col]))
+        assert want[3, 1] == 1.0 and np.isinf(want[0, 0])                             # a collision and an empty scene are covered

@@ -42,3 +42,15 @@ def test_prepend_rules():
     pred[:, 0] = cur + 1e-9                                  # already starts at the current positions
     one, _ = PO.prepend_current(pred, cur)
     assert one.shape == (4, 10, 2)
+
+
+def test_safety_metrics_match_reference():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "safety.npz"))
+    keys = ("min_distance", "collision", "ttc", "clearance", "clearance_ahead")
+    for use_fp, want in ((False, g["single"]), (True, g["footprint"])):
+        for q in range(len(g["ego"])):
+            k = int(g["n_peds"][q])
+            m = PO.safety_metrics(g["ego"][q], g["pos"][q, :k], g["vel"][q, :k], 1.0, 0.2,
+                                  g["fp_offsets"] if use_fp else None, float(g["fp_radius"][0]))
+            got = np.array([float(m[key]) for key in keys])
+            assert np.array_equal(got.view(np.uint64), want[q].view(np.uint64)), (use_fp, q, got, want[q])
