@@ -1,10 +1,14 @@
 """Phase timeline of fot_sweep_items (tuning aid): runs the bench workload against a library built
-with -DFOT_PHASE_CLOCKS and prints the share of warp-cycles spent between the kernel's barriers."""
+with -DFOT_PHASE_CLOCKS and prints the share of warp-cycles spent between the kernel's barriers.
+
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -shared \\
+       -DFOT_PHASE_CLOCKS -I include -o tools/tuning/libfot_clk.so integrated_path_planning_b200/csrc/fot_api.cu
+"""
 import ctypes as C, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 sys.path.insert(0, ROOT)
 from integrated_path_planning_b200 import _lib
-_lib.LIB_PATH = os.path.join(ROOT, "tools/scratch/libfot_clk.so")
+_lib.LIB_PATH = os.path.join(ROOT, "tools/tuning/libfot_clk.so")
 import torch
 import bench
 from tests import scenarios
