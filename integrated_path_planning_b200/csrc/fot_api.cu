@@ -290,6 +290,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   G.lcap = std::max(1, SP + b->n_static);
   G.ochunk = G.lcap <= 256 ? G.lcap : 128;
   G.qcap = 1024;
+  if (const char* env = getenv("FOT_QCAP")) G.qcap = std::max(1, std::min(1 << 15, atoi(env)));   // tests: force the queue-full path
   G.spline_smem = nx <= 128 ? 1 : 0;
   const size_t dyn_bytes = (size_t)SP * b->T_obs * 16;
   auto layout = [&](bool stage) {

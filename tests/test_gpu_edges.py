@@ -1,0 +1,122 @@
+"""GPU: edge cases of the sample-major sweep that the seeded queries do not reach -- non-finite states,
+negative limits, the full-queue path of the collision phase, obstacle horizons longer than the time grid,
+unstaged obstacle fields, one block per CTA vs one query per CTA."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import frenet_oracle as O
+from tests import runners, scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+def _planner(knobs=None, wp=scenarios.STRAIGHT_60):
+    from integrated_path_planning_b200 import BatchFrenetPlanner, CubicSpline2D
+    return BatchFrenetPlanner(CubicSpline2D(*wp), **(knobs or scenarios.S1_KNOBS))
+
+
+def _oracle(knobs=None, wp=scenarios.STRAIGHT_60):
+    return O.OraclePlanner(O.Spline2D(*wp), O.Knobs(**(knobs or scenarios.S1_KNOBS)))
+
+
+def _env(**kv):
+    class _Ctx:
+        def __enter__(self):
+            self.old = {k: os.environ.get(k) for k in kv}
+            os.environ.update({k: str(v) for k, v in kv.items()})
+
+        def __exit__(self, *a):
+            for k, v in self.old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return _Ctx()
+
+
+def _check(res, refs):
+    for i, ref in enumerate(refs):
+        n_c = len(ref.categories)
+        assert int(res.n_cand[i]) == n_c
+        assert np.array_equal(res.cand_cat[i, :n_c].astype(np.int8), ref.categories), i
+        assert int(res.best_idx[i]) == ref.best_index
+        assert res.stats[i].tolist() == [ref.stats.get(k, 0) for k in runners.GOLDEN_STAT_KEYS]
+
+
+def test_non_finite_states_drop_every_candidate():
+    """NaN / inf anywhere in the Frenet state: the reference's empty / non-finite guards drop all candidates
+    silently (histogram all zero, no path); finite neighbours in the same batch are unaffected."""
+    dyn = scenarios.pedestrian_field(np.random.default_rng(1), 5)
+    states = np.array([[5.0, np.nan, 0, 0, 0, 0], [5.0, 5.0, 0.0, np.inf, 0.0, 0.0], [np.nan, 5, 0, 0, 0, 0],
+                       [5.0, 5.0, 0.0, 0.1, 0.0, 0.0]])
+    pl, orc = _planner(), _oracle()
+    res = pl.plan_batch(states, 6.0, dynamic_obstacles=np.stack([dyn] * 4), want_candidates=True)
+    refs = [orc.plan_frenet(tuple(s), np.empty((0, 2)), dyn, 6.0) for s in states]
+    _check(res, refs)
+    assert res.best_idx[:3].tolist() == [-1, -1, -1] and res.stats[:3].sum() == 0 and res.best_idx[3] >= 0
+
+
+def test_negative_limits_reject_everything():
+    """`abs(a) > negative` is true for every checked sample: the squared device tests must agree."""
+    dyn = scenarios.pedestrian_field(np.random.default_rng(2), 4)
+    fs = np.array([[5.0, 5.0, 0.0, 0.0, 0.0, 0.0]])
+    pl, orc = _planner(), _oracle()
+    for key, col in (("max_accel", 1), ("max_speed", 0), ("max_curvature", 2), ("max_lat_accel", 3)):
+        lim = pl.resolve_limits({key: -1.0})
+        res = pl.plan_batch(fs, 6.0, dynamic_obstacles=dyn[None], limits=lim, want_candidates=True)
+        _check(res, [orc.plan_frenet(tuple(fs[0]), np.empty((0, 2)), dyn, 6.0, {key: -1.0})])
+        assert res.best_idx[0] == -1
+
+
+def test_full_collision_queue_degrades_to_in_place_tests():
+    """A dense crowd in the lane with the queue capped at 4 entries: every survivor of the window test is
+    tested by the thread that found it; results must not change."""
+    rng = np.random.default_rng(3)
+    n = 12
+    frenet = np.stack([rng.uniform(2, 15, n), rng.uniform(1, 7, n), rng.uniform(-1, 1, n), rng.uniform(-1, 1, n),
+                       rng.normal(0, 0.2, n), rng.normal(0, 0.05, n)], axis=1)
+    dyn = np.stack([scenarios.pedestrian_field(np.random.default_rng(40 + i), 60, y_range=(-3.5, 3.5)) for i in range(n)])
+    wall = scenarios.wall(x=33.0, half=1.5, n=13)
+    pl = _planner()
+    run = lambda: pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn, static_obstacles=wall, want_candidates=True)
+    base = run()
+    with _env(FOT_QCAP=4):
+        capped = run()
+    with _env(FOT_STAGE_DYN=0, FOT_BPC=1):
+        unstaged = run()
+    with _env(FOT_SWEEP="generic"):
+        generic = run()
+    for other in (capped, unstaged, generic):
+        assert np.array_equal(base.cand_cat, other.cand_cat)
+        assert np.array_equal(base.best_idx, other.best_idx) and np.array_equal(base.stats, other.stats)
+        assert np.array_equal(base.best_cost.view(np.uint64), other.best_cost.view(np.uint64))
+    orc = _oracle()
+    _check(base, [orc.plan_frenet(tuple(frenet[i]), wall, dyn[i], 6.0) for i in range(3)])
+    assert base.stats[:, 6].sum() > 0
+
+
+def test_obstacle_horizon_longer_than_the_time_grid_and_single_step():
+    """T_obs = 80 > 51 samples (extra steps are never indexed) and T_obs = 1 (every sample clamps to it)."""
+    fs = np.array([[5.0, 5.0, 0.0, 0.2, 0.0, 0.0]])
+    pl, orc = _planner(), _oracle()
+    long = scenarios.pedestrian_field(np.random.default_rng(5), 9, n_steps=80)
+    long[:, 60:] = [12.0, 0.0]                                # would block the lane if those steps were used
+    res = pl.plan_batch(fs, 6.0, dynamic_obstacles=long[None], want_candidates=True)
+    _check(res, [orc.plan_frenet(tuple(fs[0]), np.empty((0, 2)), long, 6.0)])
+    one = scenarios.pedestrian_field(np.random.default_rng(6), 9, n_steps=1)
+    res = pl.plan_batch(fs, 6.0, dynamic_obstacles=one[None], want_candidates=True)
+    _check(res, [orc.plan_frenet(tuple(fs[0]), np.empty((0, 2)), one, 6.0)])
+
+
+def test_many_speeds_split_a_horizon_over_several_blocks():
+    """n_v = 16 terminal speeds do not fit one block of 320 threads (6 pairs x 51 samples): the horizon is cut
+    into chunks of pairs; d_t_s small, coarse lateral grid to keep the oracle fast."""
+    knobs = dict(scenarios.S1_KNOBS, d_t_s=0.4, d_road_w=0.9, min_t=4.6, max_t=5.0)
+    fs = np.array([[5.0, 5.0, 0.0, 0.2, 0.0, 0.0], [8.0, 2.0, 0.5, -0.4, 0.1, 0.0]])
+    dyn = np.stack([scenarios.pedestrian_field(np.random.default_rng(70 + i), 20) for i in range(2)])
+    pl, orc = _planner(knobs), _oracle(knobs)
+    res = pl.plan_batch(fs, 6.0, dynamic_obstacles=dyn, want_candidates=True)
+    _check(res, [orc.plan_frenet(tuple(fs[i]), np.empty((0, 2)), dyn[i], 6.0) for i in range(2)])
+    assert int(res.n_cand[0]) == 5 * 16 * 7 + 9            # 5 horizons x 16 speeds x 7 offsets + 9 brake horizons below min_t = 4.6
