@@ -201,6 +201,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   unsigned* cleanw = reinterpret_cast<unsigned*>(smb + G.o_clean);  // [pcap][nwc] kinematically clean (phase D)
   unsigned short* slowq = reinterpret_cast<unsigned short*>(smb + G.o_slow);   // [threads] items with a low-speed sample
   __shared__ int s_qcount[2];
+  __shared__ int s_next[2];             // work counters of the collision rounds
   __shared__ int s_nlist[2];            // static / dynamic list lengths
   __shared__ int s_nslow;               // items in the low-speed queue
   __shared__ unsigned s_box[4];         // xmin xmax ymin ymax of the block's reference points (ordered-uint floats)
@@ -289,7 +290,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
 
   // ---- phase A: per-block shared-memory state ------------------------------------------------------
   if (tid == 0) {
-    s_qcount[0] = 0; s_qcount[1] = 0; s_nlist[0] = 0; s_nlist[1] = 0; s_nslow = 0;
+    s_qcount[0] = 0; s_qcount[1] = 0; s_next[0] = 0; s_next[1] = 0; s_nlist[0] = 0; s_nlist[1] = 0; s_nslow = 0;
     s_box[0] = 0xffffffffu; s_box[1] = 0u; s_box[2] = 0xffffffffu; s_box[3] = 0u;
   }
   if (tid < G.pcap) pi_fn[tid] = 0x7fffffff;
@@ -631,7 +632,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     // exact test of entry (item, obstacle) against every live clean candidate of the item's pair.
     // (Candidates the low-speed pass rejects in the same round may still be tested: harmless, the
     // curvature category outranks the collision category.)
-    auto process = [&](int it, int e) {
+    auto process = [&](int it, int e, bool queued) {
       const int ep = it / N, en = it - ep * N;
       const bool is_dyn = e >= n_ls;
       const unsigned off = is_dyn ? olist[M + e - n_ls] : olist[e];
@@ -644,7 +645,9 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       const double X0 = fma(-sth, r[8], r[0]) - o.x, X1 = -(sth * r[9]);       // x - ox = X0 + d_i X1
       const double Y0 = fma(cth, r[8], r[1]) - o.y, Y1 = cth * r[9];
       for (int w = 0; w < G.nwc; ++w) {
-        unsigned mbits = cleanw[ep * G.nwc + w];
+        // from the queue: the masks were published before the round's barrier; in place (queue full, before that
+        // barrier): this thread's own pair, recomputed from the flags, which are final since the previous barrier
+        unsigned mbits = queued ? cleanw[ep * G.nwc + w] : clean_word(flags + ep * G.nw4, G.nw4, n_dl, w);
         if (!use_budget) mbits &= ~hitw[ep * G.nwc + w];
         while (mbits) {
           const int bit = __ffs(mbits) - 1;
@@ -697,7 +700,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
           rel &= rel - 1u;
           const int slot = atomicAdd(&s_qcount[qsel], 1);
           if (slot < G.qcap) queue[slot] = ((unsigned)tid << 16) | (unsigned)(e - e0);
-          else process(tid, e);                                                // queue full: test right here
+          else process(tid, e, false);                                         // queue full: test right here
         }
       }
     };
@@ -718,14 +721,25 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       FOT_PHASE_MARK(7);
       const int cnt = min(s_qcount[qsel], G.qcap);
       if (tid == 0) s_qcount[qsel ^ 1] = 0;
-      if (e0 == 0) {
-        const int n_units = s_nslow * n_dl;
-        for (int u = tid; u < n_units; u += bd) { const int k = u / n_dl; slow_unit(slowq[k], u - k * n_dl); }
+      // queue entries first (their cost varies with the number of live candidates), then the low-speed
+      // units; warps fetch 32 units at a time from a shared counter so that a warp stuck with long entries
+      // does not hold the block back
+      const int n_units = cnt + (e0 == 0 ? s_nslow * n_dl : 0);
+      for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_next[qsel], 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_units) break;
+        const int u = base + lane;
+        if (u < cnt) {
+          const unsigned ent = queue[u];
+          process((int)(ent >> 16), e0 + (int)(ent & 0xffffu), true);
+        } else if (u < n_units) {
+          const int k = (u - cnt) / n_dl;
+          slow_unit(slowq[k], (u - cnt) - k * n_dl);
+        }
       }
-      for (int k = tid; k < cnt; k += bd) {
-        const unsigned ent = queue[k];
-        process((int)(ent >> 16), e0 + (int)(ent & 0xffffu));
-      }
+      if (tid == 0) s_next[qsel ^ 1] = 0;
       qsel ^= 1;
       e0 = e1;
       if (e1 < n_l && !budget) {
