@@ -120,3 +120,23 @@ def test_many_speeds_split_a_horizon_over_several_blocks():
     res = pl.plan_batch(fs, 6.0, dynamic_obstacles=dyn, want_candidates=True)
     _check(res, [orc.plan_frenet(tuple(fs[i]), np.empty((0, 2)), dyn[i], 6.0) for i in range(2)])
     assert int(res.n_cand[0]) == 5 * 16 * 7 + 9            # 5 horizons x 16 speeds x 7 offsets + 9 brake horizons below min_t = 4.6
+
+
+def test_host_chunking_and_cta_grouping_do_not_change_results():
+    """1500 queries (not a multiple of the wave size): the pipelined, chunked host path with one CTA per query
+    against a single launch with one block per CTA."""
+    import bench
+    _, frenet, dyn = bench.make_queries(5000, 250)
+    frenet, dyn = np.tile(frenet, (6, 1)), np.tile(dyn, (6, 1, 1, 1, 1))
+    pl = _planner()
+    a = pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn[:, 0], want_candidates=True)
+    a = {k: getattr(a, k).copy() for k in ("best_idx", "best_cost", "stats", "cand_cat", "winner", "winner_len")}
+    with _env(FOT_HOST_CHUNKS=1, FOT_BPC=1):
+        b = pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn[:, 0], want_candidates=True)
+    for k, v in a.items():
+        w = getattr(b, k)
+        if v.dtype == np.float64:
+            assert np.array_equal(v.view(np.uint64), w.view(np.uint64)), k
+        else:
+            assert np.array_equal(v, w), k
+    assert np.array_equal(a["best_idx"][:250], a["best_idx"][250:500])
