@@ -89,6 +89,23 @@ struct ItemGeom {
   int32_t o_fn, o_flags, o_hit, o_viol, o_queue, o_list, o_slow, o_clean;
 };
 
+// 1/x and 1/sqrt(x) to fp64 accuracy from the fp32 MUFU seed and two Newton steps (branch-free; the
+// library versions carry slow paths for denormals and cost three times as many instructions).  Used for
+// quantities that only feed the validity chain (a few ulp are immaterial there); arguments are O(1).
+__device__ __forceinline__ double rcp_nr(double a) {
+  double x = (double)__frcp_rn((float)a);
+  x = fma(x, fma(-a, x, 1.0), x);
+  x = fma(x, fma(-a, x, 1.0), x);
+  return x;
+}
+__device__ __forceinline__ double rsqrt_nr(double a) {
+  double y = (double)rsqrtf((float)a);
+  const double h = 0.5 * a;
+  y = fma(y, fma(-h * y, y, 0.5), y);
+  y = fma(y, fma(-h * y, y, 0.5), y);
+  return y;
+}
+
 struct SplineView {
   const double *knots, *xa, *xb, *xc, *xd, *ya, *yb, *yc, *yd;
   int nx;
@@ -124,7 +141,7 @@ __device__ __forceinline__ RefFast spline_ref_fast(const SplineView& V, double s
   const double y2 = 2.0 * yc + 6.0 * yd * dx;
   const double x3 = 6.0 * xd, y3 = 6.0 * yd;             // cs.py:149
   const double D = x1 * x1 + y1 * y1;
-  const double rD = 1.0 / sqrt(D);
+  const double rD = rsqrt_nr(D);
   o.cth = x1 * rD;
   o.sth = y1 * rD;
   const double iD15 = rD * rD * rD;                      // D ** -1.5
@@ -355,7 +372,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     }
     const RefFast rp = spline_ref_fast(V, s);
     i_rx = rp.rx; i_ry = rp.ry; i_cth = rp.cth; i_sth = rp.sth; i_rk = rp.rk; i_rdk = rp.rdk;
-    i_isd = fabs(i_sd) > 1e-3 ? 1.0 / i_sd : 0.0;                              // fp.py:792 EPS_S_DOT
+    i_isd = fabs(i_sd) > 1e-3 ? rcp_nr(i_sd) : 0.0;                            // fp.py:792 EPS_S_DOT
     // lateral basis at this sample: d_i(t) = A(t) + d_i * B(t) (the quintic's right-hand side is linear
     // in the target, fp.py:676-683); Horner with running derivatives
     double c0, c1, c2, c3, c4, c5, b3, b4, b5;
