@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FOT_ABI_VERSION 1
+#define FOT_ABI_VERSION 2   /* 2: + prediction post-processing and safety metrics entry points */
 #define FOT_MAX_CIRCLES 8
 #define FOT_N_STATS 8    /* ok, max_speed, max_accel, max_curvature, max_lat_accel, road_bound, collision, stop_distance */
 #define FOT_N_SERIES 15  /* t s s_d s_dd s_ddd d d_d d_dd d_ddd x y yaw c v a  (data_structures.py:149-181) */

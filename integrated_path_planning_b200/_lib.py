@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfot.so")
 
-FOT_ABI_VERSION = 1
+FOT_ABI_VERSION = 2
 FOT_MAX_CIRCLES = 8
 FOT_N_STATS = 8
 FOT_N_SERIES = 15

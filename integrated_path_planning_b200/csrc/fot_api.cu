@@ -69,7 +69,8 @@ struct fot_handle {
   std::vector<cudaEvent_t> ring;     // kRing x 4 events: start, after prepass, after sweep, after winner
   long long n_launch = 0;
   int smem_optin = 0;
-  Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_bad, cost_tab;   // device scratch
+  int sms = 148;                     // SM count of the device (block-per-CTA grouping, host chunk sizes)
+  Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_box, cost_tab;   // device scratch
   int last_sweep_kind = 0;           // 1: fot_sweep_items, 2: fot_sweep (generic)
   Buf stage_h, stage_d, out_d, dyn_d, stat_d;   // host-API staging
   fot_handle() { stage_h.host = true; }
@@ -147,6 +148,7 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   h->ring.resize((size_t)fot_handle::kRing * 4);
   for (auto& ev : h->ring) CK(cudaEventCreate(&ev));
   CK(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device));
   h->smem_optin -= 2048;   // leave room for the kernels' static shared memory
   CK(cudaFuncSetAttribute(fot_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_items, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
@@ -158,7 +160,7 @@ extern "C" int fot_destroy(fot_handle_t* h) {
   if (!h) return FOT_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->dyn_bad, &h->cost_tab, &h->stage_h, &h->stage_d, &h->out_d,
+  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->dyn_box, &h->cost_tab, &h->stage_h, &h->stage_d, &h->out_d,
                  &h->dyn_d, &h->stat_d})
     b->release();
   if (h->tables_dev) cudaFree(h->tables_dev);
@@ -271,8 +273,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   // blocks per CTA: a whole query per CTA once the batch alone fills the GPU several times over,
   // one block per CTA for single plan() calls
   {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int sms = h->sms;
     const long long total = (long long)b->n_q * G.blocks_per_query;
     long long bpc = total / ((long long)sms * 2 * 4);
     bpc = std::max<long long>(1, std::min<long long>(bpc, G.blocks_per_query));
@@ -383,7 +384,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
       CK(h->stat_max2.reserve((size_t)nq_s * sizeof(double)));
     }
   } else {
-    if (need_box) CK(h->dyn_bad.reserve((size_t)b->n_q * SP * sizeof(float4)));
+    if (need_box) CK(h->dyn_box.reserve((size_t)b->n_q * SP * sizeof(float4)));
     const size_t stride = (size_t)h->plan.cfg.n_T * (b->n_v_max + 2 * h->plan.cfg.n_d) + 3 * (size_t)h->plan.cfg.n_B;
     CK(h->cost_tab.reserve((size_t)b->n_q * stride * sizeof(double)));
   }
@@ -400,7 +401,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   B.S = has_dyn ? b->S : 0; B.P = has_dyn ? b->P : 0; B.T_obs = has_dyn ? b->T_obs : 0; B.dyn_mode = b->dyn_mode;
   B.dyn_raw = has_dyn ? b->dyn : nullptr;
   B.static_raw = b->n_static > 0 ? b->static_obs : nullptr;
-  B.dyn_box = need_box ? (const float4*)h->dyn_bad.p : nullptr;
+  B.dyn_box = need_box ? (const float4*)h->dyn_box.p : nullptr;
   B.cost_tab = use_items ? (const double*)h->cost_tab.p : nullptr;
   Out O{};
   O.best_idx = r->best_idx; O.best_cost = r->best_cost; O.stats = r->stats; O.winner_len = r->winner_len;
@@ -440,7 +441,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
     const long long ablocks = (n_traj * 32 + 255) / 256;
     if (cblocks + ablocks > 0x7fffffffll) return fail(FOT_ERR_ARG, "batch too large for one launch");
     fot_prepass<<<(unsigned)(cblocks + ablocks), 256, 0, st>>>(h->plan, B, (double*)h->cost_tab.p, (unsigned)cblocks,
-                                                               (const double2*)b->dyn, (float4*)h->dyn_bad.p, n_traj, b->T_obs);
+                                                               (const double2*)b->dyn, (float4*)h->dyn_box.p, n_traj, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
   if (use_items) fot_sweep_items<<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
@@ -522,9 +523,7 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   int bounds[9] = {0, nq, nq, nq, nq, nq, nq, nq, nq};
   if ((size_t)nq * dyn_q_bytes > ((size_t)8 << 20) && nq >= 1024) {
     // chunk sizes in whole waves of the sweep (one CTA per query, two CTAs per SM) where possible
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const int wave = 2 * sms;
+    const int wave = 2 * h->sms;
     auto waves = [&](int frac16) { const int w = std::max(1, (int)((long long)nq * frac16 / 16 / wave)); return w * wave; };
     const int cuts[] = {waves(1), waves(3), waves(6), waves(11), nq};  // about 1/16, 1/8, 3/16, 5/16, 5/16 of the queries
     n_chunks = 5;
@@ -739,14 +738,11 @@ extern "C" int fot_safety_metrics_device(int device, void* stream, int n_q, int 
     return fail(FOT_ERR_ARG, "fot_safety_metrics_device: bad argument");
   int rc = pred_begin(device, "fot_safety_metrics_device: bad device ordinal");
   if (rc != FOT_OK) return rc;
-  static thread_local double* d_off = nullptr;          // footprint offsets: a few doubles, copied per call
-  if (n_circ > 0) {
-    if (!d_off) CK(cudaMalloc(&d_off, FOT_MAX_CIRCLES * sizeof(double)));
-    CK(cudaMemcpyAsync(d_off, offsets, n_circ * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  }
+  CircleOffsets off{};
+  for (int i = 0; i < n_circ; ++i) off.v[i] = offsets[i];
   const long long threads = (long long)n_q * 32;
   fot_safety_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ego, ped_pos, ped_vel, n_peds, out, n_q, P,
-                                                                                         combined_radius, d_off, n_circ);
+                                                                                         combined_radius, off, n_circ);
   return pred_end(stream);
 }
 

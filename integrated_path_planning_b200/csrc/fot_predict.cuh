@@ -217,10 +217,13 @@ __global__ void fot_best_pick_kernel(const double* __restrict__ dist, int32_t* _
 // of sight, the clearance and the clearance restricted to pedestrians ahead of the vehicle.  These are the
 // inputs of the fail-safe state machine, needed once per query and step in batched roll-outs.
 // One warp per query; out[q] = {min_distance, collision, ttc, clearance, clearance_ahead}.
+struct CircleOffsets {
+  double v[FOT_MAX_CIRCLES];          // EgoFootprint.offsets, passed by value (a kernel parameter, no device buffer)
+};
 __global__ void fot_safety_kernel(const double* __restrict__ ego, const double* __restrict__ ped_pos,
                                   const double* __restrict__ ped_vel, const int32_t* __restrict__ n_peds,
                                   double* __restrict__ out, int n_q, int P, double combined_radius,
-                                  const double* __restrict__ offsets, int n_circ) {
+                                  const CircleOffsets offsets, int n_circ) {
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (q >= n_q) return;
   const double* e = ego + 5 * (size_t)q;
@@ -235,7 +238,7 @@ __global__ void fot_safety_kernel(const double* __restrict__ ego, const double* 
     const double vx = ped_vel[((size_t)q * P + p) * 2], vy = ped_vel[((size_t)q * P + p) * 2 + 1];
     const bool ahead = (px - x) * hx + (py - y) * hy > 0.0;                    // :373-374
     for (int c = 0; c < (n_circ > 0 ? n_circ : 1); ++c) {
-      const double cx = n_circ > 0 ? x + offsets[c] * hx : x, cy = n_circ > 0 ? y + offsets[c] * hy : y;   // footprint.py:45
+      const double cx = n_circ > 0 ? x + offsets.v[c] * hx : x, cy = n_circ > 0 ? y + offsets.v[c] * hy : y;   // footprint.py:45
       const double rx = px - cx, ry = py - cy;
       const double dist = sqrt(rx * rx + ry * ry);                             // :337-339
       dmin = fmin(dmin, dist);
