@@ -174,10 +174,12 @@ int fot_probe_fma_tflops(int device, int kind, double* tflops_out);
  *   staleness      [n_q] or NULL (= 0)
  *   cur_pos        [n_q][P][2] or NULL: the t = 0 prepend of integrated_simulator.py:503-513 (skipped,
  *                  last step duplicated, when the first predicted step already equals it for every pedestrian)
+ *   obs_float32    != 0: treat the observations as the float32 tensors the simulator's observer produces
+ *                  (observer.py:131-132): positions rounded to float32, velocity a float32 quotient
  *   out            [n_q][P][T_out][2], T_out = n_steps + (cur_pos != NULL) */
 int fot_predict_cv_device(int device, void* stream, int n_q, int P, const double* p_curr, const double* p_prev,
                           const double* staleness, double sgan_dt, const double* time_target, int n_steps,
-                          const double* cur_pos, double* out);
+                          const double* cur_pos, int obs_float32, double* out);
 
 /* Replaces TrajectoryPredictor.process_prediction (:233-313) for S samples per query.
  *   pred   [n_q][S][pred_len][P][2]  raw predictor output (pred_len <= 64)

@@ -81,7 +81,7 @@ SYMBOLS = (
     ("fot_launch_stage_ms", C.c_int, (C.c_void_p, C.c_int, C.POINTER(C.c_float * 3))),
     ("fot_probe_fma_tflops", C.c_int, (C.c_int, C.c_int, c_double_p)),
     ("fot_predict_cv_device", C.c_int, (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)),
+                                        C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p)),
     ("fot_process_prediction_device", C.c_int, (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_void_p)),
     ("fot_select_best_sample_device", C.c_int, (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

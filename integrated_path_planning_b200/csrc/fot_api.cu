@@ -680,7 +680,7 @@ static int pred_end(void* stream) {
 
 extern "C" int fot_predict_cv_device(int device, void* stream, int n_q, int P, const double* p_curr, const double* p_prev,
                                      const double* staleness, double sgan_dt, const double* time_target, int n_steps,
-                                     const double* cur_pos, double* out) {
+                                     const double* cur_pos, int obs_float32, double* out) {
   if (n_q < 1 || P < 1 || n_steps < 1 || !p_curr || !time_target || !out || !(sgan_dt > 0.0))
     return fail(FOT_ERR_ARG, "fot_predict_cv_device: bad argument");
   int rc = pred_begin(device, "fot_predict_cv_device: bad device ordinal");
@@ -689,7 +689,7 @@ extern "C" int fot_predict_cv_device(int device, void* stream, int n_q, int P, c
   const size_t smem = (size_t)P * 2 * sizeof(double);
   if (smem > 48 * 1024) return fail(FOT_ERR_TOO_LARGE, "fot_predict_cv_device: too many pedestrians per query");
   fot_cv_kernel<<<n_q, 256, smem, (cudaStream_t)stream>>>(p_curr, p_prev, staleness, time_target, cur_pos, out, P, n_steps,
-                                                          T_out, sgan_dt);
+                                                          T_out, sgan_dt, obs_float32);
   return pred_end(stream);
 }
 

@@ -45,7 +45,7 @@ __device__ __forceinline__ bool block_needs_prepend(const double* first_xy, int 
 __global__ void fot_cv_kernel(const double* __restrict__ p_curr, const double* __restrict__ p_prev,
                               const double* __restrict__ staleness, const double* __restrict__ time_target,
                               const double* __restrict__ cur_pos, double* __restrict__ out, int P, int n_steps,
-                              int T_out, double sgan_dt) {
+                              int T_out, double sgan_dt, int obs_float32) {
   const int q = blockIdx.x;
   const double* pc = p_curr + (size_t)q * P * 2;
   const double* pp = p_prev ? p_prev + (size_t)q * P * 2 : nullptr;
@@ -54,10 +54,16 @@ __global__ void fot_cv_kernel(const double* __restrict__ p_curr, const double* _
   const double stale = staleness ? staleness[q] : 0.0;
   const double t0 = time_target[0] + stale;
   extern __shared__ double s_first[];                   // [P][2] first predicted step
-  for (int e = threadIdx.x; e < 2 * P; e += blockDim.x) {
-    const double v = pp ? (pc[e] - pp[e]) / sgan_dt : 0.0;           // :211
-    s_first[e] = pc[e] + v * t0;
-  }
+  // obs_float32: the simulator hands the predictor float32 observation tensors (observer.py:131-132), so the
+  // positions are float32 values and the velocity is a float32 difference divided by float32(sgan_dt); the
+  // extrapolation itself is float64 (NumPy promotes float32 * float64-scalar to float64).
+  auto base = [&](int e) { return obs_float32 ? (double)(float)pc[e] : pc[e]; };
+  auto vel = [&](int e) {
+    if (!pp) return 0.0;
+    if (obs_float32) return (double)(((float)pc[e] - (float)pp[e]) / (float)sgan_dt);
+    return (pc[e] - pp[e]) / sgan_dt;                                 // :211
+  };
+  for (int e = threadIdx.x; e < 2 * P; e += blockDim.x) s_first[e] = base(e) + vel(e) * t0;
   __syncthreads();
   const bool prepend = cur && block_needs_prepend(s_first, 2, cur, P);
   const int shift = prepend ? 1 : 0;
@@ -69,10 +75,8 @@ __global__ void fot_cv_kernel(const double* __restrict__ p_curr, const double* _
     } else {
       const int i = min(k - shift, n_steps - 1);
       const double t = time_target[i] + stale;                        // :225
-      const double vx = pp ? (pc[2 * p] - pp[2 * p]) / sgan_dt : 0.0;
-      const double vy = pp ? (pc[2 * p + 1] - pp[2 * p + 1]) / sgan_dt : 0.0;
-      x = pc[2 * p] + vx * t;                                         // :226
-      y = pc[2 * p + 1] + vy * t;
+      x = base(2 * p) + vel(2 * p) * t;                               // :226
+      y = base(2 * p + 1) + vel(2 * p + 1) * t;
     }
     o[(size_t)idx * 2] = x;
     o[(size_t)idx * 2 + 1] = y;

@@ -67,11 +67,14 @@ class DevicePredictionPostprocessor:
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # -- API -----------------------------------------------------------------------------------
-    def predict_cv(self, p_curr, p_prev=None, staleness=None, current_positions=None, out=None):
+    def predict_cv(self, p_curr, p_prev=None, staleness=None, current_positions=None, out=None,
+                   obs_float32: bool = False):
         """Constant-velocity obstacle tensor.  p_curr / p_prev [n_q, P, 2] (the last two observation
         samples, sgan_dt apart; p_prev None = zero velocity), staleness scalar or [n_q],
         current_positions [n_q, P, 2] or None.  Returns [n_q, 1, P, T, 2] on the device, T = n_steps
-        (+ 1 with the t = 0 column); `out` re-uses a caller-owned buffer of that shape."""
+        (+ 1 with the t = 0 column); `out` re-uses a caller-owned buffer of that shape.  obs_float32: treat
+        the observations as the float32 tensors the reference's observer hands its predictor (the simulator's
+        real data flow); the default takes them as the float64 values given."""
         import torch
         n_q, P = p_curr.shape[0], p_curr.shape[1]
         pc = self._dev_f64(p_curr, (n_q, P, 2))
@@ -84,7 +87,8 @@ class DevicePredictionPostprocessor:
         elif tuple(out.shape) != (n_q, 1, P, T, 2) or out.dtype != torch.float64 or not out.is_contiguous():
             raise ValueError("out must be a contiguous float64 tensor of shape [n_q, 1, P, T, 2]")
         _lib.check(self.lib.fot_predict_cv_device(self.device, self._stream(), n_q, P, _p(pc), _p(pp), _p(st), self.sgan_dt,
-                                                  _p(self.time_target), self.n_steps, _p(cur), _p(out)), "fot_predict_cv_device")
+                                                  _p(self.time_target), self.n_steps, _p(cur), int(bool(obs_float32)), _p(out)),
+                   "fot_predict_cv_device")
         return out
 
     def process_prediction(self, pred, anchor=None, staleness=None):

@@ -29,7 +29,9 @@ def time_grid(sim_dt: float, plan_horizon: float, pred_len: int, sgan_dt: float)
 
 
 def predict_cv(obs_traj: np.ndarray, sgan_dt: float, time_target: np.ndarray, staleness: float = 0.0) -> np.ndarray:
-    """obs_traj [obs_len, P, 2] -> [P, n_steps, 2]  (:188-231)."""
+    """obs_traj [obs_len, P, 2] -> [P, n_steps, 2]  (:188-231).  A float32 obs_traj reproduces the simulator's
+    data flow (the observer hands over float32 tensors): NumPy then keeps the velocity in float32 and promotes
+    the extrapolation to float64, exactly as in the reference."""
     if obs_traj.shape[0] < 2:
         current_pos = obs_traj[-1]
         velocities = np.zeros((current_pos.shape[0], 2))

@@ -52,6 +52,8 @@ def main():
         store[n + "_dense"] = tp.process_prediction(c["raw"].copy(), anchor_pos=c["anchor"], staleness=c["staleness"])
         store[n + "_cv"] = tp.predict_cv(torch.from_numpy(c["obs"]), staleness=c["staleness"])
         store[n + "_cv1"] = tp.predict_cv(torch.from_numpy(c["obs"][-1:]), staleness=c["staleness"])
+        # the simulator's real data flow: float32 observation tensors (observer.py:131-132)
+        store[n + "_cv32"] = tp.predict_cv(torch.from_numpy(c["obs"]).float(), staleness=c["staleness"])
     # closest-to-mean selection through predict_single_best with replayed samples
     rng = np.random.default_rng(7)
     for j, (S, P, T) in enumerate([(6, 5, 50), (20, 11, 50), (3, 2, 60)]):

@@ -36,6 +36,8 @@ def test_golden_resampling_and_cv():
         assert np.array_equal(_bits(cv), _bits(G[n + "_cv"])), n
         cv1 = pp.predict_cv(obs[-1][None], None, stale).cpu().numpy()[0, 0]
         assert np.array_equal(_bits(cv1), _bits(G[n + "_cv1"])), n
+        cv32 = pp.predict_cv(obs[-1][None], obs[-2][None], stale, obs_float32=True).cpu().numpy()[0, 0]
+        assert np.array_equal(_bits(cv32), _bits(G[n + "_cv32"])), n
 
 
 def test_golden_selection():

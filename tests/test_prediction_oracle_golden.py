@@ -23,6 +23,7 @@ def test_process_prediction_and_cv_match_reference():
         assert _same(PO.process_prediction(G[n + "_raw"], 0.4, tt, anchor, stale), G[n + "_dense"]), n
         assert _same(PO.predict_cv(G[n + "_obs"], 0.4, tt, stale), G[n + "_cv"]), n
         assert _same(PO.predict_cv(G[n + "_obs"][-1:], 0.4, tt, stale), G[n + "_cv1"]), n
+        assert _same(PO.predict_cv(G[n + "_obs"].astype(np.float32), 0.4, tt, stale), G[n + "_cv32"]), n
 
 
 def test_select_best_matches_reference():
