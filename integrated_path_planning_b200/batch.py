@@ -57,11 +57,11 @@ class DeviceBatch:
         dev = torch.device("cuda", eng.device)
         fs = np.ascontiguousarray(frenet_states, dtype=np.float64).reshape(-1, 6)
         n_q = fs.shape[0]
-        target = np.ascontiguousarray(np.broadcast_to(np.asarray(target_speed, np.float64), (n_q,)))
+        target = np.array(np.broadcast_to(np.asarray(target_speed, np.float64), (n_q,)))
         lim = planner.resolve_limits(None) if limits is None else limits
-        lim = np.ascontiguousarray(np.broadcast_to(np.asarray(lim, np.float64), (n_q, 4)))
+        lim = np.array(np.broadcast_to(np.asarray(lim, np.float64), (n_q, 4)))
         stop = np.full(n_q, np.nan) if max_stop_distance is None else \
-            np.ascontiguousarray(np.broadcast_to(np.asarray(max_stop_distance, np.float64), (n_q,)))
+            np.array(np.broadcast_to(np.asarray(max_stop_distance, np.float64), (n_q,)))
         v_grid, n_v = speed_grid_batch(target, eng.d_t_s)
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         self.t = {"frenet": up(fs), "target": up(target), "limits": up(lim), "stop": up(stop),

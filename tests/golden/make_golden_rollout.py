@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""Record closed-loop roll-outs of the UNMODIFIED reference simulator (BASELINE config 1 and variants).
+
+Build container only (imports /root/reference read-only):   python tests/golden/make_golden_rollout.py
+
+scenarios/scenario_01_cv.yaml is run through the reference's IntegratedSimulator exactly as
+tests/golden/make_golden.py does (pysocialforce stubbed, pedestrians replayed at constant velocity through
+ReplayPedestrianSource, CV predictor), for the scenario itself and three perturbed variants (pedestrian
+start positions / speeds, ego start speed).  Per step the ego state, the fail-safe state, whether a path was
+found and how many plan() calls the step made are stored in tests/golden/rollout_s01.npz, together with the
+inputs (pedestrian tracks, knobs) the batched driver needs to repeat the run.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("FOT_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.modules.setdefault("pysocialforce", types.ModuleType("pysocialforce"))
+
+from loguru import logger  # noqa: E402
+
+logger.remove()
+
+KNOB_KEYS = ("dt", "total_time", "obs_len", "ego_target_speed", "ego_max_speed", "ego_max_accel", "ego_max_curvature",
+             "ego_max_lat_accel", "ego_radius", "ped_radius", "obstacle_radius", "d_road_w", "max_road_width", "min_t",
+             "max_t", "d_t_s", "k_j", "k_t", "k_d", "k_s_dot", "k_lat", "k_lon",
+             "state_machine_trigger_clearance_caution", "state_machine_trigger_time_headway",
+             "state_machine_recover_clearance_caution", "state_machine_recover_clearance_emergency",
+             "state_machine_safe_distance_caution", "state_machine_safe_distance_emergency",
+             "state_machine_caution_speed_multiplier", "state_machine_caution_accel_multiplier",
+             "state_machine_emergency_accel_multiplier", "state_machine_emergency_lat_accel_multiplier",
+             "state_machine_envelope_decel", "state_machine_envelope_standoff", "ego_emergency_decel",
+             "chance_epsilon", "collision_margin_inflation")
+
+
+def run_variant(seed):
+    import yaml
+    from src.config import SimulationConfig, validate_config
+    from src.core.data_structures import VehicleState
+    from src.simulation.integrated_simulator import IntegratedSimulator
+    from src.simulation.replay_source import ReplayPedestrianSource
+
+    with open(os.path.join(REF, "scenarios", "scenario_01_cv.yaml")) as f:
+        d = yaml.safe_load(f)
+    peds = np.array(d.pop("ped_initial_states"), dtype=float)
+    d.pop("ped_groups", None)
+    d["sgan_model_path"] = None
+    d["visualization_enabled"] = False
+    d["prediction_method"] = "cv"
+    if seed > 0:
+        rng = np.random.default_rng(seed)
+        peds[:, 0:2] += rng.normal(0, 1.5, peds[:, 0:2].shape)
+        peds[:, 2:4] *= rng.uniform(0.6, 1.4, (len(peds), 1))
+        d["ego_initial_state"] = [0.0, float(rng.uniform(-0.3, 0.3)), 0.0, float(rng.uniform(2.0, 6.0)), 0.0]
+    cfg = SimulationConfig(**d)
+    validate_config(cfg)
+    sim = IntegratedSimulator(cfg)
+    assert sim.ego_footprint is None and len(sim.static_obstacle_points) == 0
+    n_frames = int(cfg.total_time / cfg.dt) + 200
+    t = np.arange(n_frames)[:, None, None] * cfg.dt
+    traj = peds[None, :, 0:2] + peds[None, :, 2:4] * t
+    sim.pedestrian_sim = ReplayPedestrianSource(traj, dt=cfg.dt)
+
+    n_calls = [0]
+    original = sim.planner.plan
+
+    def counting_plan(*a, **k):
+        n_calls[0] += 1
+        return original(*a, **k)
+
+    sim.planner.plan = counting_plan
+    sim.warmup()
+    order = {VehicleState.NORMAL: 0, VehicleState.CAUTION: 1, VehicleState.EMERGENCY: 2}
+    ego, fsm, found, calls = [], [], [], []
+    n_steps = int(cfg.total_time / cfg.dt)
+    reason = "timeout"
+    for i in range(n_steps):
+        n_calls[0] = 0
+        res = sim.step()
+        e = sim.ego_state
+        ego.append([e.x, e.y, e.yaw, e.v, e.a])
+        fsm.append(order[sim.state_machine.current_state])
+        found.append(res.planned_path is not None)
+        calls.append(n_calls[0])
+        if res.metrics.get("collision", False):
+            reason = "collision"
+            break
+        s_now = sim.coord_converter.find_nearest_point_on_path(e.x, e.y)[0]
+        if sim.reference_path.s[-1] - s_now < 2.0:
+            reason = "goal"
+            break
+    knobs = {k: getattr(cfg, k, None) for k in KNOB_KEYS}
+    return dict(traj=traj, ego0=np.array(cfg.ego_initial_state, dtype=float), ego=np.array(ego), fsm=np.array(fsm),
+                found=np.array(found), calls=np.array(calls), reason=reason, knobs=knobs,
+                wx=np.array(cfg.reference_waypoints_x, dtype=float), wy=np.array(cfg.reference_waypoints_y, dtype=float))
+
+
+def main():
+    store = {}
+    for k, seed in enumerate((0, 1, 2, 3)):
+        r = run_variant(seed)
+        for name in ("traj", "ego0", "ego", "fsm", "found", "calls", "wx", "wy"):
+            store[f"v{k}/{name}"] = r[name]
+        store[f"v{k}/reason"] = np.array(r["reason"])
+        if k == 0:
+            for key, val in r["knobs"].items():
+                store["knob/" + key] = np.array(np.nan if val is None else val, dtype=float)
+        states = np.bincount(r["fsm"], minlength=3)
+        print(f"variant {k}: {len(r['ego'])} steps, {r['reason']}, plan calls {int(r['calls'].sum())}, "
+              f"states N/C/E {states.tolist()}, failed steps {int((~r['found']).sum())}")
+    store["n_variants"] = np.array(4)
+    np.savez_compressed(os.path.join(HERE, "rollout_s01.npz"), **store)
+    print("wrote rollout_s01.npz", os.path.getsize(os.path.join(HERE, "rollout_s01.npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""Batched closed-loop roll-outs against the reference simulator's recorded runs.
+
+tests/golden/rollout_s01.npz holds four closed-loop runs of the UNMODIFIED reference IntegratedSimulator
+(scenario_01_cv and three perturbed variants; tests/golden/make_golden_rollout.py): per step the ego state,
+the fail-safe state, whether a path was found and how many plan() calls the step made, plus how the run
+ended.  The batched driver advances all four in lock-step, one sweep launch per planning attempt, and has
+to reproduce every one of them -- through the fail-safe escalations, emergency stops and the collision
+terminations of variants 1 and 2 -- with the feedback loop closed over ITS OWN outputs.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+# ego states feed back into the next step's query for hundreds of steps; the sweep's points agree with the
+# reference to ~1e-12 per call (tests/test_gpu_golden.py), so the closed loop is held to 1e-7 absolute.
+EGO_TOL = 1e-7
+
+
+@pytest.fixture(scope="module")
+def golden():
+    z = np.load(os.path.join(HERE, "golden", "rollout_s01.npz"))
+    knobs = {k[5:]: float(z[k]) for k in z.files if k.startswith("knob/")}
+    n = int(z["n_variants"])
+    runs = [{name: z[f"v{i}/{name}"] for name in ("traj", "ego0", "ego", "fsm", "found", "calls", "wx", "wy", "reason")}
+            for i in range(n)]
+    return knobs, runs
+
+
+def _drive(knobs, runs):
+    from integrated_path_planning_b200.rollout import BatchedClosedLoop
+    tracks = np.stack([r["traj"] for r in runs])
+    ego0 = np.stack([r["ego0"] for r in runs])
+    sim = BatchedClosedLoop(runs[0]["wx"], runs[0]["wy"], knobs, tracks, ego0)
+    sim.warmup()
+    return sim, sim.run()
+
+
+def test_batch_reproduces_reference_rollouts(golden):
+    knobs, runs = golden
+    sim, out = _drive(knobs, runs)
+    for i, r in enumerate(runs):
+        n = len(r["ego"])
+        assert out["steps"][i] == n, f"variant {i}: {out['steps'][i]} steps, reference {n}"
+        assert out["reason"][i] == str(r["reason"]), f"variant {i}"
+        np.testing.assert_array_equal(out["found"][i, :n], r["found"], err_msg=f"variant {i} found")
+        np.testing.assert_array_equal(out["fsm"][i, :n], r["fsm"], err_msg=f"variant {i} fail-safe state")
+        np.testing.assert_array_equal(out["calls"][i, :n], r["calls"], err_msg=f"variant {i} plan() calls")
+        np.testing.assert_allclose(out["ego"][i, :n], r["ego"], rtol=0, atol=EGO_TOL, err_msg=f"variant {i} ego")
+    assert sim.n_plan_calls == sum(int(r["calls"].sum()) for r in runs)
+
+
+def test_single_rollout_equals_its_row_in_the_batch(golden):
+    """Simulations in a batch are independent: variant 1 alone gives what it gives inside the batch of four."""
+    knobs, runs = golden
+    _, alone = _drive(knobs, runs[1:2])
+    _, batch = _drive(knobs, runs)
+    n = int(alone["steps"][0])
+    assert n == int(batch["steps"][1])
+    np.testing.assert_array_equal(alone["ego"][0, :n], batch["ego"][1, :n])
+    np.testing.assert_array_equal(alone["fsm"][0, :n], batch["fsm"][1, :n])
