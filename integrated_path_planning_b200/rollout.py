@@ -23,16 +23,16 @@ wired into this driver yet.
 from __future__ import annotations
 
 import math
+import time
 from typing import Dict, Optional
 
 import numpy as np
 
 from . import _lib
 from .batch import BatchFrenetPlanner, DeviceBatch
-from .frenet_host import CoordinateConverter, ego_to_frenet
+from .frenet_host import BatchCoordinateConverter, ego_to_frenet_many
 from .prediction import DevicePredictionPostprocessor, safety_metrics
 from .spline import CubicSpline2D
-from .types import EgoVehicleState
 
 NORMAL, CAUTION, EMERGENCY = 0, 1, 2
 SGAN_DT = 0.4          # the observer samples at the SGAN rate whatever the simulation dt (integrated_simulator.py:325)
@@ -163,8 +163,8 @@ class BatchedClosedLoop:
         # per-simulation planner state: ego curvature cache and the two nearest-point caches (the planner's
         # converter and the simulator's own goal-check converter are separate objects in the reference)
         self.last_kappa = np.zeros(self.n)
-        self.plan_conv = [CoordinateConverter(self.spline) for _ in range(self.n)]
-        self.goal_conv = [CoordinateConverter(self.spline) for _ in range(self.n)]
+        self.plan_conv = BatchCoordinateConverter(self.spline, self.n)
+        self.goal_conv = BatchCoordinateConverter(self.spline, self.n)
         # replayed pedestrians (replay_source.py:31-111): forward-difference velocities, shared clock
         vel = np.zeros_like(self.tracks)
         if self.n_frames >= 2:
@@ -179,6 +179,7 @@ class BatchedClosedLoop:
         self.active = np.ones(self.n, dtype=bool)
         self.reason = np.array(["timeout"] * self.n, dtype=object)
         self.n_plan_calls = 0
+        self.timers = {"frenet_host": 0.0, "sweep": 0.0, "prediction": 0.0, "metrics": 0.0, "total": 0.0}
 
     # -- pedestrians + observer -----------------------------------------------------------------
     def _ped_step(self):
@@ -202,15 +203,11 @@ class BatchedClosedLoop:
     # -- one planning attempt for the simulations `idx` -------------------------------------------
     def _plan(self, idx, target, limits, msd, dyn_dev):
         import torch
-        frenet = np.zeros((len(idx), 6))
-        ok = np.ones(len(idx), dtype=bool)
-        for j, i in enumerate(idx):
-            fs = ego_to_frenet(self.plan_conv[i], EgoVehicleState(*self.ego[i]), float(self.last_kappa[i]))
-            if fs is None:
-                ok[j] = False                     # conversion failure: plan() returns None (frenet_planner.py:346-374)
-            else:
-                frenet[j] = fs
+        t0 = time.perf_counter()
+        # ok False = conversion failure: plan() returns None (frenet_planner.py:346-374)
+        frenet, ok = ego_to_frenet_many(self.plan_conv, idx, self.ego[idx], self.last_kappa[idx])
         self.n_plan_calls += len(idx)
+        t1 = time.perf_counter()
         sel = torch.as_tensor(np.asarray(idx), device=dyn_dev.device)
         batch = DeviceBatch(self.planner, frenet, target, dyn_dev.index_select(0, sel), _lib.FOT_DYN_SINGLE,
                             limits=limits, max_stop_distance=msd)
@@ -219,11 +216,14 @@ class BatchedClosedLoop:
         wlen = batch.out["winner_len"].cpu().numpy()
         win = batch.out["winner"][:, 9:15, :2].cpu().numpy()          # x y yaw c v a, first two samples
         found = ok & (best >= 0)
+        self.timers["frenet_host"] += t1 - t0
+        self.timers["sweep"] += time.perf_counter() - t1
         return found, wlen, win
 
     # -- one simulation step for every active simulation -------------------------------------------
     def step(self):
         k, dt = self.k, self.dt
+        t_step = time.perf_counter()
         idx = np.nonzero(self.active)[0]
         self._ped_step()
         pos, vel = self.tracks[:, self.frame], self.vel[:, self.frame]
@@ -236,8 +236,11 @@ class BatchedClosedLoop:
         else:
             import torch
             dyn = torch.from_numpy(np.ascontiguousarray(pos[:, None, :, None, :])).to(self.post._dev)
+        t_pred = time.perf_counter()
         m = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, device=self.device)
         clearance, ahead = m["clearance"].cpu().numpy(), m["clearance_ahead"].cpu().numpy()
+        self.timers["prediction"] += t_pred - t_step
+        self.timers["metrics"] += time.perf_counter() - t_pred
         last_clearance = ahead.copy()                                  # :566-567 feeds the emergency stop
 
         # planning cycle with escalation retries (:529-653)
@@ -280,20 +283,20 @@ class BatchedClosedLoop:
                 v = max(0.0, v - max_dec * dt)
                 self.ego[i] = [x, y, yaw, v, -max_dec if v > 0 else 0.0]
                 self.last_kappa[i] = 0.0                               # planner.reset_ego_curvature()
-                if found[j]:                                           # a path of one sample still updated the cache first
-                    pass
         # termination (:870-886): collision of the NEW ego state with the same pedestrian frame, then the goal
+        t_m = time.perf_counter()
         m2 = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, device=self.device)
         collided = m2["collision"].cpu().numpy()
-        s_end = self.spline.s[-1]
-        for i in idx:
-            if collided[i]:
-                self.active[i], self.reason[i] = False, "collision"
-                continue
-            s_now = self.goal_conv[i].find_nearest_point_on_path(self.ego[i, 0], self.ego[i, 1])[0]
-            if s_end - s_now < 2.0:
-                self.active[i], self.reason[i] = False, "goal"
+        self.timers["metrics"] += time.perf_counter() - t_m
+        hit = idx[collided[idx]]
+        self.active[hit], self.reason[hit] = False, "collision"
+        alive = idx[~collided[idx]]
+        if len(alive):
+            s_now = self.goal_conv.nearest_s(alive, self.ego[alive, 0], self.ego[alive, 1])
+            done = alive[self.spline.s[-1] - s_now < 2.0]
+            self.active[done], self.reason[done] = False, "goal"
         self.time += dt
+        self.timers["total"] += time.perf_counter() - t_step
         return idx, found, calls
 
     def run(self, n_steps: Optional[int] = None):
