@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cmath>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "fot_kernels.cuh"
@@ -61,8 +62,13 @@ struct fot_handle {
   int device = 0;
   Plan plan{};
   void* tables_dev = nullptr;
-  cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
-  cudaEvent_t ev_copy[8] = {}, ev_done[8] = {};
+  cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr, copy_stream2 = nullptr, d2h_stream = nullptr;
+  static constexpr int kMaxChunks = 16;
+  cudaEvent_t ev_copy[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
+  cudaEvent_t ev_join = nullptr, ev_blob = nullptr;
+  cudaStream_t pstream[4] = {};      // gated launches: one stream per range of queries, earlier ranges at higher priority
+  Buf gate_d, gate_h;                // gated launches: device progress / error words, pinned source words
+  uint32_t gate_epoch = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   static constexpr int kRing = 256;
@@ -73,7 +79,7 @@ struct fot_handle {
   Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_box, cost_tab;   // device scratch
   int last_sweep_kind = 0;           // 1: fot_sweep_items, 2: fot_sweep (generic)
   Buf stage_h, stage_d, out_d, dyn_d, stat_d;   // host-API staging
-  fot_handle() { stage_h.host = true; }
+  fot_handle() { stage_h.host = true; gate_h.host = true; }
 };
 
 extern "C" int fot_abi_version(void) { return FOT_ABI_VERSION; }
@@ -139,7 +145,17 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   P.n_steps = I; P.n_steps_b = I + nT;
 
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_blob, cudaEventDisableTiming));
+  {
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));     // numerically lower = higher priority
+    for (int i = 0; i < 4; ++i)
+      CK(cudaStreamCreateWithPriority(&h->pstream[i], cudaStreamNonBlocking, std::min(least, greatest + i)));
+  }
   CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev_copy) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto& ev : h->ev_done) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -169,8 +185,13 @@ extern "C" int fot_destroy(fot_handle_t* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto ev : h->ev_copy) if (ev) cudaEventDestroy(ev);
   for (auto ev : h->ev_done) if (ev) cudaEventDestroy(ev);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_blob) cudaEventDestroy(h->ev_blob);
+  for (auto ps : h->pstream) if (ps) cudaStreamDestroy(ps);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return FOT_OK;
@@ -254,7 +275,8 @@ static int sweep_geometry(const fot_handle* h, const fot_batch_t* b, SweepGeom* 
 // Geometry of the sample-major kernel (fot_sweep_items).  Returns false when the batch's shape is
 // outside what that kernel covers (very long time grids, huge per-step obstacle counts); the
 // candidate-major fot_sweep then runs.
-static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g, size_t* smem_bytes) {
+static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g, size_t* smem_bytes,
+                          bool want_fused_box = false, int bpc_override = 0) {
   const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B, nx = h->plan.cfg.nx;
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const long long SPl = has_dyn ? (long long)b->S * b->P : 0;
@@ -277,6 +299,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
     const long long total = (long long)b->n_q * G.blocks_per_query;
     long long bpc = total / ((long long)sms * 2 * 4);
     bpc = std::max<long long>(1, std::min<long long>(bpc, G.blocks_per_query));
+    if (bpc_override > 0) bpc = std::max(1, std::min(bpc_override, (int)G.blocks_per_query));
     if (const char* env = getenv("FOT_BPC")) bpc = std::max(1, std::min(atoi(env), (int)G.blocks_per_query));
     G.ctas_per_query = (int)((G.blocks_per_query + bpc - 1) / bpc);
     G.bpc = (G.blocks_per_query + G.ctas_per_query - 1) / G.ctas_per_query;
@@ -294,6 +317,9 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   if (const char* env = getenv("FOT_QCAP")) G.qcap = std::max(1, std::min(1 << 15, atoi(env)));   // tests: force the queue-full path
   G.spline_smem = nx <= 128 ? 1 : 0;
   const size_t dyn_bytes = (size_t)SP * b->T_obs * 16;
+  // FOT_FUSED_BOX=1 (tests, tuning): trajectory boxes in the sweep even for a resident tensor
+  bool fuse = want_fused_box;
+  if (const char* env = getenv("FOT_FUSED_BOX")) fuse = fuse || atoi(env) != 0;
   auto layout = [&](bool stage) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
@@ -304,6 +330,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
     G.o_vlast = take((size_t)G.pcap * nd * 8);
     G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);
     G.o_dyn = take(stage ? dyn_bytes : 0);
+    G.o_box = take(stage && fuse ? (size_t)SP * 16 : 0);
     G.o_fn = take((size_t)G.pcap * 4);
     G.o_flags = take((size_t)G.pcap * G.nw4 * 4);
     G.o_hit = take((size_t)G.pcap * G.nwc * 4);
@@ -314,6 +341,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
     G.o_clean = take((size_t)G.pcap * G.nwc * 4);
     G.o_slow = take((size_t)G.threads * 2);
     G.stage_dyn = stage ? 1 : 0;
+    G.fused_box = stage && fuse ? 1 : 0;
     return off;
   };
   // stage the query's obstacle block in shared memory when two blocks per SM still fit
@@ -348,14 +376,41 @@ static int check_batch(const fot_handle* h, const fot_batch_t* b, const fot_resu
   return FOT_OK;
 }
 
-static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r, cudaStream_t st) {
+// q_off / q_total: this launch handles queries [q_off, q_off + b->n_q) of a batch of q_total whose chunks may be
+// in flight on two streams at once, so every scratch buffer is sized for the batch and addressed by q_off.
+// cuStreamWriteValue32 through the runtime's driver entry-point lookup (no link-time dependency on libcuda): a
+// stream-ordered 4-byte write with a memory fence before it, far cheaper than a 4-byte cudaMemcpyAsync.
+typedef int (*StreamWrite32)(cudaStream_t, unsigned long long, unsigned, unsigned);
+static StreamWrite32 stream_write32() {
+  static StreamWrite32 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr{};
+    if (getenv("FOT_GATE_MEMCPY")) return (StreamWrite32) nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (StreamWrite32)p;
+  }();
+  return fn;
+}
+
+struct Gate {
+  unsigned* word = nullptr;      // device slice flags (nullptr: not gated)
+  uint32_t epoch = 0;
+  int per = 1;                   // queries per upload slice
+};
+
+static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r, cudaStream_t st, size_t q_off = 0,
+                      size_t q_total = 0, Gate gate = Gate{}, int bpc_override = 0) {
+  if (q_total == 0) q_total = (size_t)b->n_q;
   // kernel choice: the sample-major fot_sweep_items unless the shape is outside its range (or
   // FOT_SWEEP=generic asks for the candidate-major kernel, which the tests use as a cross-check)
   ItemGeom ig{};
   size_t ismem = 0;
   const char* force = getenv("FOT_SWEEP");            // read per launch: the tests switch kernels in-process
-  bool use_items = item_geometry(h, b, &ig, &ismem);
+  bool use_items = item_geometry(h, b, &ig, &ismem, gate.word != nullptr, bpc_override);
   if (force && !strcmp(force, "generic")) use_items = false;
+  if (gate.word && !(use_items && ig.fused_box)) return fail(FOT_ERR_ARG, "gated launch needs fot_sweep_items with a staged obstacle block");
+  if (gate.word) { ig.gate = gate.word; ig.gate_epoch = gate.epoch; ig.gate_per = gate.per; ig.gate_q0 = (int32_t)q_off; }
   if (force && !strcmp(force, "items") && !use_items) return fail(FOT_ERR_ARG, "FOT_SWEEP=items: shape not supported by fot_sweep_items");
   SweepGeom g{};
   size_t smem = 0;
@@ -368,12 +423,17 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const size_t n_part = (size_t)b->n_q * g.blocks_per_query;
   if ((size_t)b->n_q * (size_t)g.blocks_per_query > 0x7fffffffull) return fail(FOT_ERR_ARG, "batch too large for one launch");
-  CK(h->part_cost.reserve(n_part * sizeof(double)));
-  CK(h->part_idx.reserve(n_part * sizeof(int32_t)));
+  // partial winners: chunks of one batch may cut their queries into different numbers of CTAs; the stride that
+  // addresses the scratch is the largest any chunk can use
+  const size_t part_stride = use_items ? (size_t)std::max(ig.blocks_per_query, ig.ctas_per_query) : (size_t)g.blocks_per_query;
+  if (q_off != 0 && !use_items) return fail(FOT_ERR_ARG, "chunk offsets need the fot_sweep_items path");
+  CK(h->part_cost.reserve(q_total * part_stride * sizeof(double)));
+  CK(h->part_idx.reserve(q_total * part_stride * sizeof(int32_t)));
   const int SP = has_dyn ? b->S * b->P : 0;
   const int SPp = (SP + 3) & ~3, Mp = (b->n_static + 3) & ~3;
   const int nq_s = b->static_per_query ? b->n_q : 1;
-  const bool need_box = use_items && has_dyn;
+  const bool need_box = use_items && has_dyn && !ig.fused_box;
+  const size_t cost_stride = (size_t)h->plan.cfg.n_T * (b->n_v_max + 2 * h->plan.cfg.n_d) + 3 * (size_t)h->plan.cfg.n_B;
   if (!use_items) {
     if (has_dyn) {
       CK(h->obs_tm.reserve((size_t)b->n_q * b->T_obs * 3 * SPp * sizeof(double)));
@@ -384,10 +444,11 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
       CK(h->stat_max2.reserve((size_t)nq_s * sizeof(double)));
     }
   } else {
-    if (need_box) CK(h->dyn_box.reserve((size_t)b->n_q * SP * sizeof(float4)));
-    const size_t stride = (size_t)h->plan.cfg.n_T * (b->n_v_max + 2 * h->plan.cfg.n_d) + 3 * (size_t)h->plan.cfg.n_B;
-    CK(h->cost_tab.reserve((size_t)b->n_q * stride * sizeof(double)));
+    if (need_box) CK(h->dyn_box.reserve(q_total * SP * sizeof(float4)));
+    CK(h->cost_tab.reserve(q_total * cost_stride * sizeof(double)));
   }
+  float4* dyn_box = need_box ? (float4*)h->dyn_box.p + q_off * SP : nullptr;
+  double* cost_tab = use_items ? (double*)h->cost_tab.p + q_off * cost_stride : nullptr;
 
   Batch B{};
   B.n_q = b->n_q; B.n_v_max = b->n_v_max;
@@ -401,12 +462,12 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   B.S = has_dyn ? b->S : 0; B.P = has_dyn ? b->P : 0; B.T_obs = has_dyn ? b->T_obs : 0; B.dyn_mode = b->dyn_mode;
   B.dyn_raw = has_dyn ? b->dyn : nullptr;
   B.static_raw = b->n_static > 0 ? b->static_obs : nullptr;
-  B.dyn_box = need_box ? (const float4*)h->dyn_box.p : nullptr;
-  B.cost_tab = use_items ? (const double*)h->cost_tab.p : nullptr;
+  B.dyn_box = dyn_box;
+  B.cost_tab = cost_tab;
   Out O{};
   O.best_idx = r->best_idx; O.best_cost = r->best_cost; O.stats = r->stats; O.winner_len = r->winner_len;
   O.winner = r->winner; O.cand_cat = r->cand_cat; O.cand_cost = r->cand_cost; O.cand_stride = r->cand_stride;
-  O.part_cost = (double*)h->part_cost.p; O.part_idx = (int32_t*)h->part_idx.p;
+  O.part_cost = (double*)h->part_cost.p + q_off * part_stride; O.part_idx = (int32_t*)h->part_idx.p + q_off * part_stride;
 
   cudaEvent_t* ring = h->ring.data() + (size_t)(h->n_launch % fot_handle::kRing) * 4;
   CK(cudaEventRecord(h->ev0, st));
@@ -440,8 +501,8 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
     const long long n_traj = need_box ? (long long)b->n_q * SP : 0;
     const long long ablocks = (n_traj * 32 + 255) / 256;
     if (cblocks + ablocks > 0x7fffffffll) return fail(FOT_ERR_ARG, "batch too large for one launch");
-    fot_prepass<<<(unsigned)(cblocks + ablocks), 256, 0, st>>>(h->plan, B, (double*)h->cost_tab.p, (unsigned)cblocks,
-                                                               (const double2*)b->dyn, (float4*)h->dyn_box.p, n_traj, b->T_obs);
+    fot_prepass<<<(unsigned)(cblocks + ablocks), 256, 0, st>>>(h->plan, B, cost_tab, (unsigned)cblocks,
+                                                               (const double2*)b->dyn, dyn_box, n_traj, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
   if (use_items) fot_sweep_items<<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
@@ -520,7 +581,10 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   // pipeline (the upload runs at PCIe speed), so the first chunks are small -- the sweep starts after
   // 1/16 of the upload -- and the rest are large enough to keep the wave tail short.
   int n_chunks = 1;
-  int bounds[9] = {0, nq, nq, nq, nq, nq, nq, nq, nq};
+  constexpr int kMaxChunks = fot_handle::kMaxChunks;
+  int bounds[kMaxChunks + 1];
+  bounds[0] = 0;
+  for (int c = 1; c <= kMaxChunks; ++c) bounds[c] = nq;
   if ((size_t)nq * dyn_q_bytes > ((size_t)8 << 20) && nq >= 1024) {
     // chunk sizes in whole waves of the sweep (one CTA per query, two CTAs per SM) where possible
     const int wave = 2 * h->sms;
@@ -530,16 +594,108 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     for (int c = 0; c < n_chunks; ++c) bounds[c + 1] = std::min(nq, std::max(cuts[c], bounds[c]));
   }
   if (const char* env = getenv("FOT_HOST_CHUNKS")) {
-    n_chunks = std::max(1, std::min(8, atoi(env)));
+    n_chunks = std::max(1, std::min(kMaxChunks, atoi(env)));
     const int per_ = (nq + n_chunks - 1) / n_chunks;
     for (int c = 0; c <= n_chunks; ++c) bounds[c] = std::min(nq, c * per_);
   }
+  if (const char* env = getenv("FOT_CHUNK_WAVES")) {       // tuning: chunk sizes in sweep waves, "1,2,3,4,3" (+ the rest)
+    const int wave = 2 * h->sms;
+    n_chunks = 0;
+    int at = 0;
+    for (const char* p = env; *p && n_chunks < kMaxChunks - 1 && at < nq;) {
+      at = std::min(nq, at + std::max(1, atoi(p)) * wave);
+      bounds[++n_chunks] = at;
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+    if (at < nq) bounds[++n_chunks] = nq;
+    for (int c = n_chunks + 1; c <= kMaxChunks; ++c) bounds[c] = nq;
+  }
+  // chunks alternate between two compute streams, so that the next chunk's CTAs fill the SMs the tail wave of
+  // the previous chunk leaves idle (the chunks touch disjoint scratch, see launch_all)
+  bool two_streams = n_chunks > 1;
+  if (const char* env = getenv("FOT_HOST_STREAMS")) two_streams = two_streams && atoi(env) >= 2;
+  if (two_streams) {
+    ItemGeom ig{};
+    size_t ismem = 0;
+    fot_batch_t probe = *b;
+    probe.n_q = bounds[1] - bounds[0];
+    const char* force = getenv("FOT_SWEEP");
+    if (!item_geometry(h, &probe, &ig, &ismem) || (force && !strcmp(force, "generic"))) two_streams = false;
+  }
+  // Gated launches (large uploads through fot_sweep_items): the sweep does not wait for whole chunks.  The upload
+  // is cut into fine slices, each followed by a 4-byte copy that publishes "queries uploaded so far"; the sweep
+  // is launched over few, large ranges of queries and every CTA waits for its own query's slice (ItemGeom::gate).
+  // The ranges only exist so that winners of the first queries go back while the last are still being swept.
+  bool gated = false;
+  int n_up = 0, ub[kGateSlices + 1] = {0};
+  Gate gate{};
+  {
+    const char* env = getenv("FOT_GATED");
+    const char* force = getenv("FOT_SWEEP");
+    const bool want = env ? atoi(env) != 0 : true;
+    if (want && n_chunks > 1 && has_dyn && nq < (1 << 22) && !(force && !strcmp(force, "generic"))) {
+      ItemGeom ig{};
+      size_t ismem = 0;
+      gated = item_geometry(h, b, &ig, &ismem, true) && ig.fused_box;
+    }
+  }
+  if (gated) {
+    const bool fresh = h->gate_d.p == nullptr;
+    CK(h->gate_d.reserve((kGateSlices + 1) * sizeof(uint32_t)));
+    CK(h->gate_h.reserve((kGateSlices + 1) * sizeof(uint32_t)));
+    if (fresh) CK(cudaMemset(h->gate_d.p, 0, (kGateSlices + 1) * sizeof(uint32_t)));
+    if (++h->gate_epoch == 0) h->gate_epoch = 1;             // 0 is the value of a fresh flag
+    gate.word = (unsigned*)h->gate_d.p;
+    gate.epoch = h->gate_epoch;
+    n_up = 16;
+    if (const char* env = getenv("FOT_GATE_UPLOADS")) n_up = std::max(1, std::min(kGateSlices, atoi(env)));
+    gate.per = (nq + n_up - 1) / n_up;
+    n_up = (nq + gate.per - 1) / gate.per;
+    for (int u = 0; u <= n_up; ++u) ub[u] = std::min(nq, u * gate.per);
+    // launch ranges: about 1/2, 5/16, 3/16 of the queries, in whole waves
+    const int wave = 2 * h->sms;
+    auto waves = [&](int frac16) { const int w = std::max(1, (int)((long long)nq * frac16 / 16 / wave)); return w * wave; };
+    if (!getenv("FOT_HOST_CHUNKS") && !getenv("FOT_CHUNK_WAVES")) {
+      const int cuts[] = {waves(8), waves(13), nq};
+      n_chunks = 3;
+      for (int c = 0; c < n_chunks; ++c) bounds[c + 1] = std::min(nq, std::max(cuts[c], bounds[c]));
+      for (int c = n_chunks + 1; c <= kMaxChunks; ++c) bounds[c] = nq;
+    }
+    two_streams = n_chunks > 1;
+  }
+  const auto t_wall0 = std::chrono::steady_clock::now();
   static const bool dbg = getenv("FOT_DEBUG_TIMING") != nullptr;
   cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr, d3 = nullptr, d4 = nullptr;
+  cudaEvent_t tl[kMaxChunks][4] = {};                    // debug timeline per chunk: upload done, kernels start / end, read-back done
+  if (dbg) for (auto& row : tl) for (auto& ev : row) cudaEventCreate(&ev);
   if (dbg) { cudaEventCreate(&d0); cudaEventCreate(&d1); cudaEventCreate(&d2); cudaEventCreate(&d3); cudaEventCreate(&d4);
              cudaEventRecord(d0, st); cudaEventRecord(d4, h->copy_stream); }
+  CK(cudaEventRecord(h->ev_blob, h->copy_stream));
   // every obstacle upload is queued first (they depend on nothing), one event per chunk
-  if (has_dyn)
+  if (gated) {
+    // each slice is followed, in its stream, by the write of its flag (two alternating upload streams are a
+    // tuning knob; measured slower than one)
+    uint32_t* words = (uint32_t*)h->gate_h.p;
+    int n_cs = 1;
+    if (const char* env = getenv("FOT_GATE_COPY_STREAMS")) n_cs = atoi(env) >= 2 ? 2 : 1;
+    CK(cudaStreamWaitEvent(h->copy_stream2, h->ev_blob, 0));      // nothing of this call before the previous call's flags are history
+    for (int u = 0; u < n_up; ++u) {
+      const int q0 = ub[u], cq = ub[u + 1] - q0;
+      if (cq <= 0) continue;
+      cudaStream_t cs = (n_cs == 2 && (u & 1)) ? h->copy_stream2 : h->copy_stream;
+      char* dst = (char*)h->dyn_d.p + (size_t)q0 * dyn_q_bytes;
+      const char* src = (const char*)b->dyn + (size_t)q0 * dyn_q_bytes;
+      CK(cudaMemcpyAsync(dst, src, (size_t)cq * dyn_q_bytes, cudaMemcpyHostToDevice, cs));
+      words[u] = gate.epoch;
+      if (StreamWrite32 wr = stream_write32()) {
+        if (wr(cs, (unsigned long long)(uintptr_t)(gate.word + u), gate.epoch, 0u) != 0)
+          return fail(FOT_ERR_CUDA, "cuStreamWriteValue32");
+      } else {
+        CK(cudaMemcpyAsync(gate.word + u, words + u, sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+      }
+    }
+  } else if (has_dyn)
     for (int c = 0; c < n_chunks; ++c) {
       const int q0 = bounds[c], cq = bounds[c + 1] - q0;
       if (cq <= 0) continue;
@@ -547,20 +703,27 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
       const char* src = (const char*)b->dyn + (size_t)q0 * dyn_q_bytes;
       CK(cudaMemcpyAsync(dst, src, (size_t)cq * dyn_q_bytes, cudaMemcpyHostToDevice, h->copy_stream));
       CK(cudaEventRecord(h->ev_copy[c], h->copy_stream));
+      if (dbg) cudaEventRecord(tl[c][0], h->copy_stream);
     }
-  else
-    CK(cudaEventRecord(h->ev_copy[0], h->copy_stream));   // small arrays / static obstacles only
   if (dbg) {
+    if (gated) { cudaEventRecord(h->ev_join, h->copy_stream2); cudaStreamWaitEvent(h->copy_stream, h->ev_join, 0); }
     cudaEventRecord(d1, h->copy_stream);
     cudaPointerAttributes pa{};
     cudaError_t pe = cudaPointerGetAttributes(&pa, b->dyn);
     fprintf(stderr, "[fot] dyn pointer attr: err=%d type=%d (0 unregistered, 1 host, 2 device, 3 managed)\n", (int)pe, (int)pa.type);
   }
+  int n_issued = 0;
   for (int c = 0; c < n_chunks; ++c) {
     const int q0 = bounds[c], cq = bounds[c + 1] - q0;
     if (cq <= 0) continue;
-    if (has_dyn || c == 0) CK(cudaStreamWaitEvent(st, h->ev_copy[c], 0));
+    // Gated ranges run on streams of descending priority: every range's kernels are eligible from the start, and a
+    // CTA of a later range that got an SM slot early would only sit there waiting for its slice of the upload.
+    cudaStream_t st = gated ? h->pstream[n_issued & 3] : (two_streams && (n_issued & 1)) ? h->stream2 : h->stream;
+    ++n_issued;
+    if (has_dyn && !gated) CK(cudaStreamWaitEvent(st, h->ev_copy[c], 0));
+    else CK(cudaStreamWaitEvent(st, h->ev_blob, 0));
     if (dbg && c == 0) cudaEventRecord(d2, st);
+    if (dbg) cudaEventRecord(tl[c][1], st);
     fot_batch_t db = *b;
     db.n_q = cq;
     db.frenet = (const double*)(sd + o_fr) + (size_t)q0 * 6;
@@ -580,11 +743,17 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     dr.winner = (double*)(od + r_w) + (size_t)q0 * FOT_N_SERIES * NT;
     dr.cand_cat = r->cand_cat ? (uint8_t*)(od + r_cc) + (size_t)q0 * r->cand_stride : nullptr;
     dr.cand_cost = r->cand_cost ? (double*)(od + r_cs) + (size_t)q0 * r->cand_stride : nullptr;
-    rc = launch_all(h, &db, &dr, st);
+    // (tuning knob: blocks per CTA of the last gated range; shorter CTAs there measured no better than the
+    // rule of item_geometry)
+    int tail_bpc = 0;
+    if (gated && bounds[c + 1] >= nq)
+      if (const char* env = getenv("FOT_GATE_TAIL_BPC")) tail_bpc = atoi(env);
+    rc = launch_all(h, &db, &dr, st, (size_t)q0, (size_t)nq, gate, tail_bpc);
     if (rc != FOT_OK) return rc;
     // winners of this chunk straight into the caller's arrays, on their own stream so the next
     // chunk's kernels never queue behind a copy engine that is busy with the uploads
     cudaStream_t ds = h->d2h_stream;
+    if (dbg) cudaEventRecord(tl[c][2], st);
     CK(cudaEventRecord(h->ev_done[c], st));
     CK(cudaStreamWaitEvent(ds, h->ev_done[c], 0));
     CK(cudaMemcpyAsync(r->best_idx + q0, dr.best_idx, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
@@ -599,14 +768,40 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     if (r->cand_cost)
       CK(cudaMemcpyAsync(r->cand_cost + (size_t)q0 * r->cand_stride, dr.cand_cost, (size_t)cq * r->cand_stride * 8,
                          cudaMemcpyDeviceToHost, ds));
+    if (dbg) cudaEventRecord(tl[c][3], ds);
   }
-  if (dbg) cudaEventRecord(d3, st);
+  if (dbg) {
+    cudaEventRecord(h->ev_join, h->stream2); cudaStreamWaitEvent(st, h->ev_join, 0);
+    for (auto ps : h->pstream) { cudaEventRecord(h->ev_join, ps); cudaStreamWaitEvent(st, h->ev_join, 0); }
+    cudaEventRecord(d3, st);
+  }
+  CK(cudaStreamSynchronize(h->d2h_stream));   // the last read-backs wait for the last kernels of every compute stream
   CK(cudaStreamSynchronize(st));
-  CK(cudaStreamSynchronize(h->d2h_stream));
+  CK(cudaStreamSynchronize(h->stream2));
+  if (gated) {
+    for (auto ps : h->pstream) CK(cudaStreamSynchronize(ps));
+    CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->copy_stream2));
+  }
+  if (gated && std::chrono::steady_clock::now() - t_wall0 > std::chrono::nanoseconds(kGateTimeoutNs)) {
+    unsigned gave_up = 0;
+    CK(cudaMemcpy(&gave_up, gate.word + kGateSlices, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (gave_up) {
+      cudaMemset(gate.word + kGateSlices, 0, sizeof(unsigned));
+      return fail(FOT_ERR_CUDA, "gated sweep: the obstacle upload did not arrive");
+    }
+  }
   if (dbg) {
     float a = 0, bb = 0, cc = 0, dd = 0;
     cudaEventElapsedTime(&a, d0, d1); cudaEventElapsedTime(&bb, d0, d2); cudaEventElapsedTime(&cc, d0, d3); cudaEventElapsedTime(&dd, d0, d4);
     fprintf(stderr, "[fot] chunks=%d copy-stream start %.3f ms, copies done %.3f ms, first kernel may start %.3f ms, kernels done %.3f ms\n", n_chunks, dd, a, bb, cc);
+    for (int c = 0; c < n_chunks; ++c) {
+      float t[4] = {-1, -1, -1, -1};
+      for (int k = 0; k < 4; ++k) if (k > 0 || (has_dyn && !gated)) cudaEventElapsedTime(&t[k], d0, tl[c][k]);
+      fprintf(stderr, "[fot]   chunk %2d queries %5d..%5d  upload done %.3f  kernels %.3f -> %.3f  read-back done %.3f\n", c,
+              bounds[c], bounds[c + 1], t[0], t[1], t[2], t[3]);
+    }
+    for (auto& row : tl) for (auto& ev : row) cudaEventDestroy(ev);
     cudaEventDestroy(d0); cudaEventDestroy(d1); cudaEventDestroy(d2); cudaEventDestroy(d3); cudaEventDestroy(d4);
   }
   return FOT_OK;

@@ -87,7 +87,20 @@ struct ItemGeom {
   // byte offsets into dynamic shared memory
   int32_t o_row, o_sdl, o_ct, o_dgrid, o_vlast, o_spl, o_dyn;
   int32_t o_fn, o_flags, o_hit, o_viol, o_queue, o_list, o_slow, o_clean;
+  // gated launch (host-pointer call): the sweep is launched before / while the obstacle tensor is uploaded in
+  // slices of gate_per queries; the upload streams set gate[slice] = gate_epoch behind each slice and a CTA waits
+  // for the slice of its own query.  With fused_box the trajectory boxes are computed by the CTA from its staged obstacle
+  // block (no prepass over a tensor that has not arrived yet).
+  int32_t fused_box;         // 1: boxes from the staged block into shared memory at o_box (needs stage_dyn)
+  int32_t o_box;
+  int32_t gate_q0;           // index of this launch's first query in the uploaded batch
+  int32_t gate_per;          // queries per upload slice
+  uint32_t gate_epoch;
+  unsigned* gate;            // [slice] flags, [kGateSlices] set to 1 by a CTA that gave up waiting; nullptr: no gate
 };
+
+constexpr int kGateSlices = 64;
+constexpr long long kGateTimeoutNs = 4000000000ll;   // a gated CTA gives up after 4 s (the host reports the error)
 
 // 1/x and 1/sqrt(x) to fp64 accuracy from the fp32 MUFU seed and two Newton steps (branch-free; the
 // library versions carry slow paths for denormals and cost three times as many instructions).  Used for
@@ -226,6 +239,8 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   __shared__ double s_cost[kItemThreads / 32];
   __shared__ int s_idx[kItemThreads / 32];
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_abort;
+  float4* sbox = reinterpret_cast<float4*>(smb + G.o_box);          // [SP] trajectory boxes when fused_box
 
   const int NT = P.n_t_max;
   const int q = blockIdx.x / G.ctas_per_query;
@@ -248,6 +263,28 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
 
   // ---- once per CTA: obstacle block in flight, grids and spline tables in shared memory ----------
+  if (G.gate) {
+    // this query's slice of the obstacle tensor has been uploaded once the progress word passes it
+    if (tid == 0) {
+      const unsigned* flag = G.gate + (G.gate_q0 + q) / G.gate_per;
+      int abort_ = 0;
+      long long t0 = 0;
+      for (unsigned spins = 0;; ++spins) {
+        unsigned seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (seen == G.gate_epoch) break;
+        __nanosleep(spins < 64 ? 100 : 1000);
+        long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > kGateTimeoutNs) { abort_ = 1; G.gate[kGateSlices] = 1u; break; }
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");      // the bulk copy below reads what the upload wrote
+      s_abort = abort_;
+    }
+    __syncthreads();
+    if (s_abort) return;
+  }
   if (tid == 0 && G.stage_dyn && state_ok) {
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -271,6 +308,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   }
   double my_cost = INFINITY;            // running arg-min over every block this CTA sweeps
   int my_idx = 0x7fffffff;
+  bool boxes_done = false;
 #ifdef FOT_PHASE_CLOCKS
   long long t_phase = clock64();
 #endif
@@ -442,6 +480,33 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   const double rc_s = sqrt(P.cfg.collide_r2) * (1.0 + 1e-9) + 1e-9 + max_off;
   const double rc_d = sqrt(r2_dyn) * (1.0 + 1e-9) + 1e-9 + max_off;
   const double wroad = fmax(P.cfg.max_road_width + 1e-9, fabs(fs[3]));
+  if (G.fused_box && !boxes_done) {
+    // first block of the CTA: box every predicted trajectory of the staged obstacle block (what fot_prepass
+    // does for a resident tensor): one warp per trajectory, fp32 rounded outward, NaN trajectory -> NaN box
+    mbar_wait(&s_bar, 0u);
+    for (int j = tid >> 5; j < SP; j += bd >> 5) {
+      const double2* src = dynst + (size_t)j * B.T_obs;
+      double xlo = INFINITY, xhi = -INFINITY, ylo = INFINITY, yhi = -INFINITY;
+      bool bad = false;
+      for (int k = lane; k < B.T_obs; k += 32) {
+        const double2 o = src[k];
+        bad |= (o.x != o.x) || (o.y != o.y);
+        xlo = fmin(xlo, o.x); xhi = fmax(xhi, o.x); ylo = fmin(ylo, o.y); yhi = fmax(yhi, o.y);
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        xlo = fmin(xlo, __shfl_xor_sync(0xffffffffu, xlo, off)); xhi = fmax(xhi, __shfl_xor_sync(0xffffffffu, xhi, off));
+        ylo = fmin(ylo, __shfl_xor_sync(0xffffffffu, ylo, off)); yhi = fmax(yhi, __shfl_xor_sync(0xffffffffu, yhi, off));
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      if (lane == 0) {
+        const float nanf_ = __int_as_float(0x7fc00000);
+        sbox[j] = bad ? make_float4(nanf_, nanf_, nanf_, nanf_)
+                      : make_float4(__double2float_rd(xlo), __double2float_ru(xhi), __double2float_rd(ylo), __double2float_ru(yhi));
+      }
+    }
+    boxes_done = true;
+    __syncthreads();
+  }
   if (has_dyn || M > 0) {
     // keep the obstacles whose (trajectory) box meets the box of the reference points padded by the
     // widest reach of a clean candidate; a NaN box (fp.py:1211-1222) fails every comparison
@@ -456,7 +521,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
           olist[slot] = (unsigned)j;
         }
       }
-      const float4* boxes = B.dyn_box + (size_t)q * SP;
+      const float4* boxes = G.fused_box ? sbox : B.dyn_box + (size_t)q * SP;
       for (int j = tid; j < SP; j += bd) {
         const float4 ob = boxes[j];                       // xmin xmax ymin ymax
         if (ob.x <= bx1 && ob.y >= bx0 && ob.z <= by1 && ob.w >= by0) {

@@ -140,3 +140,34 @@ def test_host_chunking_and_cta_grouping_do_not_change_results():
         else:
             assert np.array_equal(v, w), k
     assert np.array_equal(a["best_idx"][:250], a["best_idx"][250:500])
+
+
+def test_gated_upload_pipeline_matches_the_single_launch():
+    """The host-pointer call launches the sweep while the obstacle tensor is still being uploaded: CTAs wait for
+    the slice of their query and box the predicted trajectories themselves.  Every variant of that pipeline
+    (gated, chunked on two streams, chunked on one, odd slice counts, flags by copy instead of stream write)
+    has to return what one plain launch over the resident tensor returns -- including queries with a NaN
+    trajectory, whose box is NaN (fp.py:1211-1222), and a shared static wall."""
+    import bench
+    _, frenet, dyn = bench.make_queries(7000, 200)
+    frenet, dyn = np.tile(frenet, (6, 1)), np.tile(dyn, (6, 1, 1, 1, 1)).copy()
+    dyn[3::17, 0, 5, 20:, :] = np.nan                      # a pedestrian whose prediction breaks off
+    dyn[8::29, 0, 2, 0, 1] = np.nan
+    wall = np.stack([np.full(12, 30.0), np.linspace(-3.0, 3.0, 12)], axis=1)
+    pl = _planner()
+    keys = ("best_idx", "best_cost", "stats", "cand_cat", "winner", "winner_len")
+    run = lambda: pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn[:, 0], static_obstacles=wall, want_candidates=True)
+    with _env(FOT_HOST_CHUNKS=1):
+        ref = run()
+        ref = {k: getattr(ref, k).copy() for k in keys}
+    assert len(set(ref["best_idx"].tolist())) > 20
+    variants = [dict(), dict(FOT_GATED=0), dict(FOT_GATED=0, FOT_HOST_STREAMS=1), dict(FOT_GATE_UPLOADS=7),
+                dict(FOT_GATE_UPLOADS=64, FOT_GATE_COPY_STREAMS=2), dict(FOT_GATE_MEMCPY=1, FOT_CHUNK_WAVES="1,1"),
+                dict(FOT_GATE_TAIL_BPC=1), dict(FOT_GATED=0, FOT_HOST_CHUNKS=1, FOT_FUSED_BOX=1)]
+    for env in variants:
+        with _env(**env):
+            got = run()
+        for k, v in ref.items():
+            w = getattr(got, k)
+            same = np.array_equal(v.view(np.uint64), w.view(np.uint64)) if v.dtype == np.float64 else np.array_equal(v, w)
+            assert same, (env, k)
