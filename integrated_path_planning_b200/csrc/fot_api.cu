@@ -167,7 +167,8 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   CK(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device));
   h->smem_optin -= 2048;   // leave room for the kernels' static shared memory
   CK(cudaFuncSetAttribute(fot_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-  CK(cudaFuncSetAttribute(fot_sweep_items, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   *out = h;
   return FOT_OK;
 }
@@ -505,7 +506,8 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
                                                                (const double2*)b->dyn, dyn_box, n_traj, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
-  if (use_items) fot_sweep_items<<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
+  if (use_items && ig.fused_box) fot_sweep_items<true><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
+  else if (use_items) fot_sweep_items<false><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
   else fot_sweep<<<(unsigned)n_part, kSweepThreads, smem, st>>>(h->plan, B, O, g);
   h->last_sweep_kind = use_items ? 1 : 2;
   CK(cudaEventRecord(ring[2], st));

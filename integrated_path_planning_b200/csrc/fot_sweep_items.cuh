@@ -212,6 +212,10 @@ __device__ __forceinline__ unsigned clean_word(const unsigned* flags_pp, int nw4
   return rem >= 32 ? m : (m & ((1u << rem) - 1u));
 }
 
+// kFused: the variant of the gated host-pointer call (waits for its query's upload slice, boxes the trajectories
+// itself).  A template parameter rather than a run-time branch: the resident path keeps exactly the code (and the
+// register allocation) it is tuned for.
+template <bool kFused>
 __global__ void __launch_bounds__(kItemThreads, FOT_ITEM_MIN_CTAS)
 fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   extern __shared__ __align__(16) unsigned char smb[];
@@ -263,7 +267,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
 
   // ---- once per CTA: obstacle block in flight, grids and spline tables in shared memory ----------
-  if (G.gate) {
+  if (kFused && G.gate) {
     // this query's slice of the obstacle tensor has been uploaded once the progress word passes it
     if (tid == 0) {
       const unsigned* flag = G.gate + (G.gate_q0 + q) / G.gate_per;
@@ -480,7 +484,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   const double rc_s = sqrt(P.cfg.collide_r2) * (1.0 + 1e-9) + 1e-9 + max_off;
   const double rc_d = sqrt(r2_dyn) * (1.0 + 1e-9) + 1e-9 + max_off;
   const double wroad = fmax(P.cfg.max_road_width + 1e-9, fabs(fs[3]));
-  if (G.fused_box && !boxes_done) {
+  if (kFused && !boxes_done) {
     // first block of the CTA: box every predicted trajectory of the staged obstacle block (what fot_prepass
     // does for a resident tensor): one warp per trajectory, fp32 rounded outward, NaN trajectory -> NaN box
     mbar_wait(&s_bar, 0u);
@@ -521,7 +525,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
           olist[slot] = (unsigned)j;
         }
       }
-      const float4* boxes = G.fused_box ? sbox : B.dyn_box + (size_t)q * SP;
+      const float4* boxes = kFused ? sbox : B.dyn_box + (size_t)q * SP;
       for (int j = tid; j < SP; j += bd) {
         const float4 ob = boxes[j];                       // xmin xmax ymin ymax
         if (ob.x <= bx1 && ob.y >= bx0 && ob.z <= by1 && ob.w >= by0) {
