@@ -99,6 +99,9 @@ struct ItemGeom {
   unsigned* gate;            // [slice] flags, [kGateSlices] set to 1 by a CTA that gave up waiting; nullptr: no gate
 };
 
+#ifndef FOT_GATE_SLEEP_NS
+#define FOT_GATE_SLEEP_NS 1000
+#endif
 constexpr int kGateSlices = 64;
 constexpr long long kGateTimeoutNs = 4000000000ll;   // a gated CTA gives up after 4 s (the host reports the error)
 
@@ -275,9 +278,14 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       long long t0 = 0;
       for (unsigned spins = 0;; ++spins) {
         unsigned seen;
+#ifdef FOT_GATE_POLL_RELAXED
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (seen == G.gate_epoch) { asm volatile("fence.acq_rel.sys;" ::: "memory"); break; }
+#else
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
         if (seen == G.gate_epoch) break;
-        __nanosleep(spins < 64 ? 100 : 1000);
+#endif
+        __nanosleep(spins < 64 ? 100 : FOT_GATE_SLEEP_NS);
         long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (t0 == 0) t0 = now;

@@ -53,6 +53,10 @@ def speed_grid_batch(target_speed: np.ndarray, d_t_s: float):
     """Vectorised speed_grid: returns (v_grid [n_q, n_v_max], n_v [n_q]); same elementwise
     arithmetic as the scalar version."""
     target = np.asarray(target_speed, dtype=np.float64).reshape(-1)
+    if target.size > 1 and target.min() == target.max():
+        # one target speed for the whole batch (the usual case): one row, repeated -- same arithmetic per element
+        grid, n_v = speed_grid_batch(target[:1], d_t_s)
+        return np.repeat(grid, target.size, axis=0), np.repeat(n_v, target.size)
     n_down = np.trunc(target / d_t_s + 1e-9).astype(np.int64)
     if np.any(n_down < 0):
         raise ValueError("target_speed too negative for the speed grid")
