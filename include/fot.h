@@ -143,9 +143,13 @@ int fot_candidate_count(const fot_handle_t* h, int n_v, int has_brake);
  * which is then synchronised before returning). */
 int fot_plan_batch_device(fot_handle_t* h, const fot_batch_t* batch, const fot_result_t* res, void* stream);
 
-/* Same call with HOST pointers everywhere: stages inputs through the handle's pinned buffers,
- * runs the kernels, copies the results back, and returns when they are in `res`. This is the
- * entry point FrenetPlanner.plan() binds. */
+/* Same call with HOST pointers everywhere: stages the small per-query arrays through the handle's
+ * pinned buffers, uploads the obstacle tensor straight from the caller's memory, runs the kernels,
+ * copies the results back, and returns when they are in `res`. This is the entry point
+ * FrenetPlanner.plan() binds.  Large batches are pipelined: the tensor goes up in slices while the
+ * sweep is already running (every CTA waits for the slice of its own query), and the winners of the
+ * first queries come back while the last are still swept.  Page-locked (pinned) `batch->dyn` and
+ * result arrays make those copies true asynchronous DMAs; pageable memory works but serialises. */
 int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* batch, const fot_result_t* res);
 
 /* Device-side time of the kernels of the last fot_plan_batch_* call on this handle, in ms

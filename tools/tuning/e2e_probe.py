@@ -11,7 +11,7 @@ nq = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 spline, frenet, dyn = bench.make_queries(0, nq)
 planner = BatchFrenetPlanner(spline, device=0, **scenarios.S1_KNOBS)
-dyn_host = torch.from_numpy(dyn).pin_memory().numpy()
+dyn_host = dyn if os.environ.get("PROBE_PAGEABLE") else torch.from_numpy(dyn).pin_memory().numpy()   # PROBE_PAGEABLE=1: an ordinary NumPy array
 variants = [v for v in os.environ.get("PROBE_VARIANTS", "").split(";") if v] or [""]
 ref = None
 for v in variants:
