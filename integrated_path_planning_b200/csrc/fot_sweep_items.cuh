@@ -582,10 +582,35 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
 
   const double sd4 = sd2 * sd2;
   unsigned anyslow = 0u;
+  // Three of the tests can be settled per ITEM for every lateral target at once, because the quantities are
+  // affine / convex in d_i: the lateral offset d(d_i) is affine and fma is monotone, so max |d| sits at an end of
+  // the grid (exact); the step vector is affine, so |step| <= |E0| + max|d_i| |E1| (teleport, checked with a
+  // margin); v^2 = s_dot^2 (q^2 + d'^2) is convex, so its maximum is at an end (checked with a margin for the
+  // rounding of the interior points).  When that holds for all items of a warp the loop below runs without
+  // those tests; otherwise the warp runs the full chain.  Two more guards go the same way: q(d_i) = 1 - kappa_r d
+  // is affine, so the singularity test q <= 0.05 is decided by the smaller end (exact), and when every coefficient
+  // is finite and below 1e40 no intermediate of the chain can overflow, so the non-finite test cannot fire.
+  // Together 13 of the 46 FP64-pipe instructions per candidate.
+  bool lite;
+  {
+    const double ga = brake_blk ? 0.0 : P.d_min, gb = brake_blk ? 0.0 : P.d_max, gabs = fmax(fabs(ga), fabs(gb));
+    const double bx = fabs(E0x) + gabs * fabs(E1x), by = fabs(E0y) + gabs * fabs(E1y);
+    const bool ok_tele = fma(bx, bx, by * by) <= 0.99 * tele2;
+    const bool ok_road = fabs(fma(ga, B0, A0)) <= road_thr && fabs(fma(gb, B0, A0)) <= road_thr;
+    const double qa = fma(ga, Q1, Q0), pa = fma(ga, P1, P0), qb = fma(gb, Q1, Q0), pb = fma(gb, P1, P0);
+    const double vcap = vmax2 * (1.0 - 1e-12);
+    const bool ok_speed = sd2 * fma(qa, qa, pa * pa) <= vcap && sd2 * fma(qb, qb, pb * pb) <= vcap;
+    const bool ok_sing = fmin(qa, qb) > 0.05;
+    const double mag = fabs(Q0) + fabs(P0) + fabs(R0) + fabs(M0) + fabs(S0) + sd2 + fabs(i_rk) +
+                       gabs * (fabs(Q1) + fabs(P1) + fabs(R1) + fabs(M1) + fabs(S1));
+    const bool ok_fin = mag <= 1e40;
+    lite = __all_sync(0xffffffffu, !valid || (ok_tele && ok_road && ok_speed && ok_sing && ok_fin));   // NaN anywhere: full chain
+  }
   // one candidate sample, straight-line: flags of candidate i0 + U into byte U of acc
-  auto sample = [&](double di, unsigned& acc, unsigned sh) {
-    const double d = fma(di, B0, A0), qq = fma(di, Q1, Q0), dpr = fma(di, P1, P0), dpp = fma(di, R1, R0);
-    const double m = fma(di, M1, M0), sq = fma(di, S1, S0), ex = fma(di, E1x, E0x), ey = fma(di, E1y, E0y);
+  auto sample = [&](auto lite_tag, double di, unsigned& acc, unsigned sh) {
+    constexpr bool kLite = decltype(lite_tag)::value;
+    const double qq = fma(di, Q1, Q0), dpr = fma(di, P1, P0), dpp = fma(di, R1, R0);
+    const double m = fma(di, M1, M0), sq = fma(di, S1, S0);
     const double h2 = fma(qq, qq, dpr * dpr);                                  // hypot(q, d')^2 = (q / cos delta)^2
     const double w = fma(i_rk, h2, fma(dpp, qq, m * dpr));                     // kappa h^3   (cc.py:144-147)
     const double h6 = h2 * h2 * h2;
@@ -593,42 +618,58 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     const double v2 = sd2 * h2;                                                // v^2         (cc.py:150-152)
     const double T = fma(dpr, fma(-i_rk, h2, w), -(m * h2));
     const double Z = fma(sd2, T, sq * h2);                                     // a h q       (cc.py:155-157)
-    const double step2 = fma(ex, ex, ey * ey);                                 // fp.py:954 (squared)
-    const double fin = fabs(Z) + fabs(w) + h6;
     const double acc_rhs = amax2 * (qq * qq * h2), curv_rhs = kmax2 * h6, lat_lhs = sd4 * w2, lat_rhs = latmax2 * h2;
     const double Z2 = Z * Z;
-    asm("{\n .reg .pred p, f;\n .reg .f64 t;\n"
-        " abs.f64 t, %2;\n setp.lt.f64 p, t, 0d7FF0000000000000;\n setp.le.and.f64 p, %2, 0d3FA999999999999A, p;\n"   // q <= 0.05 and finite (fp.py:826-833)
-        " setp.geu.or.f64 p, %3, 0d7FF0000000000000, p;\n"                      // non-finite v / a / kappa (fp.py:944-946)
-        " setp.gt.or.f64 p, %4, %5, p;\n"                                       // teleport (fp.py:953-956)
-        " @p or.b32 %0, %0, %6;\n"
-        " setp.gt.f64 f, %7, %8;\n"                                             // v > 0.5 (fp.py:1019)
-        " @!f or.b32 %1, %1, 1;\n"
-        " setp.gt.and.f64 p, %9, %10, f;\n"                                     // |kappa| > k_max when fast (fp.py:1020)
-        " @p or.b32 %0, %0, %11;\n"
-        "}"
-        : "+r"(acc), "+r"(anyslow)
-        : "d"(qq), "d"(fin), "d"(step2), "d"(tele2), "r"(F_DROP << sh), "d"(v2), "d"(fast2), "d"(w2), "d"(curv_rhs), "r"(F_CURV << sh));
-    flag_gt(acc, v2, vmax2, F_SPEED << sh);                                    // fp.py:964
+    if constexpr (kLite) {
+      asm("{\n .reg .pred p, f;\n"
+          " setp.gt.f64 f, %2, %3;\n"                                             // v > 0.5 (fp.py:1019)
+          " @!f or.b32 %1, %1, 1;\n"
+          " setp.gt.and.f64 p, %4, %5, f;\n"                                      // |kappa| > k_max when fast (fp.py:1020)
+          " @p or.b32 %0, %0, %6;\n"
+          "}"
+          : "+r"(acc), "+r"(anyslow)
+          : "d"(v2), "d"(fast2), "d"(w2), "d"(curv_rhs), "r"(F_CURV << sh));
+    } else {
+      const double ex = fma(di, E1x, E0x), ey = fma(di, E1y, E0y);
+      const double step2 = fma(ex, ex, ey * ey);                               // fp.py:954 (squared)
+      const double fin = fabs(Z) + fabs(w) + h6;
+      asm("{\n .reg .pred p, f;\n .reg .f64 t;\n"
+          " abs.f64 t, %2;\n setp.lt.f64 p, t, 0d7FF0000000000000;\n setp.le.and.f64 p, %2, 0d3FA999999999999A, p;\n"   // q <= 0.05 and finite (fp.py:826-833)
+          " setp.geu.or.f64 p, %3, 0d7FF0000000000000, p;\n"                      // non-finite v / a / kappa (fp.py:944-946)
+          " setp.gt.or.f64 p, %4, %5, p;\n"                                       // teleport (fp.py:953-956)
+          " @p or.b32 %0, %0, %6;\n"
+          " setp.gt.f64 f, %7, %8;\n"                                             // v > 0.5 (fp.py:1019)
+          " @!f or.b32 %1, %1, 1;\n"
+          " setp.gt.and.f64 p, %9, %10, f;\n"                                     // |kappa| > k_max when fast (fp.py:1020)
+          " @p or.b32 %0, %0, %11;\n"
+          "}"
+          : "+r"(acc), "+r"(anyslow)
+          : "d"(qq), "d"(fin), "d"(step2), "d"(tele2), "r"(F_DROP << sh), "d"(v2), "d"(fast2), "d"(w2), "d"(curv_rhs), "r"(F_CURV << sh));
+      flag_gt(acc, v2, vmax2, F_SPEED << sh);                                  // fp.py:964
+      flag_abs_gt(acc, fma(di, B0, A0), road_thr, F_ROAD << sh);               // fp.py:982
+    }
     flag_gt(acc, Z2, acc_rhs, F_ACCEL << sh);                                  // fp.py:966
     flag_gt(acc, lat_lhs, lat_rhs, F_LAT << sh);                               // fp.py:975  v^2 |kappa| > a_lat
-    flag_abs_gt(acc, d, road_thr, F_ROAD << sh);                               // fp.py:982
   };
-  for (int i0 = 0; i0 < n_dl; i0 += 4) {
-    unsigned acc = 0u;
-    if (valid) {
-      if (brake_blk) {
-        sample(0.0, acc, 0u);
-      } else if (i0 + 4 <= n_dl) {
-        const double g0 = dgrid[i0], g1 = dgrid[i0 + 1], g2 = dgrid[i0 + 2], g3 = dgrid[i0 + 3];
-        sample(g0, acc, 0u); sample(g1, acc, 8u); sample(g2, acc, 16u); sample(g3, acc, 24u);
-      } else {
-        for (int u = 0; i0 + u < n_dl; ++u) sample(dgrid[i0 + u], acc, 8u * u);
+  auto sweep_targets = [&](auto lite_tag) {
+    for (int i0 = 0; i0 < n_dl; i0 += 4) {
+      unsigned acc = 0u;
+      if (valid) {
+        if (brake_blk) {
+          sample(lite_tag, 0.0, acc, 0u);
+        } else if (i0 + 4 <= n_dl) {
+          const double g0 = dgrid[i0], g1 = dgrid[i0 + 1], g2 = dgrid[i0 + 2], g3 = dgrid[i0 + 3];
+          sample(lite_tag, g0, acc, 0u); sample(lite_tag, g1, acc, 8u); sample(lite_tag, g2, acc, 16u); sample(lite_tag, g3, acc, 24u);
+        } else {
+          for (int u = 0; i0 + u < n_dl; ++u) sample(lite_tag, dgrid[i0 + u], acc, 8u * u);
+        }
       }
+      const unsigned red = __reduce_or_sync(segmask, acc & keep4);
+      if (seg_leader && active && red) atomicOr(&flags_p[i0 >> 2], red);
     }
-    const unsigned red = __reduce_or_sync(segmask, acc & keep4);
-    if (seg_leader && active && red) atomicOr(&flags_p[i0 >> 2], red);
-  }
+  };
+  if (lite) sweep_targets(std::true_type{});
+  else sweep_targets(std::false_type{});
   // Low-speed regime (fp.py:1022-1032): items that saw a candidate with v <= 0.5 queue up; the block
   // redoes the two low-speed tests for them in phase D, one (item, candidate) unit per thread.
   if (anyslow && chk) slowq[atomicAdd(&s_nslow, 1)] = (unsigned short)tid;
