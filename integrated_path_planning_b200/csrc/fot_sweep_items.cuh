@@ -591,7 +591,7 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
   // is affine, so the singularity test q <= 0.05 is decided by the smaller end (exact), and when every coefficient
   // is finite and below 1e40 no intermediate of the chain can overflow, so the non-finite test cannot fire.
   // Together 13 of the 46 FP64-pipe instructions per candidate.
-  bool lite;
+  bool lite, skip;
   {
     const double ga = brake_blk ? 0.0 : P.d_min, gb = brake_blk ? 0.0 : P.d_max, gabs = fmax(fabs(ga), fabs(gb));
     const double bx = fabs(E0x) + gabs * fabs(E1x), by = fabs(E0y) + gabs * fabs(E1y);
@@ -604,7 +604,24 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     const double mag = fabs(Q0) + fabs(P0) + fabs(R0) + fabs(M0) + fabs(S0) + sd2 + fabs(i_rk) +
                        gabs * (fabs(Q1) + fabs(P1) + fabs(R1) + fabs(M1) + fabs(S1));
     const bool ok_fin = mag <= 1e40;
-    lite = __all_sync(0xffffffffu, !valid || (ok_tele && ok_road && ok_speed && ok_sing && ok_fin));   // NaN anywhere: full chain
+    const bool lite_ok = ok_tele && ok_road && ok_speed && ok_sing && ok_fin;
+    lite = __all_sync(0xffffffffu, !valid || lite_ok);                         // NaN anywhere: full chain
+    // Interval screen of what is left (acceleration, curvature, lateral acceleration, the low-speed regime): with
+    // q in [qmin, qmax] (positive here), |d'| <= Pm, |d''| <= Rm, ... every test is implied for ALL lateral targets
+    // by one comparison of bounds.  Loose near the limits, but most items are far inside them: a warp whose items
+    // all pass leaves every flag clear without looking at a single candidate.
+    const double qmin = fmin(qa, qb), qmax = fmax(qa, qb), Pm = fmax(fabs(pa), fabs(pb));
+    const double Rm = fmax(fabs(fma(ga, R1, R0)), fabs(fma(gb, R1, R0)));
+    const double Mm = fmax(fabs(fma(ga, M1, M0)), fabs(fma(gb, M1, M0)));
+    const double Sm = fmax(fabs(fma(ga, S1, S0)), fabs(fma(gb, S1, S0)));
+    const double h2lo = qmin * qmin, h2hi = fma(qmax, qmax, Pm * Pm), ark = fabs(i_rk);
+    const double Wm = fma(ark, h2hi, fma(Rm, qmax, Mm * Pm));                  // |kappa h^3|
+    const double Tm = fma(Pm, fma(ark, h2hi, Wm), Mm * h2hi);
+    const double Zm = fma(sd2, Tm, Sm * h2hi);                                 // |a h q|
+    const double slack = 1.0 + 1e-9, Wm2 = Wm * Wm * slack;
+    const bool ok_rest = Wm2 <= kmax2 * (h2lo * h2lo * h2lo) && sd4 * Wm2 <= latmax2 * h2lo &&
+                         Zm * Zm * slack <= amax2 * (h2lo * h2lo) && sd2 * h2lo > 0.25 * slack;
+    skip = __all_sync(0xffffffffu, !valid || (lite_ok && (!chk || ok_rest)));
   }
   // one candidate sample, straight-line: flags of candidate i0 + U into byte U of acc
   auto sample = [&](auto lite_tag, double di, unsigned& acc, unsigned sh) {
@@ -668,7 +685,8 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
       if (seg_leader && active && red) atomicOr(&flags_p[i0 >> 2], red);
     }
   };
-  if (lite) sweep_targets(std::true_type{});
+  if (skip) { }
+  else if (lite) sweep_targets(std::true_type{});
   else sweep_targets(std::false_type{});
   // Low-speed regime (fp.py:1022-1032): items that saw a candidate with v <= 0.5 queue up; the block
   // redoes the two low-speed tests for them in phase D, one (item, candidate) unit per thread.
