@@ -622,6 +622,18 @@ fot_sweep_items(const Plan P, const Batch B, const Out O, const ItemGeom G) {
     const bool ok_rest = Wm2 <= kmax2 * (h2lo * h2lo * h2lo) && sd4 * Wm2 <= latmax2 * h2lo &&
                          Zm * Zm * slack <= amax2 * (h2lo * h2lo) && sd2 * h2lo > 0.25 * slack;
     skip = __all_sync(0xffffffffu, !valid || (lite_ok && (!chk || ok_rest)));
+#ifdef FOT_PHASE_CLOCKS
+    {   // screen statistics: valid items, items that need the loop, warps with valid items (high word: full chain), skipped warps
+      const unsigned bv = __ballot_sync(0xffffffffu, valid), bd_ = __ballot_sync(0xffffffffu, valid && !(lite_ok && (!chk || ok_rest)));
+      const unsigned bl = __ballot_sync(0xffffffffu, valid && !lite_ok);
+      if (lane == 0 && bv) {
+        atomicAdd(&g_phase_clk[12], (unsigned long long)__popc(bv));
+        atomicAdd(&g_phase_clk[13], (unsigned long long)__popc(bd_));
+        atomicAdd(&g_phase_clk[14], 1ull | ((unsigned long long)(bl != 0) << 32));
+        atomicAdd(&g_phase_clk[15], (unsigned long long)(bd_ == 0));
+      }
+    }
+#endif
   }
   // one candidate sample, straight-line: flags of candidate i0 + U into byte U of acc
   auto sample = [&](auto lite_tag, double di, unsigned& acc, unsigned sh) {

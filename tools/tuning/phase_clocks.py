@@ -31,3 +31,7 @@ tot = sum(v[:12])
 for n, x in zip(names, v[:12]):
     print(f"{n:32s} {x / tot * 100:6.2f} %   {x / (nq * 12 * 10):9.0f} cycles per warp per block")
 print("total cycles per warp per block", tot / (nq * 12 * 10))
+
+print(f"validity screen: valid items {v[12]:.3e}, dirty items {v[13]:.3e} ({v[13] / max(v[12], 1) * 100:.1f} %), warps with valid items "
+      f"{v[14] & 0xffffffff:.3e}, of them skipped {v[15]:.3e} ({v[15] / max(v[14] & 0xffffffff, 1) * 100:.1f} %), full-chain warps "
+      f"{v[14] >> 32:.3e} ({(v[14] >> 32) / max(v[14] & 0xffffffff, 1) * 100:.1f} %)")
