@@ -39,7 +39,7 @@ UNIT = "evals/s"
 FLOP_PER_EVAL = 5.0      # 2 SUB + 1 MUL + 1 FMA
 N_PEDS, T_OBS = 50, 51
 TARGET_SPEED = 6.0
-NCU_DRAM_READ, NCU_DRAM_WRITE = 187.842304e6, 6.291456e6   # bytes per 4096-query launch (ncu --set full)
+NCU_DRAM_READ, NCU_DRAM_WRITE = 187.824896e6, 4.817152e6   # bytes per 4096-query launch (ncu --set full)
 
 
 # ------------------------------------------------------------------------------------------
