@@ -171,3 +171,28 @@ def test_gated_upload_pipeline_matches_the_single_launch():
             w = getattr(got, k)
             same = np.array_equal(v.view(np.uint64), w.view(np.uint64)) if v.dtype == np.float64 else np.array_equal(v, w)
             assert same, (env, k)
+
+
+def test_validity_screens_agree_with_the_oracle_near_the_limits():
+    """Phase C settles several tests once per item for the whole grid of lateral targets (ends of the grid for the
+    affine / convex ones, interval bounds for the rest) and skips the candidate loop for warps of clean items.
+    Limits drawn right through the range the candidates actually take -- speeds, accelerations, curvatures,
+    lateral accelerations and road widths that cut the grid -- put many items on the boundary of every screen; the
+    categories of all candidates must still be the reference's, on a straight and on a curved path."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for k in range(14):
+        over = dict(max_speed=float(rng.uniform(2.0, 9.0)), max_accel=float(rng.uniform(0.3, 3.0)),
+                    max_curvature=float(rng.uniform(0.01, 0.3)), max_lat_accel=float(rng.uniform(0.05, 2.0)))
+        fs = np.array([rng.uniform(3, 25), rng.uniform(0.0, 9.0), rng.uniform(-1.5, 1.5), rng.uniform(-2.9, 2.9),
+                       rng.uniform(-1.0, 1.0), rng.uniform(-0.5, 0.5)])
+        cases.append((over, fs, float(rng.uniform(0.5, 9.0))))
+    for wp in (scenarios.STRAIGHT_60, scenarios.s_curve_waypoints(), scenarios.arc_waypoints()):
+        for road in (2.7, 1.1):
+            knobs = dict(scenarios.S1_KNOBS, max_road_width=road)
+            pl, orc = _planner(knobs, wp), _oracle(knobs, wp)
+            for over, fs, target in cases:
+                dyn = scenarios.pedestrian_field(rng, 6)
+                res = pl.plan_batch(fs[None], target, dynamic_obstacles=dyn[None], limits=pl.resolve_limits(over),
+                                    want_candidates=True)
+                _check(res, [orc.plan_frenet(tuple(fs), np.empty((0, 2)), dyn, target, over)])
