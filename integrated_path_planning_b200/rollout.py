@@ -17,8 +17,8 @@ pedestrian source and the constant-velocity predictor (src/simulation/integrated
 src/pedestrian/observer.py:52-86; src/simulation/replay_source.py:31-111), so that a batch reproduces the
 reference's trajectories (tests/test_gpu_rollout.py, golden roll-outs recorded from the unmodified
 reference by tests/golden/make_golden_rollout.py).  Pedestrian ground truth stays outside (replay), as in
-the reference's own pysocialforce-free source; static obstacles and the multi-circle footprint are not
-wired into this driver yet.
+the reference's own pysocialforce-free source; static obstacles are shared by the simulations of a batch; the
+multi-circle footprint is not wired into this driver yet.
 """
 from __future__ import annotations
 
@@ -45,6 +45,33 @@ def _knob(knobs, key, default):
     return v
 
 
+def expand_static_obstacles(static_obstacles, step: float = 0.5) -> np.ndarray:
+    """Boundary points of rectangular obstacles for the planner's point-obstacle test
+    (integrated_simulator.py:804-836: edges sampled every `step`, duplicates removed, rows sorted by np.unique).
+    An [M, 2] array is taken as points already."""
+    if static_obstacles is None or len(static_obstacles) == 0:
+        return np.empty((0, 2))
+    arr = np.asarray(static_obstacles, dtype=np.float64)
+    if arr.ndim == 2 and arr.shape[1] == 2:
+        return np.ascontiguousarray(arr)
+    pts = []
+    for rect in static_obstacles:
+        if len(rect) != 4:
+            continue
+        x_min, x_max, y_min, y_max = rect
+        xs = np.arange(x_min, x_max + step, step)
+        ys = np.arange(y_min, y_max + step, step)
+        for x in xs:
+            pts.append((x, y_min))
+            pts.append((x, y_max))
+        for y in ys:
+            pts.append((x_min, y))
+            pts.append((x_max, y))
+    if not pts:
+        return np.empty((0, 2))
+    return np.unique(np.array(pts), axis=0)
+
+
 class _StateMachines:
     """FailSafeStateMachine for N simulations at once (src/core/state_machine.py:29-278)."""
 
@@ -65,67 +92,69 @@ class _StateMachines:
         self.last_clearance_ahead = np.full(n, np.inf)
 
     def update(self, idx, found, clearance, clearance_ahead, ego_speed):
-        """state_machine.py:116-179 for the simulations `idx`."""
-        self.last_clearance[idx] = clearance
+        """state_machine.py:116-179 for the simulations `idx` (array form of the per-state branches)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        ok = np.asarray(found, dtype=bool)
+        cl = np.asarray(clearance, dtype=np.float64)
+        self.last_clearance[idx] = cl
         self.last_clearance_ahead[idx] = clearance_ahead
-        for j, i in enumerate(idx):
-            trig = self.trigger_clearance + self.trigger_headway * max(float(ego_speed[j]), 0.0)
-            st, ok, cl = self.state[i], bool(found[j]), float(clearance[j])
-            if st == NORMAL:
-                if not ok:
-                    self.state[i] = CAUTION
-                    self.failures[i] += 1
-                elif trig > 0.0 and cl < trig:
-                    self.state[i] = CAUTION
-                    self.failures[i] = 0
-                else:
-                    self.failures[i] = 0
-            elif st == CAUTION:
-                if ok and self.failures[i] == 0:
-                    if cl > max(self.clearance_caution, trig):
-                        self.state[i] = NORMAL
-                elif not ok:
-                    self.state[i] = EMERGENCY
-                    self.failures[i] += 1
-                else:
-                    self.failures[i] = 0
-            else:
-                if ok and cl > self.clearance_emergency:
-                    self.state[i] = CAUTION
+        trig = self.trigger_clearance + self.trigger_headway * np.maximum(np.asarray(ego_speed, dtype=np.float64), 0.0)
+        st, fails = self.state[idx], self.failures[idx]
+        new_st, new_f = st.copy(), fails.copy()
+        normal, caution, emergency = st == NORMAL, st == CAUTION, st == EMERGENCY
+        # NORMAL: failure -> CAUTION (+1); preventive trigger -> CAUTION (counter 0); else counter 0
+        m = normal & ~ok
+        new_st[m], new_f[m] = CAUTION, fails[m] + 1
+        m = normal & ok & (trig > 0.0) & (cl < trig)
+        new_st[m], new_f[m] = CAUTION, 0
+        m = normal & ok & ~((trig > 0.0) & (cl < trig))
+        new_f[m] = 0
+        # CAUTION: clean success -> NORMAL when the clearance gate is open; failure -> EMERGENCY (+1); else counter 0
+        m = caution & ok & (fails == 0) & (cl > np.maximum(self.clearance_caution, trig))
+        new_st[m] = NORMAL
+        m = caution & ~ok
+        new_st[m], new_f[m] = EMERGENCY, fails[m] + 1
+        m = caution & ok & (fails != 0)
+        new_f[m] = 0
+        # EMERGENCY: success with a wide clearance -> CAUTION
+        m = emergency & ok & (cl > self.clearance_emergency)
+        new_st[m] = CAUTION
+        self.state[idx], self.failures[idx] = new_st, new_f
 
     def planner_config(self, idx):
         """state_machine.py:181-278: (target speed, limits [n,4], max_stop_distance (NaN = none))."""
         k = self.k
+        idx = np.asarray(idx, dtype=np.int64)
+        n = len(idx)
         v_target = float(k["ego_target_speed"])
-        base = np.array([k["ego_max_speed"], k["ego_max_accel"], k["ego_max_curvature"], _knob(k, "ego_max_lat_accel", 3.0)])
-        target = np.empty(len(idx))
-        limits = np.tile(base, (len(idx), 1))
-        msd = np.full(len(idx), np.nan)
-        for j, i in enumerate(idx):
-            ca = float(self.last_clearance_ahead[i])
-            v_env = None                                                                             # :252-266
-            if self.envelope_decel > 0.0 and math.isfinite(ca):
-                v_env = math.sqrt(2.0 * self.envelope_decel * max(ca - self.envelope_standoff, 0.0))
-            room = max(ca - 0.2, 0.05) if math.isfinite(ca) else None                                # :268-278
-            st = self.state[i]
-            if st == NORMAL:
-                target[j] = v_env if (v_env is not None and v_env < v_target) else v_target
-            elif st == CAUTION:
-                speed_mult = _knob(k, "state_machine_caution_speed_multiplier", 0.8)
-                t = v_target * speed_mult
-                if v_env is not None:
-                    t = min(t, v_env)
-                    if v_env <= 0.0 and room is not None:
-                        msd[j] = room
-                target[j] = t
-                limits[j, 1] = k["ego_max_accel"] * _knob(k, "state_machine_caution_accel_multiplier", 1.5)
-                limits[j, 0] = k["ego_max_speed"] * speed_mult
-            else:
-                target[j] = 0.0
-                limits[j, 1] = k["ego_max_accel"] * _knob(k, "state_machine_emergency_accel_multiplier", 3.0)
-                limits[j, 3] = _knob(k, "ego_max_lat_accel", 3.0) * _knob(k, "state_machine_emergency_lat_accel_multiplier", 2.0)
-                if self.envelope_decel > 0.0 and room is not None:
-                    msd[j] = room
+        lat = _knob(k, "ego_max_lat_accel", 3.0)
+        limits = np.tile(np.array([k["ego_max_speed"], k["ego_max_accel"], k["ego_max_curvature"], lat], dtype=np.float64), (n, 1))
+        ca = self.last_clearance_ahead[idx]
+        seen = np.isfinite(ca)
+        with np.errstate(invalid="ignore"):
+            # safe-speed envelope (:252-266) and stop room (:268-278); NaN = None
+            env_on = (self.envelope_decel > 0.0) & seen
+            v_env = np.where(env_on, np.sqrt(2.0 * self.envelope_decel * np.maximum(np.where(seen, ca, 0.0) - self.envelope_standoff, 0.0)), np.nan)
+            room = np.where(seen, np.maximum(np.where(seen, ca, 0.0) - 0.2, 0.05), np.nan)
+        st = self.state[idx]
+        normal, caution, emergency = st == NORMAL, st == CAUTION, st == EMERGENCY
+        target = np.full(n, v_target)
+        msd = np.full(n, np.nan)
+        m = normal & env_on & (v_env < v_target)
+        target[m] = v_env[m]
+        speed_mult = _knob(k, "state_machine_caution_speed_multiplier", 0.8)
+        t_c = np.where(env_on, np.minimum(v_target * speed_mult, np.where(env_on, v_env, 0.0)), v_target * speed_mult)
+        target[caution] = t_c[caution]
+        m = caution & env_on & (v_env <= 0.0)
+        msd[m] = room[m]
+        limits[caution, 1] = k["ego_max_accel"] * _knob(k, "state_machine_caution_accel_multiplier", 1.5)
+        limits[caution, 0] = k["ego_max_speed"] * speed_mult
+        target[emergency] = 0.0
+        limits[emergency, 1] = k["ego_max_accel"] * _knob(k, "state_machine_emergency_accel_multiplier", 3.0)
+        limits[emergency, 3] = lat * _knob(k, "state_machine_emergency_lat_accel_multiplier", 2.0)
+        if self.envelope_decel > 0.0:
+            m = emergency & seen
+            msd[m] = room[m]
         return target, limits, msd
 
 
@@ -139,10 +168,13 @@ class BatchedClosedLoop:
     """
 
     def __init__(self, waypoints_x, waypoints_y, knobs: Dict[str, float], ped_tracks: np.ndarray, ego0: np.ndarray,
-                 device: int = 0):
+                 device: int = 0, static_obstacles=None):
         k = {key: (None if (isinstance(v, float) and math.isnan(v)) else v) for key, v in knobs.items()}
         self.k = k
         self.dt = float(k["dt"])
+        # static obstacles, shared by all simulations: boundary points [M, 2], or rectangles
+        # [x_min, x_max, y_min, y_max] expanded as IntegratedSimulator._expand_static_obstacles does
+        self.static_points = expand_static_obstacles(static_obstacles)
         self.tracks = np.ascontiguousarray(ped_tracks, dtype=np.float64)
         self.n, self.n_frames, self.P, _ = self.tracks.shape
         self.ego = np.array(ego0, dtype=np.float64).reshape(self.n, 5).copy()
@@ -210,7 +242,8 @@ class BatchedClosedLoop:
         t1 = time.perf_counter()
         sel = torch.as_tensor(np.asarray(idx), device=dyn_dev.device)
         batch = DeviceBatch(self.planner, frenet, target, dyn_dev.index_select(0, sel), _lib.FOT_DYN_SINGLE,
-                            limits=limits, max_stop_distance=msd)
+                            limits=limits, max_stop_distance=msd,
+                            static_obstacles=self.static_points if len(self.static_points) else None)
         batch.launch(None)
         best = batch.out["best_idx"].cpu().numpy()
         wlen = batch.out["winner_len"].cpu().numpy()
@@ -267,22 +300,21 @@ class BatchedClosedLoop:
                                 self.ego[idx[failed], 3])
 
         # ego update (:655-676) or adaptive emergency stop (:749-802)
-        for j, i in enumerate(idx):
-            if found[j] and wlen[j] >= 2:
-                x, y, yaw, c, v, a = win[j, :, 1]
-                self.ego[i] = [x, y, yaw, v, a]
-                self.last_kappa[i] = float(c)                          # frenet_planner.py:301-302
-            else:
-                cap = k.get("ego_emergency_decel") or k["ego_max_accel"] * 2.0
-                cl = float(last_clearance[i])
-                x, y, yaw, v, a = self.ego[i]
-                required = v ** 2 / (2.0 * max(cl - 0.2, 0.05)) if math.isfinite(cl) else cap
-                max_dec = float(np.clip(required, k["ego_max_accel"], cap))
-                x += v * np.cos(yaw) * dt
-                y += v * np.sin(yaw) * dt
-                v = max(0.0, v - max_dec * dt)
-                self.ego[i] = [x, y, yaw, v, -max_dec if v > 0 else 0.0]
-                self.last_kappa[i] = 0.0                               # planner.reset_ego_curvature()
+        follow = found & (wlen >= 2)
+        f_idx = idx[follow]
+        self.ego[f_idx] = win[follow][:, [0, 1, 2, 4, 5], 1]          # x y yaw v a of the winner's second sample
+        self.last_kappa[f_idx] = win[follow][:, 3, 1]                  # frenet_planner.py:301-302
+        for i in idx[~follow]:                                         # the few without a path: scalar, as the reference computes it
+            cap = k.get("ego_emergency_decel") or k["ego_max_accel"] * 2.0
+            cl = float(last_clearance[i])
+            x, y, yaw, v, a = self.ego[i]
+            required = v ** 2 / (2.0 * max(cl - 0.2, 0.05)) if math.isfinite(cl) else cap
+            max_dec = float(np.clip(required, k["ego_max_accel"], cap))
+            x += v * np.cos(yaw) * dt
+            y += v * np.sin(yaw) * dt
+            v = max(0.0, v - max_dec * dt)
+            self.ego[i] = [x, y, yaw, v, -max_dec if v > 0 else 0.0]
+            self.last_kappa[i] = 0.0                                   # planner.reset_ego_curvature()
         # termination (:870-886): collision of the NEW ego state with the same pedestrian frame, then the goal
         t_m = time.perf_counter()
         m2 = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, device=self.device)

@@ -39,14 +39,14 @@ KNOB_KEYS = ("dt", "total_time", "obs_len", "ego_target_speed", "ego_max_speed",
              "chance_epsilon", "collision_margin_inflation")
 
 
-def run_variant(seed):
+def run_variant(seed, scenario="scenario_01_cv"):
     import yaml
     from src.config import SimulationConfig, validate_config
     from src.core.data_structures import VehicleState
     from src.simulation.integrated_simulator import IntegratedSimulator
     from src.simulation.replay_source import ReplayPedestrianSource
 
-    with open(os.path.join(REF, "scenarios", "scenario_01_cv.yaml")) as f:
+    with open(os.path.join(REF, "scenarios", scenario + ".yaml")) as f:
         d = yaml.safe_load(f)
     peds = np.array(d.pop("ped_initial_states"), dtype=float)
     d.pop("ped_groups", None)
@@ -57,11 +57,15 @@ def run_variant(seed):
         rng = np.random.default_rng(seed)
         peds[:, 0:2] += rng.normal(0, 1.5, peds[:, 0:2].shape)
         peds[:, 2:4] *= rng.uniform(0.6, 1.4, (len(peds), 1))
-        d["ego_initial_state"] = [0.0, float(rng.uniform(-0.3, 0.3)), 0.0, float(rng.uniform(2.0, 6.0)), 0.0]
+        e0 = list(d["ego_initial_state"])
+        if scenario == "scenario_01_cv":         # (kept as first recorded: rollout_s01.npz)
+            d["ego_initial_state"] = [0.0, float(rng.uniform(-0.3, 0.3)), 0.0, float(rng.uniform(2.0, 6.0)), 0.0]
+        else:
+            d["ego_initial_state"] = [e0[0], e0[1] + float(rng.uniform(-0.3, 0.3)), e0[2], float(rng.uniform(2.0, 6.0)), 0.0]
     cfg = SimulationConfig(**d)
     validate_config(cfg)
     sim = IntegratedSimulator(cfg)
-    assert sim.ego_footprint is None and len(sim.static_obstacle_points) == 0
+    assert sim.ego_footprint is None
     n_frames = int(cfg.total_time / cfg.dt) + 200
     t = np.arange(n_frames)[:, None, None] * cfg.dt
     traj = peds[None, :, 0:2] + peds[None, :, 2:4] * t
@@ -98,10 +102,43 @@ def run_variant(seed):
     knobs = {k: getattr(cfg, k, None) for k in KNOB_KEYS}
     return dict(traj=traj, ego0=np.array(cfg.ego_initial_state, dtype=float), ego=np.array(ego), fsm=np.array(fsm),
                 found=np.array(found), calls=np.array(calls), reason=reason, knobs=knobs,
+                static_points=np.asarray(sim.static_obstacle_points, dtype=float).reshape(-1, 2),
                 wx=np.array(cfg.reference_waypoints_x, dtype=float), wy=np.array(cfg.reference_waypoints_y, dtype=float))
 
 
+def record(scenario, out_name, seeds):
+    store = {}
+    for k, seed in enumerate(seeds):
+        r = run_variant(seed, scenario)
+        for name in ("traj", "ego0", "ego", "fsm", "found", "calls", "wx", "wy"):
+            store[f"v{k}/{name}"] = r[name]
+        store[f"v{k}/reason"] = np.array(r["reason"])
+        if k == 0:
+            for key, val in r["knobs"].items():
+                store["knob/" + key] = np.array(np.nan if val is None else val, dtype=float)
+            store["static_points"] = r["static_points"]
+        states = np.bincount(r["fsm"], minlength=3)
+        print(f"{scenario} variant {k}: {len(r['ego'])} steps, {r['reason']}, plan calls {int(r['calls'].sum())}, "
+              f"states N/C/E {states.tolist()}, failed steps {int((~r['found']).sum())}, static points {len(r['static_points'])}")
+    store["n_variants"] = np.array(len(seeds))
+    np.savez_compressed(os.path.join(HERE, out_name), **store)
+    print("wrote", out_name, os.path.getsize(os.path.join(HERE, out_name)) // 1024, "KiB")
+
+
 def main():
+    """No argument: scenario_01_cv and three perturbed variants -> rollout_s01.npz (as first recorded).
+    `s02` / `s03`: scenario_02_cv (corridor between two static walls) / scenario_03_cv (right turn) and one
+    perturbed variant each -> rollout_s02.npz / rollout_s03.npz."""
+    which = sys.argv[1:] or ["s01"]
+    if "s02" in which:
+        record("scenario_02_cv", "rollout_s02.npz", (0, 1))
+    if "s03" in which:
+        record("scenario_03_cv", "rollout_s03.npz", (0, 1))
+    if "s01" in which:
+        main_s01()
+
+
+def main_s01():
     store = {}
     for k, seed in enumerate((0, 1, 2, 3)):
         r = run_variant(seed)

@@ -20,28 +20,35 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 EGO_TOL = 1e-7
 
 
-@pytest.fixture(scope="module")
-def golden():
-    z = np.load(os.path.join(HERE, "golden", "rollout_s01.npz"))
+def _load(name):
+    z = np.load(os.path.join(HERE, "golden", name))
     knobs = {k[5:]: float(z[k]) for k in z.files if k.startswith("knob/")}
     n = int(z["n_variants"])
     runs = [{name: z[f"v{i}/{name}"] for name in ("traj", "ego0", "ego", "fsm", "found", "calls", "wx", "wy", "reason")}
             for i in range(n)]
-    return knobs, runs
+    static = z["static_points"] if "static_points" in z.files else None
+    return knobs, runs, static
 
 
-def _drive(knobs, runs):
+@pytest.fixture(scope="module")
+def golden():
+    return _load("rollout_s01.npz")[:2]
+
+
+def _drive(knobs, runs, static=None):
     from integrated_path_planning_b200.rollout import BatchedClosedLoop
     tracks = np.stack([r["traj"] for r in runs])
     ego0 = np.stack([r["ego0"] for r in runs])
-    sim = BatchedClosedLoop(runs[0]["wx"], runs[0]["wy"], knobs, tracks, ego0)
+    sim = BatchedClosedLoop(runs[0]["wx"], runs[0]["wy"], knobs, tracks, ego0, static_obstacles=static)
     sim.warmup()
     return sim, sim.run()
 
 
-def test_batch_reproduces_reference_rollouts(golden):
-    knobs, runs = golden
-    sim, out = _drive(knobs, runs)
+@pytest.mark.parametrize("name", ["rollout_s01.npz", "rollout_s02.npz", "rollout_s03.npz"])
+def test_batch_reproduces_reference_rollouts(name):
+    """s01: open road, 14 pedestrians (four variants); s02: corridor between two static walls; s03: right turn."""
+    knobs, runs, static = _load(name)
+    sim, out = _drive(knobs, runs, static)
     for i, r in enumerate(runs):
         n = len(r["ego"])
         assert out["steps"][i] == n, f"variant {i}: {out['steps'][i]} steps, reference {n}"
