@@ -17,8 +17,8 @@ pedestrian source and the constant-velocity predictor (src/simulation/integrated
 src/pedestrian/observer.py:52-86; src/simulation/replay_source.py:31-111), so that a batch reproduces the
 reference's trajectories (tests/test_gpu_rollout.py, golden roll-outs recorded from the unmodified
 reference by tests/golden/make_golden_rollout.py).  Pedestrian ground truth stays outside (replay), as in
-the reference's own pysocialforce-free source; static obstacles are shared by the simulations of a batch; the
-multi-circle footprint is not wired into this driver yet.
+the reference's own pysocialforce-free source; static obstacles and the ego footprint (single circle or the
+multi-circle cover) are shared by the simulations of a batch.
 """
 from __future__ import annotations
 
@@ -43,6 +43,27 @@ def _knob(knobs, key, default):
     if v is None or (isinstance(v, float) and math.isnan(v)):
         return default
     return v
+
+
+class _Footprint:
+    """EgoFootprint.multi_circle (src/core/footprint.py:27-42): n equal circles along the heading axis covering the
+    vehicle_length x vehicle_width rectangle."""
+
+    def __init__(self, vehicle_length: float, vehicle_width: float, n_circles: int):
+        if n_circles < 1:
+            raise ValueError(f"n_circles must be >= 1, got {n_circles}")
+        seg = vehicle_length / n_circles
+        self.offsets = -vehicle_length / 2 + seg / 2 + seg * np.arange(n_circles)
+        self.radius = float(np.hypot(seg / 2, vehicle_width / 2))
+
+
+def footprint_from_knobs(k) -> Optional[_Footprint]:
+    """footprint_from_config (footprint.py:68-78): None = the legacy single circle of ego_radius."""
+    mode = k.get("ego_footprint", None)
+    multi = mode == "multi_circle" or bool(k.get("ego_footprint_multi_circle", 0.0))
+    if not multi:
+        return None
+    return _Footprint(_knob(k, "vehicle_length", 4.5), _knob(k, "vehicle_width", 2.0), int(_knob(k, "ego_footprint_n_circles", 3)))
 
 
 def expand_static_obstacles(static_obstacles, step: float = 0.5) -> np.ndarray:
@@ -79,7 +100,8 @@ class _StateMachines:
         self.k = k
         self.state = np.zeros(n, dtype=np.int64)
         self.failures = np.zeros(n, dtype=np.int64)
-        combined = _knob(k, "ego_radius", 1.0) + _knob(k, "ped_radius", 0.2)                       # :44-46
+        fp = footprint_from_knobs(k)                                                               # effective_ego_radius
+        combined = (fp.radius if fp is not None else _knob(k, "ego_radius", 1.0)) + _knob(k, "ped_radius", 0.2)   # :44-46
         rc, re = k.get("state_machine_recover_clearance_caution"), k.get("state_machine_recover_clearance_emergency")
         nan = lambda v: v is None or (isinstance(v, float) and math.isnan(v))
         self.clearance_caution = _knob(k, "state_machine_safe_distance_caution", 2.0) - combined if nan(rc) else rc
@@ -180,6 +202,7 @@ class BatchedClosedLoop:
         self.ego = np.array(ego0, dtype=np.float64).reshape(self.n, 5).copy()
         self.spline = CubicSpline2D(list(waypoints_x), list(waypoints_y))
         self.ego_radius, self.ped_radius = _knob(k, "ego_radius", 1.0), _knob(k, "ped_radius", 0.3)
+        self.footprint = footprint_from_knobs(k)
         self.planner = BatchFrenetPlanner(
             self.spline, max_speed=k["ego_max_speed"], max_accel=k["ego_max_accel"], max_curvature=k["ego_max_curvature"],
             max_lat_accel=_knob(k, "ego_max_lat_accel", 3.0), dt=self.dt, d_road_w=k["d_road_w"],
@@ -187,7 +210,7 @@ class BatchedClosedLoop:
             obstacle_radius=_knob(k, "obstacle_radius", self.ped_radius), min_t=_knob(k, "min_t", 4.0),
             max_t=_knob(k, "max_t", 5.0), d_t_s=_knob(k, "d_t_s", 5.0 / 3.6), k_j=k["k_j"], k_t=k["k_t"], k_d=k["k_d"],
             k_s_dot=k["k_s_dot"], k_lat=k["k_lat"], k_lon=k["k_lon"], chance_epsilon=_knob(k, "chance_epsilon", 0.0),
-            collision_margin_inflation=_knob(k, "collision_margin_inflation", 1.0), device=device)
+            collision_margin_inflation=_knob(k, "collision_margin_inflation", 1.0), footprint=self.footprint, device=device)
         self.device = device
         self.post = DevicePredictionPostprocessor(pred_len=int(_knob(k, "pred_len", 12)), sgan_dt=SGAN_DT, sim_dt=self.dt,
                                                   plan_horizon=_knob(k, "max_t", 5.0), device=device)
@@ -270,7 +293,7 @@ class BatchedClosedLoop:
             import torch
             dyn = torch.from_numpy(np.ascontiguousarray(pos[:, None, :, None, :])).to(self.post._dev)
         t_pred = time.perf_counter()
-        m = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, device=self.device)
+        m = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, footprint=self.footprint, device=self.device)
         clearance, ahead = m["clearance"].cpu().numpy(), m["clearance_ahead"].cpu().numpy()
         self.timers["prediction"] += t_pred - t_step
         self.timers["metrics"] += time.perf_counter() - t_pred
@@ -317,7 +340,7 @@ class BatchedClosedLoop:
             self.last_kappa[i] = 0.0                                   # planner.reset_ego_curvature()
         # termination (:870-886): collision of the NEW ego state with the same pedestrian frame, then the goal
         t_m = time.perf_counter()
-        m2 = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, device=self.device)
+        m2 = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, footprint=self.footprint, device=self.device)
         collided = m2["collision"].cpu().numpy()
         self.timers["metrics"] += time.perf_counter() - t_m
         hit = idx[collided[idx]]

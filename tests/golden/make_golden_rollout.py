@@ -36,10 +36,10 @@ KNOB_KEYS = ("dt", "total_time", "obs_len", "ego_target_speed", "ego_max_speed",
              "state_machine_caution_speed_multiplier", "state_machine_caution_accel_multiplier",
              "state_machine_emergency_accel_multiplier", "state_machine_emergency_lat_accel_multiplier",
              "state_machine_envelope_decel", "state_machine_envelope_standoff", "ego_emergency_decel",
-             "chance_epsilon", "collision_margin_inflation")
+             "chance_epsilon", "collision_margin_inflation", "vehicle_length", "vehicle_width", "ego_footprint_n_circles")
 
 
-def run_variant(seed, scenario="scenario_01_cv"):
+def run_variant(seed, scenario="scenario_01_cv", footprint=False):
     import yaml
     from src.config import SimulationConfig, validate_config
     from src.core.data_structures import VehicleState
@@ -53,6 +53,8 @@ def run_variant(seed, scenario="scenario_01_cv"):
     d["sgan_model_path"] = None
     d["visualization_enabled"] = False
     d["prediction_method"] = "cv"
+    if footprint:
+        d["ego_footprint"] = "multi_circle"
     if seed > 0:
         rng = np.random.default_rng(seed)
         peds[:, 0:2] += rng.normal(0, 1.5, peds[:, 0:2].shape)
@@ -65,7 +67,7 @@ def run_variant(seed, scenario="scenario_01_cv"):
     cfg = SimulationConfig(**d)
     validate_config(cfg)
     sim = IntegratedSimulator(cfg)
-    assert sim.ego_footprint is None
+    assert (sim.ego_footprint is not None) == bool(footprint)
     n_frames = int(cfg.total_time / cfg.dt) + 200
     t = np.arange(n_frames)[:, None, None] * cfg.dt
     traj = peds[None, :, 0:2] + peds[None, :, 2:4] * t
@@ -100,16 +102,17 @@ def run_variant(seed, scenario="scenario_01_cv"):
             reason = "goal"
             break
     knobs = {k: getattr(cfg, k, None) for k in KNOB_KEYS}
+    knobs["ego_footprint_multi_circle"] = 1.0 if footprint else 0.0
     return dict(traj=traj, ego0=np.array(cfg.ego_initial_state, dtype=float), ego=np.array(ego), fsm=np.array(fsm),
                 found=np.array(found), calls=np.array(calls), reason=reason, knobs=knobs,
                 static_points=np.asarray(sim.static_obstacle_points, dtype=float).reshape(-1, 2),
                 wx=np.array(cfg.reference_waypoints_x, dtype=float), wy=np.array(cfg.reference_waypoints_y, dtype=float))
 
 
-def record(scenario, out_name, seeds):
+def record(scenario, out_name, seeds, footprint=False):
     store = {}
     for k, seed in enumerate(seeds):
-        r = run_variant(seed, scenario)
+        r = run_variant(seed, scenario, footprint)
         for name in ("traj", "ego0", "ego", "fsm", "found", "calls", "wx", "wy"):
             store[f"v{k}/{name}"] = r[name]
         store[f"v{k}/reason"] = np.array(r["reason"])
@@ -132,6 +135,8 @@ def main():
     which = sys.argv[1:] or ["s01"]
     if "s02" in which:
         record("scenario_02_cv", "rollout_s02.npz", (0, 1))
+    if "s02fp" in which:          # the same corridor with the three-circle footprint of the 4.5 m x 2.0 m vehicle
+        record("scenario_02_cv", "rollout_s02fp.npz", (0, 2), footprint=True)
     if "s03" in which:
         record("scenario_03_cv", "rollout_s03.npz", (0, 1))
     if "s01" in which:

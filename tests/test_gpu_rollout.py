@@ -44,9 +44,10 @@ def _drive(knobs, runs, static=None):
     return sim, sim.run()
 
 
-@pytest.mark.parametrize("name", ["rollout_s01.npz", "rollout_s02.npz", "rollout_s03.npz"])
+@pytest.mark.parametrize("name", ["rollout_s01.npz", "rollout_s02.npz", "rollout_s02fp.npz", "rollout_s03.npz"])
 def test_batch_reproduces_reference_rollouts(name):
-    """s01: open road, 14 pedestrians (four variants); s02: corridor between two static walls; s03: right turn."""
+    """s01: open road, 14 pedestrians (four variants); s02: corridor between two static walls; s02fp: the same with
+    the three-circle footprint (planner collision test, safety metrics and state-machine radii); s03: right turn."""
     knobs, runs, static = _load(name)
     sim, out = _drive(knobs, runs, static)
     for i, r in enumerate(runs):
