@@ -215,20 +215,22 @@ def main():
     evals_step = batch.dense_evals()
     stream = torch.cuda.Stream(device=local_rank)
     # The one collective of the path: every step's winners (cost per query) are all-gathered.  The
-    # gather runs on its own stream behind the sweep that produced them, double-buffered, so the next
+    # gather runs on its own stream behind the sweep that produced them, four staging buffers deep, so the next
     # step's sweep does not wait for the slowest rank of this one; the timed region ends after the
-    # last gather has completed on every rank.
-    gstream = torch.cuda.Stream(device=local_rank) if world > 1 else None
-    stage_buf = [torch.empty_like(batch.out["best_cost"]) for _ in range(2)] if world > 1 else None
+    # last gather has completed on every rank.  The gather stream has the higher priority: the collective's few
+    # CTAs then take the first SM slots the running sweep frees instead of queueing behind its whole grid.
+    N_GBUF = 4
+    gstream = torch.cuda.Stream(device=local_rank, priority=-1) if world > 1 else None
+    stage_buf = [torch.empty_like(batch.out["best_cost"]) for _ in range(N_GBUF)] if world > 1 else None
     gathered = [torch.empty((world,) + tuple(batch.out["best_cost"].shape), dtype=torch.float64, device="cuda")
-                for _ in range(2)] if world > 1 else None
-    g_done = [None, None]
+                for _ in range(N_GBUF)] if world > 1 else None
+    g_done = [None] * N_GBUF
     step_no = [0]
 
     def resident_step():
         batch.launch(stream.cuda_stream)
         if world > 1:
-            k = step_no[0] & 1
+            k = step_no[0] % N_GBUF
             step_no[0] += 1
             with torch.cuda.stream(stream):
                 if g_done[k] is not None:
@@ -273,6 +275,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = evals_step * world / (ms_step * 1e-3)
+    # per-rank kernel time of a step (prepass + sweep + winner, CUDA events of each rank's own launches): with no
+    # data-path collective the slowest GPU sets the pace, and this is where a scaling loss shows
+    per_rank_ms = [float(stage.sum(axis=1).mean())]
+    if world > 1:
+        tk = torch.tensor(per_rank_ms, dtype=torch.float64, device="cuda")
+        allk = torch.empty(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allk, tk)
+        per_rank_ms = [float(v) for v in allk.cpu()]
+    per_rank_mhz = [float(clocks.get("sm_mhz") or 0.0)]
+    if world > 1:
+        tk = torch.tensor(per_rank_mhz, dtype=torch.float64, device="cuda")
+        allk = torch.empty(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allk, tk)
+        per_rank_mhz = [float(v) for v in allk.cpu()]
 
     # e2e leg: host-pointer C-ABI call, pinned inputs, H2D + kernels + D2H inside the timed region
     dyn_pinned = torch.from_numpy(dyn).pin_memory()
@@ -428,6 +444,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "winners_match_resident": same},
             "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+            "per_rank_kernel_ms_per_step": per_rank_ms, "per_rank_sm_mhz": per_rank_mhz,
             "plan_latency": plan_latency, "e2e_device_prediction": e2e_cv, "closed_loop": closed_loop,
             "candidates_per_s": float(res.n_cand.sum()) * world / (ms_step * 1e-3),
             "evals_per_step_per_gpu": evals_step}
