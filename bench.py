@@ -331,10 +331,7 @@ def main():
             for d, h_ in zip(dev_in, host_in):
                 d.copy_(h_, non_blocking=True)
             post.predict_cv(dev_in[0], dev_in[1], None, dev_in[2], out=dyn_buf)
-            batch_cv.launch(stream.cuda_stream)
-            for k, v in batch_cv.out.items():
-                host_out[k].copy_(v, non_blocking=True)
-        stream.synchronize()
+        batch_cv.launch_to_host(host_out, stream.cuda_stream)    # ranges of queries; winners go back while the rest is swept
 
     for _ in range(args.warmup):
         cv_step()

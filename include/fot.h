@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FOT_ABI_VERSION 2   /* 2: + prediction post-processing and safety metrics entry points */
+#define FOT_ABI_VERSION 3   /* 2: + prediction post-processing and safety metrics; 3: + fot_plan_batch_device_to_host */
 #define FOT_MAX_CIRCLES 8
 #define FOT_N_STATS 8    /* ok, max_speed, max_accel, max_curvature, max_lat_accel, road_bound, collision, stop_distance */
 #define FOT_N_SERIES 15  /* t s s_d s_dd s_ddd d d_d d_dd d_ddd x y yaw c v a  (data_structures.py:149-181) */
@@ -142,6 +142,13 @@ int fot_candidate_count(const fot_handle_t* h, int n_v, int has_brake);
  * DEVICE pointers.  Asynchronous on `stream` (a cudaStream_t, NULL = the handle's own stream,
  * which is then synchronised before returning). */
 int fot_plan_batch_device(fot_handle_t* h, const fot_batch_t* batch, const fot_result_t* res, void* stream);
+
+/* DEVICE inputs (`batch`), HOST results (`res`): for a caller whose obstacle tensor is produced on the GPU (the
+ * entry points below) and whose winners are consumed on the host -- frenet_planner.py:271-294 for n_q queries
+ * behind integrated_simulator.py:447-525.  Queries are swept in ranges and each range's winners are copied back
+ * while the next range runs.  `stream`: the cudaStream_t on which the inputs become ready (NULL: ready now).
+ * Returns when the results are in `res` (page-locked result arrays make the copies asynchronous). */
+int fot_plan_batch_device_to_host(fot_handle_t* h, const fot_batch_t* batch, const fot_result_t* res, void* stream);
 
 /* Same call with HOST pointers everywhere: stages the small per-query arrays through the handle's
  * pinned buffers, uploads the obstacle tensor straight from the caller's memory, runs the kernels,

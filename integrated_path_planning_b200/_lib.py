@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfot.so")
 
-FOT_ABI_VERSION = 2
+FOT_ABI_VERSION = 3
 FOT_MAX_CIRCLES = 8
 FOT_N_STATS = 8
 FOT_N_SERIES = 15
@@ -77,6 +77,7 @@ SYMBOLS = (
     ("fot_candidate_count", C.c_int, (C.c_void_p, C.c_int, C.c_int)),
     ("fot_plan_batch_device", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult), C.c_void_p)),
     ("fot_plan_batch_host", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult))),
+    ("fot_plan_batch_device_to_host", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult), C.c_void_p)),
     ("fot_last_kernel_ms", C.c_float, (C.c_void_p,)),
     ("fot_launch_stage_ms", C.c_int, (C.c_void_p, C.c_int, C.POINTER(C.c_float * 3))),
     ("fot_probe_fma_tflops", C.c_int, (C.c_int, C.c_int, c_double_p)),

@@ -809,6 +809,88 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   return FOT_OK;
 }
 
+// Device inputs, HOST results: the call of a caller whose obstacle tensor was produced on the GPU (the prediction
+// post-processing of fot_predict.cuh) but who consumes the winners on the host.  The queries are swept in three
+// ranges on the priority streams, and each range's winners go back over PCIe while the next range is swept, so
+// only the last range's read-back is exposed.  `stream` is the stream on which the inputs become ready (NULL:
+// they are ready now).  Returns when the results are in `res`.
+extern "C" int fot_plan_batch_device_to_host(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r, void* stream) {
+  int rc = check_batch(h, b, r);
+  if (rc != FOT_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  const int nq = b->n_q, NT = h->plan.n_t_max;
+  size_t ro = 0;
+  auto rtake = [&](size_t bytes) { size_t o = ro; ro = align_up(ro + bytes); return o; };
+  const size_t r_bi = rtake((size_t)nq * 4), r_bc = rtake((size_t)nq * 8), r_st = rtake((size_t)nq * FOT_N_STATS * 4),
+               r_wl = rtake((size_t)nq * 4), r_w = rtake((size_t)nq * FOT_N_SERIES * NT * 8);
+  const size_t r_cc = r->cand_cat ? rtake((size_t)nq * r->cand_stride) : 0;
+  const size_t r_cs = r->cand_cost ? rtake((size_t)nq * r->cand_stride * 8) : 0;
+  CK(h->out_d.reserve(ro));
+  char* od = (char*)h->out_d.p;
+  // ranges: about 1/2, 5/16, 3/16 of the queries in whole waves; one range for small batches or the fallback kernel
+  int n_ranges = 1, bounds[4] = {0, nq, nq, nq};
+  {
+    ItemGeom ig{};
+    size_t ismem = 0;
+    const char* force = getenv("FOT_SWEEP");
+    const bool items = item_geometry(h, b, &ig, &ismem) && !(force && !strcmp(force, "generic"));
+    if (items && nq >= 1024) {
+      const int wave = 2 * h->sms;
+      auto waves = [&](int frac16) { const int w = std::max(1, (int)((long long)nq * frac16 / 16 / wave)); return w * wave; };
+      const int cuts[] = {waves(8), waves(13), nq};
+      n_ranges = 3;
+      for (int c = 0; c < n_ranges; ++c) bounds[c + 1] = std::min(nq, std::max(cuts[c], bounds[c]));
+    }
+  }
+  if (stream) CK(cudaEventRecord(h->ev_blob, (cudaStream_t)stream));
+  const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
+  const size_t dyn_q_bytes = has_dyn ? (size_t)b->S * b->P * b->T_obs * 16 : 0;
+  for (int c = 0; c < n_ranges; ++c) {
+    const int q0 = bounds[c], cq = bounds[c + 1] - q0;
+    if (cq <= 0) continue;
+    cudaStream_t st = h->pstream[c & 3];
+    if (stream) CK(cudaStreamWaitEvent(st, h->ev_blob, 0));
+    fot_batch_t db = *b;
+    db.n_q = cq;
+    db.frenet = b->frenet + (size_t)q0 * 6;
+    db.target_speed = b->target_speed + q0;
+    db.limits = b->limits + (size_t)q0 * 4;
+    db.stop_dist = b->stop_dist + q0;
+    db.v_grid = b->v_grid + (size_t)q0 * b->n_v_max;
+    db.n_v = b->n_v + q0;
+    if (has_dyn) db.dyn = (const double*)((const char*)b->dyn + (size_t)q0 * dyn_q_bytes);
+    if (b->n_static > 0 && b->static_per_query) db.static_obs = b->static_obs + (size_t)q0 * b->n_static * 2;
+    fot_result_t dr = *r;
+    dr.best_idx = (int32_t*)(od + r_bi) + q0;
+    dr.best_cost = (double*)(od + r_bc) + q0;
+    dr.stats = (int32_t*)(od + r_st) + (size_t)q0 * FOT_N_STATS;
+    dr.winner_len = (int32_t*)(od + r_wl) + q0;
+    dr.winner = (double*)(od + r_w) + (size_t)q0 * FOT_N_SERIES * NT;
+    dr.cand_cat = r->cand_cat ? (uint8_t*)(od + r_cc) + (size_t)q0 * r->cand_stride : nullptr;
+    dr.cand_cost = r->cand_cost ? (double*)(od + r_cs) + (size_t)q0 * r->cand_stride : nullptr;
+    rc = launch_all(h, &db, &dr, st, (size_t)q0, (size_t)nq);
+    if (rc != FOT_OK) return rc;
+    cudaStream_t ds = h->d2h_stream;
+    CK(cudaEventRecord(h->ev_done[c], st));
+    CK(cudaStreamWaitEvent(ds, h->ev_done[c], 0));
+    CK(cudaMemcpyAsync(r->best_idx + q0, dr.best_idx, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
+    CK(cudaMemcpyAsync(r->best_cost + q0, dr.best_cost, (size_t)cq * 8, cudaMemcpyDeviceToHost, ds));
+    CK(cudaMemcpyAsync(r->stats + (size_t)q0 * FOT_N_STATS, dr.stats, (size_t)cq * FOT_N_STATS * 4, cudaMemcpyDeviceToHost, ds));
+    CK(cudaMemcpyAsync(r->winner_len + q0, dr.winner_len, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
+    CK(cudaMemcpyAsync(r->winner + (size_t)q0 * FOT_N_SERIES * NT, dr.winner, (size_t)cq * FOT_N_SERIES * NT * 8,
+                       cudaMemcpyDeviceToHost, ds));
+    if (r->cand_cat)
+      CK(cudaMemcpyAsync(r->cand_cat + (size_t)q0 * r->cand_stride, dr.cand_cat, (size_t)cq * r->cand_stride,
+                         cudaMemcpyDeviceToHost, ds));
+    if (r->cand_cost)
+      CK(cudaMemcpyAsync(r->cand_cost + (size_t)q0 * r->cand_stride, dr.cand_cost, (size_t)cq * r->cand_stride * 8,
+                         cudaMemcpyDeviceToHost, ds));
+  }
+  CK(cudaStreamSynchronize(h->d2h_stream));
+  for (int c = 0; c < n_ranges; ++c) CK(cudaStreamSynchronize(h->pstream[c & 3]));
+  return FOT_OK;
+}
+
 extern "C" float fot_last_kernel_ms(const fot_handle_t* h) {
   if (!h || !h->timed) return -1.0f;
   float ms = -1.0f;

@@ -196,3 +196,30 @@ def test_validity_screens_agree_with_the_oracle_near_the_limits():
                 res = pl.plan_batch(fs[None], target, dynamic_obstacles=dyn[None], limits=pl.resolve_limits(over),
                                     want_candidates=True)
                 _check(res, [orc.plan_frenet(tuple(fs), np.empty((0, 2)), dyn, target, over)])
+
+
+def test_device_inputs_host_results_entry_point_matches_the_resident_launch():
+    """fot_plan_batch_device_to_host: device-resident batch, winners delivered to host arrays range by range.
+    Same bits as the plain launch followed by a read-back, for a batch that is cut into three ranges and for a
+    small one that is not."""
+    import torch
+    import bench
+    from integrated_path_planning_b200 import DeviceBatch, _lib
+    pl = _planner()
+    for count, tile in ((230, 6), (40, 1)):
+        _, frenet, dyn = bench.make_queries(9000, count)
+        frenet, dyn = np.tile(frenet, (tile, 1)), np.tile(dyn, (tile, 1, 1, 1, 1))
+        batch = DeviceBatch(pl, frenet, 6.0, dyn, _lib.FOT_DYN_SINGLE)
+        batch.launch(None)
+        want = {k: v.cpu() for k, v in batch.out.items()}
+        host = {k: torch.full(v.shape, -7, dtype=v.dtype).pin_memory() for k, v in batch.out.items()}
+        batch.launch_to_host(host, torch.cuda.current_stream().cuda_stream)
+        for k in want:
+            a, b = want[k].numpy(), host[k].numpy()
+            if k == "winner":                                  # rows are defined up to winner_len; the padding is not written
+                n = want["winner_len"].numpy()
+                for q in range(a.shape[0]):
+                    assert np.array_equal(a[q, :, :n[q]].view(np.uint64), b[q, :, :n[q]].view(np.uint64)), (count * tile, q)
+                continue
+            same = np.array_equal(a.view(np.uint64), b.view(np.uint64)) if a.dtype == np.float64 else np.array_equal(a, b)
+            assert same, (count * tile, k)
