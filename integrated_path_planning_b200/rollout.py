@@ -190,7 +190,7 @@ class BatchedClosedLoop:
     """
 
     def __init__(self, waypoints_x, waypoints_y, knobs: Dict[str, float], ped_tracks: np.ndarray, ego0: np.ndarray,
-                 device: int = 0, static_obstacles=None):
+                 device: int = 0, static_obstacles=None, record: bool = False):
         k = {key: (None if (isinstance(v, float) and math.isnan(v)) else v) for key, v in knobs.items()}
         self.k = k
         self.dt = float(k["dt"])
@@ -234,6 +234,9 @@ class BatchedClosedLoop:
         self.active = np.ones(self.n, dtype=bool)
         self.reason = np.array(["timeout"] * self.n, dtype=object)
         self.n_plan_calls = 0
+        # record=True keeps what IntegratedSimulator.save_results writes (full planned paths, predictions, metrics)
+        self.record = bool(record)
+        self.history = [[] for _ in range(self.n)]
         self.timers = {"frenet_host": 0.0, "sweep": 0.0, "prediction": 0.0, "metrics": 0.0, "total": 0.0}
 
     # -- pedestrians + observer -----------------------------------------------------------------
@@ -272,6 +275,7 @@ class BatchedClosedLoop:
         wlen = batch.out["winner_len"].cpu().numpy()
         win = batch.out["winner"][:, 9:15, :2].cpu().numpy()          # x y yaw c v a, first two samples
         found = ok & (best >= 0)
+        self._last_full = (batch.out["winner"].cpu().numpy(), batch.out["best_cost"].cpu().numpy()) if self.record else None
         self.timers["frenet_host"] += t1 - t0
         self.timers["sweep"] += time.perf_counter() - t1
         return found, wlen, win
@@ -292,6 +296,11 @@ class BatchedClosedLoop:
         else:
             import torch
             dyn = torch.from_numpy(np.ascontiguousarray(pos[:, None, :, None, :])).to(self.post._dev)
+        rec = None
+        if self.record:
+            ready = len(self.hist) >= self.obs_len
+            pred = self.post.predict_cv(self.hist[-1], self.hist[-2], stale, None, obs_float32=True)[:, 0].cpu().numpy() if ready else None
+            rec = {"time": self.time, "pred": pred, "old_a": self.ego[:, 4].copy()}
         t_pred = time.perf_counter()
         m = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, footprint=self.footprint, device=self.device)
         clearance, ahead = m["clearance"].cpu().numpy(), m["clearance_ahead"].cpu().numpy()
@@ -303,6 +312,8 @@ class BatchedClosedLoop:
         state_before = self.fsm.state[idx].copy()
         target, limits, msd = self.fsm.planner_config(idx)
         found, wlen, win = self._plan(idx, target, limits, msd, dyn)
+        if self.record:
+            full_w, full_c = (a.copy() for a in self._last_full)
         self.fsm.update(idx, found, clearance[idx], ahead[idx], self.ego[idx, 3])
         attempts = np.zeros(len(idx), dtype=np.int64)
         calls = np.ones(len(idx), dtype=np.int64)
@@ -316,6 +327,8 @@ class BatchedClosedLoop:
             t2, l2, m2 = self.fsm.planner_config(sub)
             f2, w2, win2 = self._plan(sub, t2, l2, m2, dyn)
             found[retry], wlen[retry], win[retry] = f2, w2, win2
+            if self.record:
+                full_w[retry], full_c[retry] = self._last_full
             failed = retry[~f2]
             state_before[failed] = self.fsm.state[idx[failed]]
             if len(failed):
@@ -350,9 +363,51 @@ class BatchedClosedLoop:
             s_now = self.goal_conv.nearest_s(alive, self.ego[alive, 0], self.ego[alive, 1])
             done = alive[self.spline.s[-1] - s_now < 2.0]
             self.active[done], self.reason[done] = False, "goal"
+        if self.record:
+            md, ttc = m2["min_distance"].cpu().numpy(), m2["ttc"].cpu().numpy()
+            names = ("NORMAL", "CAUTION", "EMERGENCY")
+            for j, i in enumerate(idx):
+                n_w = int(wlen[j]) if found[j] else 0
+                self.history[i].append({
+                    "time": rec["time"], "ego": self.ego[i].copy(), "jerk": (self.ego[i, 4] - rec["old_a"][i]) / dt,
+                    "state": names[int(self.fsm.state[i])], "min_distance": float(md[i]), "ttc": float(ttc[i]),
+                    "ped_pos": pos[i].copy(), "ped_vel": vel[i].copy(), "pred": None if rec["pred"] is None else rec["pred"][i],
+                    "path": full_w[j][:, :n_w].copy() if found[j] else None, "cost": float(full_c[j]) if found[j] else float("inf")})
         self.time += dt
         self.timers["total"] += time.perf_counter() - t_step
         return idx, found, calls
+
+    def save_results(self, i: int, output_dir: str) -> str:
+        """trajectory.npz of simulation `i` with the keys, shapes and construction of
+        IntegratedSimulator.save_results (integrated_simulator.py:906-985); needs record=True.  (The reference's
+        metrics_summary.csv / metrics_report.txt come from its own metrics module and are not written here.)"""
+        import os
+        if not self.record:
+            raise RuntimeError("BatchedClosedLoop(record=True) is needed to write result files")
+        h = self.history[i]
+        os.makedirs(output_dir, exist_ok=True)
+        col = lambda row: 9 + ("x", "y", "yaw", "c", "v", "a").index(row)         # winner block rows (types.SERIES)
+        planned = lambda row: [np.array(r["path"][col(row)]) if r["path"] is not None else np.array([]) for r in h]
+        goals = self.tracks[i, -1]
+        path = os.path.join(output_dir, "trajectory.npz")
+        np.savez(
+            path,
+            times=np.array([r["time"] for r in h]),
+            ego_x=np.array([r["ego"][0] for r in h]), ego_y=np.array([r["ego"][1] for r in h]),
+            ego_v=np.array([r["ego"][3] for r in h]), ego_yaw=np.array([r["ego"][2] for r in h]),
+            ego_jerk=np.array([r["jerk"] for r in h]),
+            ego_state=np.array([r["state"] for r in h]),
+            min_distances=np.array([r["min_distance"] for r in h]), ttc=np.array([r["ttc"] for r in h]),
+            proc_prediction=np.zeros(len(h)), proc_planning=np.zeros(len(h)),      # wall-clock per step: not reproduced
+            ped_positions=np.array([r["ped_pos"] for r in h], dtype=object),
+            ped_velocities=np.array([r["ped_vel"] for r in h], dtype=object),
+            ped_goals=np.array([goals.copy() for _ in h], dtype=object),
+            predicted_trajectories=np.array([r["pred"] if r["pred"] is not None else np.empty((0,)) for r in h], dtype=object),
+            planned_x=np.array(planned("x"), dtype=object), planned_y=np.array(planned("y"), dtype=object),
+            planned_v=np.array(planned("v"), dtype=object), planned_a=np.array(planned("a"), dtype=object),
+            planned_yaw=np.array(planned("yaw"), dtype=object),
+            planned_cost=np.array([r["cost"] for r in h]))
+        return path
 
     def run(self, n_steps: Optional[int] = None):
         """IntegratedSimulator.run (:842-892) for every simulation; returns per-simulation histories."""

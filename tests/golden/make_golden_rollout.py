@@ -109,6 +109,57 @@ def run_variant(seed, scenario="scenario_01_cv", footprint=False):
                 wx=np.array(cfg.reference_waypoints_x, dtype=float), wy=np.array(cfg.reference_waypoints_y, dtype=float))
 
 
+def record_trajectory_file(n_steps=80, n_pred=5):
+    """The reference's own result file: scenario_01_cv for `n_steps` steps, IntegratedSimulator.save_results(), and
+    the first `n_steps` entries of every array of its trajectory.npz (predictions: first `n_pred` steps only) ->
+    rollout_s01_trajectory.npz.  Ragged per-step arrays are stored padded with NaN plus their lengths."""
+    import tempfile
+    import yaml
+    from src.config import SimulationConfig, validate_config
+    from src.simulation.integrated_simulator import IntegratedSimulator
+    from src.simulation.replay_source import ReplayPedestrianSource
+    with open(os.path.join(REF, "scenarios", "scenario_01_cv.yaml")) as f:
+        d = yaml.safe_load(f)
+    peds = np.array(d.pop("ped_initial_states"), dtype=float)
+    d.pop("ped_groups", None)
+    d["sgan_model_path"] = None
+    d["visualization_enabled"] = False
+    d["prediction_method"] = "cv"
+    cfg = SimulationConfig(**d)
+    validate_config(cfg)
+    sim = IntegratedSimulator(cfg)
+    n_frames = int(cfg.total_time / cfg.dt) + 200
+    t = np.arange(n_frames)[:, None, None] * cfg.dt
+    sim.pedestrian_sim = ReplayPedestrianSource(peds[None, :, 0:2] + peds[None, :, 2:4] * t, dt=cfg.dt)
+    sim.warmup()
+    for _ in range(n_steps):
+        sim.step()
+    sim.termination_reason = "timeout"
+    out = tempfile.mkdtemp()
+    sim.save_results(out)
+    z = np.load(os.path.join(out, "trajectory.npz"), allow_pickle=True)
+    store = {"keys": np.array(sorted(z.files))}
+    for key in z.files:
+        a = z[key]
+        if a.dtype == object:
+            rows = [np.asarray(r, dtype=float) for r in a]
+            if key == "predicted_trajectories":
+                rows = rows[:n_pred]
+            store[key + "/shape"] = np.array([r.shape + (0,) * (3 - r.ndim) for r in rows])
+            flat = [r.reshape(-1) for r in rows]
+            pad = np.full((len(flat), max(len(r) for r in flat)), np.nan)
+            for i, r in enumerate(flat):
+                pad[i, :len(r)] = r
+            store[key] = pad
+        elif a.dtype.kind in "US":
+            store[key] = a.astype("U16")
+        else:
+            store[key] = a
+    np.savez_compressed(os.path.join(HERE, "rollout_s01_trajectory.npz"), **store)
+    print("wrote rollout_s01_trajectory.npz", os.path.getsize(os.path.join(HERE, "rollout_s01_trajectory.npz")) // 1024, "KiB",
+          {k: (z[k].shape, str(z[k].dtype)) for k in z.files})
+
+
 def record(scenario, out_name, seeds, footprint=False):
     store = {}
     for k, seed in enumerate(seeds):
@@ -135,6 +186,8 @@ def main():
     which = sys.argv[1:] or ["s01"]
     if "s02" in which:
         record("scenario_02_cv", "rollout_s02.npz", (0, 1))
+    if "trajfile" in which:
+        record_trajectory_file()
     if "s02fp" in which:          # the same corridor with the three-circle footprint of the 4.5 m x 2.0 m vehicle
         record("scenario_02_cv", "rollout_s02fp.npz", (0, 2), footprint=True)
     if "s03" in which:

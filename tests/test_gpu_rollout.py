@@ -70,3 +70,45 @@ def test_single_rollout_equals_its_row_in_the_batch(golden):
     assert n == int(batch["steps"][1])
     np.testing.assert_array_equal(alone["ego"][0, :n], batch["ego"][1, :n])
     np.testing.assert_array_equal(alone["fsm"][0, :n], batch["fsm"][1, :n])
+
+
+def test_result_file_matches_the_reference_writer(tmp_path):
+    """trajectory.npz as IntegratedSimulator.save_results writes it (integrated_simulator.py:906-985): 80 steps of
+    scenario_01_cv through the reference and its own writer are the golden file; the batched driver's writer must
+    produce the same keys, dtypes and shapes and the same values (wall-clock timing columns aside)."""
+    g = np.load(os.path.join(HERE, "golden", "rollout_s01_trajectory.npz"))
+    knobs, runs, _ = _load("rollout_s01.npz")
+    from integrated_path_planning_b200.rollout import BatchedClosedLoop
+    sim = BatchedClosedLoop(runs[0]["wx"], runs[0]["wy"], knobs, runs[0]["traj"][None], runs[0]["ego0"][None], record=True)
+    sim.warmup()
+    n = len(g["times"])
+    for _ in range(n):
+        sim.step()
+    z = np.load(sim.save_results(0, str(tmp_path)), allow_pickle=True)
+    assert sorted(z.files) == g["keys"].tolist()
+    for key in z.files:
+        got = z[key]
+        if key in ("proc_prediction", "proc_planning"):
+            assert got.shape == (n,)
+            continue
+        if key == "ego_state":
+            assert got.dtype.kind == "U" and got.tolist() == g[key].tolist()
+            continue
+        if got.dtype != object:
+            assert got.shape == g[key].shape and got.dtype == g[key].dtype, key
+            fin = np.isfinite(g[key])
+            assert np.array_equal(np.isfinite(got), fin), key
+            np.testing.assert_allclose(got[fin], g[key][fin], rtol=1e-9, atol=EGO_TOL, err_msg=key)
+            continue
+        # np.array(list_of_equal_arrays, dtype=object) keeps the full shape, ragged rows give a 1-D object array --
+        # as recorded by tests/golden/make_golden_rollout.py from the reference's file
+        top = {"ped_positions": (n, 14, 2), "ped_velocities": (n, 14, 2), "ped_goals": (n, 14, 2),
+               "predicted_trajectories": (n, 14, 50, 2)}.get(key, (n,))
+        assert got.shape == top, (key, got.shape)
+        rows = [np.asarray(r, dtype=float) for r in got]
+        shapes, want = g[key + "/shape"], g[key]
+        for i in range(len(want)):                      # (predictions: the golden file keeps the first few steps)
+            shape = tuple(int(v) for v in shapes[i][:rows[i].ndim])
+            assert rows[i].shape == shape, (key, i, rows[i].shape, shape)
+            np.testing.assert_allclose(rows[i].reshape(-1), want[i][:rows[i].size], rtol=1e-9, atol=EGO_TOL, err_msg=f"{key}[{i}]")
+        assert len(rows) == n
