@@ -176,8 +176,8 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
 extern "C" int fot_destroy(fot_handle_t* h) {
   if (!h) return FOT_OK;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
-  for (Buf* b : {&h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->dyn_box, &h->cost_tab, &h->stage_h, &h->stage_d, &h->out_d,
+  cudaDeviceSynchronize();          // every stream of the handle (compute, priority, copy) is idle before its buffers go
+  for (Buf* b : {&h->gate_d, &h->gate_h, &h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->dyn_box, &h->cost_tab, &h->stage_h, &h->stage_d, &h->out_d,
                  &h->dyn_d, &h->stat_d})
     b->release();
   if (h->tables_dev) cudaFree(h->tables_dev);
