@@ -168,6 +168,7 @@ class SweepEngine:
         self.T, self.d_grid, self.Tb = self._keep["T"], self._keep["d_grid"], self._keep["Tb"]
         self.n_steps, self.n_steps_b, self.n_total = self._keep["n_steps"], self._keep["n_steps_b"], n_total
         self._pinned = {}
+        self._grid_cache = None
         self._h = C.c_void_p()
         _lib.check(self.lib.fot_create(C.byref(cfg), C.byref(tb), self.device, C.byref(self._h)), "fot_create")
         self.n_t_max = self.lib.fot_n_t_max(self._h)
@@ -204,7 +205,13 @@ class SweepEngine:
         target = f64c(np.broadcast_to(np.asarray(target_speed, dtype=np.float64), (n_q,)))
         limits = f64c(np.broadcast_to(np.asarray(limits, dtype=np.float64), (n_q, 4)))
         stop = f64c(np.full(n_q, np.nan) if stop_dist is None else np.broadcast_to(np.asarray(stop_dist, dtype=np.float64), (n_q,)))
-        v_grid, n_v = speed_grid_batch(target, self.d_t_s)
+        # one target speed for the whole batch (the usual case): the grid of the previous call with the same target
+        key = (float(target_speed), n_q) if np.ndim(target_speed) == 0 else None
+        if key is not None and self._grid_cache is not None and self._grid_cache[0] == key:
+            v_grid, n_v = self._grid_cache[1]
+        else:
+            v_grid, n_v = speed_grid_batch(target, self.d_t_s)
+            self._grid_cache = (key, (v_grid, n_v)) if key is not None else None
         b = _lib.FotBatch()
         b.n_q, b.n_v_max = n_q, v_grid.shape[1]
         b.frenet, b.target_speed, b.limits, b.stop_dist = _ptr(frenet), _ptr(target), _ptr(limits), _ptr(stop)
