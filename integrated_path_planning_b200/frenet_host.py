@@ -7,6 +7,7 @@ every candidate polynomial, so they follow the reference's arithmetic literally.
 """
 from __future__ import annotations
 
+import bisect
 import math
 from typing import Optional, Tuple
 
@@ -41,6 +42,8 @@ class CoordinateConverter:
             from .spline import spline_tables
             t = spline_tables(reference_path)
             self._tab = tuple(t[k] for k in ("knots", "xa", "xb", "xc", "xd", "ya", "yb", "yc", "yd"))
+            self._knots_list = [float(v) for v in self._tab[0]]
+            self._seg_cols = {}
         except Exception:
             self._tab = None
 
@@ -70,6 +73,28 @@ class CoordinateConverter:
             px = np.where(inside, px, np.nan)
             py = np.where(inside, py, np.nan)
         return px, py
+
+    def _xy3(self, s_lo, s_hi, s_mid):
+        """Positions of the three points of one refinement step.  They almost always share a spline segment; then
+        the segment search is done once on Python floats and x and y are evaluated together as one [2, 3] array
+        expression with the segment's coefficients as [2, 1] columns -- the same element-wise NumPy operations
+        (subtract, power, multiply, add, in the same order) as `_xy_many`, a third of the calls."""
+        tab = self._tab
+        if tab is not None and self._batched:
+            knots = self._knots_list
+            lo, hi = min(s_lo, s_hi, s_mid), max(s_lo, s_hi, s_mid)
+            if knots[0] <= lo and hi <= knots[-1]:
+                i = min(max(bisect.bisect_right(knots, lo) - 1, 0), len(knots) - 2)      # searchsorted(side="right") - 1, clipped
+                if min(max(bisect.bisect_right(knots, hi) - 1, 0), len(knots) - 2) == i:
+                    col = self._seg_cols.get(i)
+                    if col is None:
+                        _, xa, xb, xc, xd, ya, yb, yc, yd = tab
+                        col = self._seg_cols[i] = tuple(np.array([[u[i]], [v[i]]]) for u, v in ((xa, ya), (xb, yb), (xc, yc), (xd, yd)))
+                    a, b, c, d = col
+                    dx = np.array([s_lo, s_hi, s_mid], dtype=np.float64) - tab[0][i]
+                    p = a + b * dx + c * dx ** 2.0 + d * dx ** 3.0
+                    return p[0], p[1]
+        return self._xy_many([s_lo, s_hi, s_mid])
 
     def _heading_curvature(self, rs):
         """yaw, curvature, curvature rate at rs: CubicSpline2D.calc_yaw / calc_curvature /
@@ -132,7 +157,7 @@ class CoordinateConverter:
         for _ in range(20):
             s_lo = max(0, best_s - step)
             s_hi = min(path_end, best_s + step)
-            px3, py3 = self._xy_many([s_lo, s_hi, best_s])
+            px3, py3 = self._xy3(s_lo, s_hi, best_s)
             gap_lo = math.hypot(x - px3[0], y - py3[0])
             gap_hi = math.hypot(x - px3[1], y - py3[1])
             gap_c = math.hypot(x - px3[2], y - py3[2])

@@ -100,3 +100,27 @@ def test_near_tie_rows_use_the_reference_arithmetic():
     want = scalar.find_nearest_point_on_path(x, y)[0]
     got = batch.nearest_s([0], [x], [y])[0]
     assert got == want
+
+
+def test_lean_three_point_evaluator_is_the_reference_point_by_point():
+    """The refinement steps evaluate their three points through one [2, 3] array expression; a converter that calls
+    the path's calc_position once per point, as the reference does (coordinate_converter.py:253-280), must see
+    exactly the same nearest points, Frenet states and caches -- straight path, curved path, segment borders."""
+    for path, seed in ((_path(), 5), (_curved_path(), 6)):
+        rng = np.random.default_rng(seed)
+        ego = _walks(path, 6, 80, rng)
+        knots = np.asarray(path.s if not hasattr(path, "sx") else path.sx.x)
+        for i in range(6):
+            lean, literal = CoordinateConverter(path), CoordinateConverter(path)
+            literal._batched = False
+            for t in range(80):
+                e = ego[t, i].copy()
+                if t % 9 == 0:                                 # park the ego next to a knot: the three points straddle segments
+                    kx, ky = path.calc_position(float(knots[1 + (t // 9) % (len(knots) - 2)]))
+                    e[0], e[1] = float(np.asarray(kx).reshape(-1)[0]), float(np.asarray(ky).reshape(-1)[0]) + 0.4
+                a = ego_to_frenet(lean, EgoVehicleState(*e), 0.01)
+                b = ego_to_frenet(literal, EgoVehicleState(*e), 0.01)
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert np.array_equal(a, b), (i, t, a - b)
+                assert lean._prev_s == literal._prev_s
