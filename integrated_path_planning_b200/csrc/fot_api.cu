@@ -684,7 +684,7 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     uint32_t* words = (uint32_t*)h->gate_h.p;
     int n_cs = 1;
     if (const char* env = getenv("FOT_GATE_COPY_STREAMS")) n_cs = atoi(env) >= 2 ? 2 : 1;
-    bool flag_stream = n_cs == 1;
+    bool flag_stream = false;
     if (const char* env = getenv("FOT_GATE_FLAG_STREAM")) flag_stream = atoi(env) != 0 && n_cs == 1;
     CK(cudaStreamWaitEvent(h->copy_stream2, h->ev_blob, 0));      // nothing of this call before the previous call's flags are history
     for (int u = 0; u < n_up; ++u) {
@@ -695,9 +695,11 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
       const char* src = (const char*)b->dyn + (size_t)q0 * dyn_q_bytes;
       CK(cudaMemcpyAsync(dst, src, (size_t)cq * dyn_q_bytes, cudaMemcpyHostToDevice, cs));
       words[u] = gate.epoch;
-      // The flag is written by a second stream behind an event of the slice, so that the upload stream carries
-      // nothing but copies and event records: a stream write (or a 4-byte copy) between two slices costs the
-      // upload ~15 us of DMA idle time each (uploads done at 3.3 ms instead of 3.1).  FOT_GATE_FLAG_STREAM=0: in line.
+      // FOT_GATE_FLAG_STREAM=1: the flag is written by a second stream behind an event of the slice, so that the
+      // upload stream carries nothing but copies and event records (a stream write between two slices costs the
+      // upload ~15 us of DMA idle time: uploads done at 3.3 ms instead of 3.1).  Faster in isolation (3.75 against
+      // 3.86 ms per call), no better inside bench.py, and it depends on the two streams not sharing a hardware
+      // queue; the default keeps the flag in line, where its order behind the slice needs nothing else.
       cudaStream_t fs = cs;
       if (flag_stream) {
         CK(cudaEventRecord(h->ev_slice[u], cs));
