@@ -27,7 +27,8 @@
 extern "C" {
 #endif
 
-#define FOT_ABI_VERSION 3   /* 2: + prediction post-processing and safety metrics; 3: + fot_plan_batch_device_to_host */
+#define FOT_ABI_VERSION 4   /* 2: + prediction post-processing and safety metrics; 3: + fot_plan_batch_device_to_host;
+                               4: + fot_result_t.winner_samples, fot_fetch_winners, fot_reload_options */
 #define FOT_MAX_CIRCLES 8
 #define FOT_N_STATS 8    /* ok, max_speed, max_accel, max_curvature, max_lat_accel, road_bound, collision, stop_distance */
 #define FOT_N_SERIES 15  /* t s s_d s_dd s_ddd d d_d d_dd d_ddd x y yaw c v a  (data_structures.py:149-181) */
@@ -118,9 +119,19 @@ typedef struct fot_result {
   uint8_t* cand_cat;    /* [n_q][cand_stride] or NULL */
   double*  cand_cost;   /* [n_q][cand_stride] or NULL */
   int32_t  cand_stride;
-  int32_t  reserved;
+  int32_t  winner_samples; /* host-result entry points only: 0 = every series in full (row length n_t_max); k > 0 = only the
+                              first min(k, n_t_max) samples of each series are copied back and `winner` is
+                              [n_q][FOT_N_SERIES][k].  A closed-loop caller consumes sample 1 of the winner and nothing
+                              else (integrated_simulator.py:660-667: get_state_at_index(1), c[1]); k = 2 cuts the
+                              read-back from 6.1 KB to 240 B per query.  The full series of the last call stay on the
+                              device: fot_fetch_winners.  Must be 0 for fot_plan_batch_device. */
 } fot_result_t;
 
+/* A handle owns one device's planner tables, streams and scratch buffers.  ONE fot_plan_batch_* call may be in flight per
+ * handle: the calls share the handle's scratch (arg-min partials, cost tables, trajectory boxes) and timing events, so
+ * launches on one handle must be stream-ordered with each other -- an asynchronous fot_plan_batch_device launch has to
+ * be followed on the same stream, or synchronised, before the next call on that handle.  Use one handle per concurrent
+ * caller (handles are cheap: < 1 MB plus scratch that grows with the batch). */
 typedef struct fot_handle fot_handle_t;
 
 /* ABI version of the loaded library. */
@@ -159,8 +170,19 @@ int fot_plan_batch_device_to_host(fot_handle_t* h, const fot_batch_t* batch, con
  * result arrays make those copies true asynchronous DMAs; pageable memory works but serialises. */
 int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* batch, const fot_result_t* res);
 
-/* Device-side time of the kernels of the last fot_plan_batch_* call on this handle, in ms
- * (CUDA events on the launching stream); negative if unavailable. */
+/* Full winner series of queries [q0, q0 + n) of the LAST fot_plan_batch_host / _device_to_host call on this handle,
+ * from the device-resident result block into out[n][FOT_N_SERIES][n_t_max] (HOST pointer).  For callers that asked for
+ * winner_samples > 0 and need the whole trajectory of a few queries after all (logging, plotting). */
+int fot_fetch_winners(fot_handle_t* h, int q0, int n, double* out);
+
+/* The FOT_* tuning environment variables (chunking / gating of the host-pointer call, kernel choice, queue capacity;
+ * listed in csrc/fot_api.cu `struct Options`) are resolved ONCE, in fot_create; no planning call reads the environment.
+ * This re-reads them for handle `h` (NULL: every live handle of the process): the tests and tuning scripts switch
+ * variants on a live handle with it. */
+int fot_reload_options(fot_handle_t* h);
+
+/* Device-side time of the kernels of the last fot_plan_batch_* call on this handle, in ms (CUDA events; for a call that
+ * was cut into chunks / ranges: from the first chunk's start to the last kernel of any chunk); negative if unavailable. */
 float fot_last_kernel_ms(const fot_handle_t* h);
 
 /* Device time of the three stages of the `back`-th most recent launch on this handle (0 = the

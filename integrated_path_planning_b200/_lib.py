@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfot.so")
 
-FOT_ABI_VERSION = 3
+FOT_ABI_VERSION = 4
 FOT_MAX_CIRCLES = 8
 FOT_N_STATS = 8
 FOT_N_SERIES = 15
@@ -63,7 +63,7 @@ class FotResult(C.Structure):
         ("best_idx", C.c_void_p), ("best_cost", C.c_void_p), ("stats", C.c_void_p),
         ("winner_len", C.c_void_p), ("winner", C.c_void_p),
         ("cand_cat", C.c_void_p), ("cand_cost", C.c_void_p),
-        ("cand_stride", C.c_int32), ("reserved", C.c_int32),
+        ("cand_stride", C.c_int32), ("winner_samples", C.c_int32),
     ]
 
 
@@ -78,6 +78,8 @@ SYMBOLS = (
     ("fot_plan_batch_device", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult), C.c_void_p)),
     ("fot_plan_batch_host", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult))),
     ("fot_plan_batch_device_to_host", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult), C.c_void_p)),
+    ("fot_fetch_winners", C.c_int, (C.c_void_p, C.c_int, C.c_int, C.c_void_p)),
+    ("fot_reload_options", C.c_int, (C.c_void_p,)),
     ("fot_last_kernel_ms", C.c_float, (C.c_void_p,)),
     ("fot_launch_stage_ms", C.c_int, (C.c_void_p, C.c_int, C.POINTER(C.c_float * 3))),
     ("fot_probe_fma_tflops", C.c_int, (C.c_int, C.c_int, c_double_p)),

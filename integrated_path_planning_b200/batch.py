@@ -27,10 +27,11 @@ class BatchFrenetPlanner(FrenetPlanner):
 
     def plan_batch(self, frenet_states, target_speed, dynamic_obstacles=None, distribution=None,
                    static_obstacles=None, constraint_overrides=None, limits=None, max_stop_distance=None,
-                   want_candidates: bool = False) -> SweepResult:
+                   want_candidates: bool = False, winner_samples: int = 0) -> SweepResult:
         """frenet_states [n_q,6]; target_speed scalar or [n_q]; dynamic_obstacles [n_q,P,T,2] or
         distribution [n_q,S,P,T,2]; static_obstacles [M,2] (shared) or [n_q,M,2]; limits [n_q,4]
-        overrides constraint_overrides; max_stop_distance scalar / [n_q] (NaN = none)."""
+        overrides constraint_overrides; max_stop_distance scalar / [n_q] (NaN = none); winner_samples = k > 0
+        reads back only the first k samples of each winner series (`engine.fetch_winners` for the rest)."""
         fs = np.asarray(frenet_states, dtype=np.float64).reshape(-1, 6)
         n_q = fs.shape[0]
         if limits is None:
@@ -43,7 +44,8 @@ class BatchFrenetPlanner(FrenetPlanner):
             mode, dyn = _lib.FOT_DYN_SINGLE, d.reshape(n_q, 1, *d.shape[1:])
         per_query = static_obstacles is not None and np.ndim(static_obstacles) == 3
         return self.engine.run_host(fs, target_speed, limits, max_stop_distance, static_obstacles, dyn, mode,
-                                    static_per_query=per_query, want_candidates=want_candidates)
+                                    static_per_query=per_query, want_candidates=want_candidates,
+                                    winner_samples=winner_samples)
 
 
 class DeviceBatch:
@@ -83,21 +85,24 @@ class DeviceBatch:
             self.t["dyn"] = dyn.contiguous()
             b.dyn, b.S, b.P, b.T_obs, b.dyn_mode = self.t["dyn"].data_ptr(), dyn.shape[1], dyn.shape[2], dyn.shape[3], dyn_mode
         self.batch = b
-        self.out = {
-            "best_idx": torch.empty(n_q, dtype=torch.int32, device=dev),
-            "best_cost": torch.empty(n_q, dtype=torch.float64, device=dev),
-            "stats": torch.empty(n_q, _lib.FOT_N_STATS, dtype=torch.int32, device=dev),
-            "winner_len": torch.empty(n_q, dtype=torch.int32, device=dev),
-            "winner": torch.empty(n_q, _lib.FOT_N_SERIES, eng.n_t_max, dtype=torch.float64, device=dev),
-        }
+        # the whole winner block in one contiguous buffer (what the sharded sweep gathers with one collective)
+        self.block = WinnerBlock(n_q, eng.n_t_max, device=dev)
+        self.out = self.block.views
         r = _lib.FotResult()
         r.best_idx, r.best_cost, r.stats = self.out["best_idx"].data_ptr(), self.out["best_cost"].data_ptr(), self.out["stats"].data_ptr()
         r.winner_len, r.winner = self.out["winner_len"].data_ptr(), self.out["winner"].data_ptr()
         self.result = r
 
     def launch(self, stream: Optional[int] = None) -> None:
-        """Enqueue prepass + sweep + winner kernels on `stream` (raw cudaStream_t; None = the
-        handle's stream, synchronised before returning)."""
+        """Enqueue prepass + sweep + winner kernels on `stream` (raw cudaStream_t).  None: torch's current stream
+        of the batch's device -- ordered behind whatever torch work produced the input tensors -- synchronised
+        before returning."""
+        if stream is None:
+            import torch
+            cur = torch.cuda.current_stream(self.out["best_idx"].device)
+            self.engine.run_device(self.batch, self.result, cur.cuda_stream or None)
+            cur.synchronize()
+            return
         self.engine.run_device(self.batch, self.result, stream)
 
     def launch_to_host(self, host_out: dict, stream: Optional[int] = None) -> None:
@@ -122,18 +127,79 @@ class DeviceBatch:
         return int(pts.sum()) * n_circ * int(per_point)
 
 
-def gather_winners(out: dict, group=None) -> dict:
-    """The one collective of the sharded sweep: all_gather of each rank's winner block
-    (best_idx, best_cost, stats, winner_len, winner) over the default process group
-    (NCCL on GPUs, gloo in the CPU tests)."""
+class WinnerBlock:
+    """A rank's winner block for `cap` queries in ONE contiguous buffer: best_idx | winner_len | stats | best_cost |
+    winner, each section 256-byte aligned (what `gather_winners` moves with one collective, SURVEY.md section 8e:
+    about 6.2 KB per query).  `views[key]` are typed tensors into the buffer; the kernels write straight into them."""
+
+    def __init__(self, cap: int, n_t_max: int, device=None, sections=None):
+        import torch
+        self.cap = int(cap)
+        self.sections = sections or (("best_idx", torch.int32, ()), ("winner_len", torch.int32, ()),
+                                     ("stats", torch.int32, (_lib.FOT_N_STATS,)), ("best_cost", torch.float64, ()),
+                                     ("winner", torch.float64, (_lib.FOT_N_SERIES, int(n_t_max))))
+        self.offsets, off = {}, 0
+        for key, dt, shape in self.sections:
+            n = self.cap * int(np.prod(shape, dtype=np.int64)) * torch.empty((), dtype=dt).element_size()
+            self.offsets[key] = (off, n)
+            off = (off + n + 255) // 256 * 256
+        self.nbytes = max(off, 256)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.views = self.unpack(self.buf)
+
+    def unpack(self, buf):
+        """Typed views of a buffer laid out like this block (leading dims of `buf` are kept: [world, nbytes] ->
+        [world, cap, ...])."""
+        lead = tuple(buf.shape[:-1])
+        out = {}
+        for key, dt, shape in self.sections:
+            off, n = self.offsets[key]
+            out[key] = buf[..., off:off + n].contiguous().view(dt).reshape(lead + (self.cap,) + tuple(shape)) if lead \
+                else buf[off:off + n].view(dt).reshape((self.cap,) + tuple(shape))
+        return out
+
+
+def gather_winners(out: dict, group=None, counts=None) -> dict:
+    """The one collective of the sharded sweep: every rank's winner block (best_idx, best_cost, stats, winner_len,
+    winner -- any dict of tensors with the queries on dim 0) packed into ONE contiguous buffer and moved by ONE
+    `all_gather_into_tensor` over the process group (NCCL on GPUs, gloo in the CPU tests); returns the blocks of all
+    ranks concatenated in rank order.
+
+    Ranks may hold different numbers of queries (`shard_bounds` gives the last rank a shorter or empty block): every
+    block is padded to the longest one and the padding is trimmed after the gather.  `counts` = queries per rank when
+    the caller knows them (e.g. from `shard_bounds`); otherwise they are exchanged first (one extra, 8-byte
+    collective).  A `WinnerBlock`'s views are gathered without the packing copy when its capacity already equals the
+    longest block."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return out
     world = dist.get_world_size(group)
-    gathered = {}
-    for key, t in out.items():
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t.contiguous(), group=group)
-        gathered[key] = torch.cat(parts, dim=0)
-    return gathered
+    first = next(iter(out.values()))
+    n_local, dev = int(first.shape[0]), first.device
+    if counts is None:
+        mine = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        allc = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        counts = [int(c) for c in allc.cpu()]
+    counts = [int(c) for c in counts]
+    assert len(counts) == world and counts[dist.get_rank(group)] == n_local, (counts, n_local)
+    per = max(counts)
+    sections = tuple((k, t.dtype, tuple(t.shape[1:])) for k, t in out.items())
+    blk = WinnerBlock(per, 0, device=dev, sections=sections)
+    own = getattr(first, "_base", None)
+    zero_copy = per == n_local and own is not None and own.dtype == torch.uint8 and own.numel() == blk.nbytes and \
+        all(t._base is own and t.data_ptr() == own.data_ptr() + blk.offsets[k][0] for k, t in out.items())
+    if zero_copy:
+        send = own
+    else:
+        send = blk.buf
+        send.zero_()
+        for k, t in out.items():
+            blk.views[k][:n_local].copy_(t)
+    gathered = torch.empty((world, blk.nbytes), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered.view(-1), send, group=group)
+    parts = blk.unpack(gathered)
+    if all(c == per for c in counts):
+        return {k: v.reshape((world * per,) + tuple(v.shape[2:])) for k, v in parts.items()}
+    return {k: torch.cat([v[r, :counts[r]] for r in range(world)], dim=0) for k, v in parts.items()}

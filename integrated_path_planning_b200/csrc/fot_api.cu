@@ -8,6 +8,8 @@
 #include <string>
 #include <chrono>
 #include <vector>
+#include <mutex>
+#include <set>
 
 #include "fot_kernels.cuh"
 #include "fot_sweep_items.cuh"
@@ -56,9 +58,55 @@ struct Buf {
   }
 };
 
+// Tuning / test knobs (FOT_* environment variables).  They are resolved ONCE, when the handle is created -- no entry
+// point reads the environment on the planning path -- and again only on an explicit fot_reload_options() (the tests
+// and tuning scripts switch variants on a live handle that way).  Defaults are the product behaviour.
+struct Options {
+  int item_threads = 0;        // FOT_ITEM_THREADS   0: kItemThreads
+  int bpc = 0;                 // FOT_BPC            blocks per CTA (0: rule of item_geometry)
+  int qcap = 1024;             // FOT_QCAP           collision queue entries (tests force the queue-full path)
+  int fused_box = 0;           // FOT_FUSED_BOX      1: trajectory boxes in the sweep even for a resident tensor
+  int stage_dyn = 1;           // FOT_STAGE_DYN      0: never stage the obstacle block in shared memory
+  int sweep = 0;               // FOT_SWEEP          0 auto, 1 "items" (fail if unsupported), 2 "generic" (candidate-major kernel)
+  int host_chunks = 0;         // FOT_HOST_CHUNKS    equal chunks of the host-pointer call (0: rule)
+  std::string chunk_waves;     // FOT_CHUNK_WAVES    chunk sizes in sweep waves, "1,2,3" (+ the rest)
+  int host_streams = 2;        // FOT_HOST_STREAMS   1: chunks on one compute stream
+  int gated = 1;               // FOT_GATED          0: chunked launches instead of gated ones
+  int gate_uploads = 16;       // FOT_GATE_UPLOADS   upload slices of a gated call
+  int gate_copy_streams = 1;   // FOT_GATE_COPY_STREAMS
+  int gate_flag_stream = 0;    // FOT_GATE_FLAG_STREAM  1: slice flags written by a second stream
+  int gate_tail_bpc = 0;       // FOT_GATE_TAIL_BPC  blocks per CTA of the last gated range
+  int gate_memcpy = 0;         // FOT_GATE_MEMCPY    1: flags by 4-byte copies instead of stream writes
+  int debug_timing = 0;        // FOT_DEBUG_TIMING   1: print the timeline of every host-pointer call
+  void resolve() {
+    *this = Options{};
+    auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    item_threads = geti("FOT_ITEM_THREADS", 0);
+    bpc = geti("FOT_BPC", 0);
+    qcap = std::max(1, std::min(1 << 15, geti("FOT_QCAP", 1024)));
+    fused_box = geti("FOT_FUSED_BOX", 0) != 0;
+    stage_dyn = geti("FOT_STAGE_DYN", 1) != 0;
+    if (const char* e = getenv("FOT_SWEEP")) sweep = !strcmp(e, "generic") ? 2 : !strcmp(e, "items") ? 1 : 0;
+    host_chunks = geti("FOT_HOST_CHUNKS", 0);
+    if (const char* e = getenv("FOT_CHUNK_WAVES")) chunk_waves = e;
+    host_streams = geti("FOT_HOST_STREAMS", 2);
+    gated = geti("FOT_GATED", 1) != 0;
+    gate_uploads = geti("FOT_GATE_UPLOADS", 16);
+    gate_copy_streams = geti("FOT_GATE_COPY_STREAMS", 1) >= 2 ? 2 : 1;
+    gate_flag_stream = geti("FOT_GATE_FLAG_STREAM", 0) != 0;
+    gate_tail_bpc = geti("FOT_GATE_TAIL_BPC", 0);
+    gate_memcpy = getenv("FOT_GATE_MEMCPY") != nullptr;
+    debug_timing = getenv("FOT_DEBUG_TIMING") != nullptr;
+  }
+};
+
+std::mutex g_live_mu;
+std::set<fot_handle*> g_live;     // handles alive in this process (fot_reload_options(NULL) walks them)
+
 }  // namespace
 
 struct fot_handle {
+  Options opt;
   int device = 0;
   Plan plan{};
   void* tables_dev = nullptr;
@@ -79,6 +127,8 @@ struct fot_handle {
   int sms = 148;                     // SM count of the device (block-per-CTA grouping, host chunk sizes)
   Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_box, cost_tab;   // device scratch
   int last_sweep_kind = 0;           // 1: fot_sweep_items, 2: fot_sweep (generic)
+  const double* last_winner_d = nullptr;   // full winner series of the last host-result call (device, in out_d)
+  int last_winner_nq = 0;
   Buf stage_h, stage_d, out_d, dyn_d, stat_d;   // host-API staging
   fot_handle() { stage_h.host = true; gate_h.host = true; }
 };
@@ -99,16 +149,19 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   CK(cudaSetDevice(device));
 
   fot_handle* h = new fot_handle();
+  // any failure below releases everything created so far (streams, events, tables) through fot_destroy
+  struct Guard { fot_handle* h; ~Guard() { if (h) fot_destroy(h); } } guard{h};
+  h->opt.resolve();
   h->device = device;
   h->plan.cfg = *cfg;
   const int nT = cfg->n_T, nB = cfg->n_B, nd = cfg->n_d, nx = cfg->nx;
   int n_t_max = nB > 0 ? cfg->n_total : 0;
   for (int j = 0; j < nT; ++j) {
-    if (tb->n_steps[j] < 1) { delete h; return fail(FOT_ERR_ARG, "fot_create: horizon shorter than 2 samples"); }
+    if (tb->n_steps[j] < 1) return fail(FOT_ERR_ARG, "fot_create: horizon shorter than 2 samples");
     n_t_max = std::max(n_t_max, tb->n_steps[j] + 1);
   }
   for (int j = 0; j < nB; ++j)
-    if (tb->n_steps_b[j] + 1 > cfg->n_total) { delete h; return fail(FOT_ERR_ARG, "fot_create: brake horizon longer than max_t"); }
+    if (tb->n_steps_b[j] + 1 > cfg->n_total) return fail(FOT_ERR_ARG, "fot_create: brake horizon longer than max_t");
   h->plan.n_t_max = n_t_max;
   h->plan.d_sorted = 1;
   h->plan.d_min = h->plan.d_max = tb->d_grid[0];
@@ -131,10 +184,10 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   if (nB) ints.insert(ints.end(), tb->n_steps_b, tb->n_steps_b + nB);
   const size_t dbytes = dbl.size() * sizeof(double), ibytes = ints.size() * sizeof(int32_t);
   cudaError_t e = cudaMalloc(&h->tables_dev, dbytes + ibytes);
-  if (e != cudaSuccess) { delete h; return fail(FOT_ERR_CUDA, "cudaMalloc(tables)", e); }
+  if (e != cudaSuccess) { h->tables_dev = nullptr; return fail(FOT_ERR_CUDA, "cudaMalloc(tables)", e); }
   e = cudaMemcpy(h->tables_dev, dbl.data(), dbytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy((char*)h->tables_dev + dbytes, ints.data(), ibytes, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { cudaFree(h->tables_dev); delete h; return fail(FOT_ERR_CUDA, "cudaMemcpy(tables)", e); }
+  if (e != cudaSuccess) return fail(FOT_ERR_CUDA, "cudaMemcpy(tables)", e);
   const double* D = (const double*)h->tables_dev;
   const int32_t* I = (const int32_t*)((char*)h->tables_dev + dbytes);
   Plan& P = h->plan;
@@ -171,12 +224,22 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   CK(cudaFuncSetAttribute(fot_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  { std::lock_guard<std::mutex> lk(g_live_mu); g_live.insert(h); }
+  guard.h = nullptr;
   *out = h;
+  return FOT_OK;
+}
+
+extern "C" int fot_reload_options(fot_handle_t* h) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  if (h) { if (!g_live.count(h)) return fail(FOT_ERR_ARG, "fot_reload_options: unknown handle"); h->opt.resolve(); return FOT_OK; }
+  for (fot_handle* x : g_live) x->opt.resolve();
   return FOT_OK;
 }
 
 extern "C" int fot_destroy(fot_handle_t* h) {
   if (!h) return FOT_OK;
+  { std::lock_guard<std::mutex> lk(g_live_mu); g_live.erase(h); }
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();          // every stream of the handle (compute, priority, copy) is idle before its buffers go
   for (Buf* b : {&h->gate_d, &h->gate_h, &h->obs_tm, &h->obs_max2, &h->stat_tm, &h->stat_max2, &h->part_cost, &h->part_idx, &h->dyn_box, &h->cost_tab, &h->stage_h, &h->stage_d, &h->out_d,
@@ -287,7 +350,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   if (NT > 128 || nd > 8192 || SPl > 32768 || b->n_static > 32768) return false;   // 128: one NumPy pairwise block
   const int SP = (int)SPl;
   int max_threads = kItemThreads;
-  if (const char* env = getenv("FOT_ITEM_THREADS")) max_threads = std::max(NT, std::min(kItemThreads, atoi(env)));
+  if (h->opt.item_threads > 0) max_threads = std::max(NT, std::min(kItemThreads, h->opt.item_threads));
   const int ppc_max = max_threads / NT;
   ItemGeom G{};
   G.chunks = (b->n_v_max + ppc_max - 1) / ppc_max;
@@ -304,7 +367,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
     long long bpc = total / ((long long)sms * 2 * 4);
     bpc = std::max<long long>(1, std::min<long long>(bpc, G.blocks_per_query));
     if (bpc_override > 0) bpc = std::max(1, std::min(bpc_override, (int)G.blocks_per_query));
-    if (const char* env = getenv("FOT_BPC")) bpc = std::max(1, std::min(atoi(env), (int)G.blocks_per_query));
+    if (h->opt.bpc > 0) bpc = std::max(1, std::min(h->opt.bpc, (int)G.blocks_per_query));
     G.ctas_per_query = (int)((G.blocks_per_query + bpc - 1) / bpc);
     G.bpc = (G.blocks_per_query + G.ctas_per_query - 1) / G.ctas_per_query;
   }
@@ -317,13 +380,11 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   G.vwords = max_viol > 0 ? (b->S + 31) / 32 : 0;
   G.lcap = std::max(1, SP + b->n_static);
   G.ochunk = G.lcap <= 256 ? G.lcap : 128;
-  G.qcap = 1024;
-  if (const char* env = getenv("FOT_QCAP")) G.qcap = std::max(1, std::min(1 << 15, atoi(env)));   // tests: force the queue-full path
+  G.qcap = h->opt.qcap;                   // (the tests shrink it to force the queue-full path)
   G.spline_smem = nx <= 128 ? 1 : 0;
   const size_t dyn_bytes = (size_t)SP * b->T_obs * 16;
-  // FOT_FUSED_BOX=1 (tests, tuning): trajectory boxes in the sweep even for a resident tensor
-  bool fuse = want_fused_box;
-  if (const char* env = getenv("FOT_FUSED_BOX")) fuse = fuse || atoi(env) != 0;
+  // option fused_box (tests, tuning): trajectory boxes in the sweep even for a resident tensor
+  const bool fuse = want_fused_box || h->opt.fused_box;
   auto layout = [&](bool stage) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
@@ -350,7 +411,7 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   };
   // stage the query's obstacle block in shared memory when two blocks per SM still fit
   bool stage = has_dyn && dyn_bytes > 0 && dyn_bytes <= 64 * 1024 && ((uintptr_t)b->dyn & 15) == 0;
-  if (const char* env = getenv("FOT_STAGE_DYN")) stage = stage && atoi(env) != 0;
+  stage = stage && h->opt.stage_dyn;
   size_t bytes = layout(stage);
   if (stage && bytes > 110 * 1024) { stage = false; bytes = layout(false); }
   if (bytes > (size_t)h->smem_optin) return false;
@@ -377,6 +438,7 @@ static int check_batch(const fot_handle* h, const fot_batch_t* b, const fot_resu
     return fail(FOT_ERR_ARG, "null result array");
   if ((r->cand_cat || r->cand_cost) && r->cand_stride < fot_candidate_count(h, b->n_v_max, 1))
     return fail(FOT_ERR_ARG, "cand_stride too small");
+  if (r->winner_samples < 0) return fail(FOT_ERR_ARG, "winner_samples must be >= 0");
   return FOT_OK;
 }
 
@@ -389,7 +451,6 @@ static StreamWrite32 stream_write32() {
   static StreamWrite32 fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qr{};
-    if (getenv("FOT_GATE_MEMCPY")) return (StreamWrite32) nullptr;
     if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
       p = nullptr;
     return (StreamWrite32)p;
@@ -404,18 +465,17 @@ struct Gate {
 };
 
 static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r, cudaStream_t st, size_t q_off = 0,
-                      size_t q_total = 0, Gate gate = Gate{}, int bpc_override = 0) {
+                      size_t q_total = 0, Gate gate = Gate{}, int bpc_override = 0, bool record_span = true) {
   if (q_total == 0) q_total = (size_t)b->n_q;
   // kernel choice: the sample-major fot_sweep_items unless the shape is outside its range (or
   // FOT_SWEEP=generic asks for the candidate-major kernel, which the tests use as a cross-check)
   ItemGeom ig{};
   size_t ismem = 0;
-  const char* force = getenv("FOT_SWEEP");            // read per launch: the tests switch kernels in-process
   bool use_items = item_geometry(h, b, &ig, &ismem, gate.word != nullptr, bpc_override);
-  if (force && !strcmp(force, "generic")) use_items = false;
+  if (h->opt.sweep == 2) use_items = false;
   if (gate.word && !(use_items && ig.fused_box)) return fail(FOT_ERR_ARG, "gated launch needs fot_sweep_items with a staged obstacle block");
   if (gate.word) { ig.gate = gate.word; ig.gate_epoch = gate.epoch; ig.gate_per = gate.per; ig.gate_q0 = (int32_t)q_off; }
-  if (force && !strcmp(force, "items") && !use_items) return fail(FOT_ERR_ARG, "FOT_SWEEP=items: shape not supported by fot_sweep_items");
+  if (h->opt.sweep == 1 && !use_items) return fail(FOT_ERR_ARG, "FOT_SWEEP=items: shape not supported by fot_sweep_items");
   SweepGeom g{};
   size_t smem = 0;
   if (!use_items) {
@@ -474,7 +534,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   O.part_cost = (double*)h->part_cost.p + q_off * part_stride; O.part_idx = (int32_t*)h->part_idx.p + q_off * part_stride;
 
   cudaEvent_t* ring = h->ring.data() + (size_t)(h->n_launch % fot_handle::kRing) * 4;
-  CK(cudaEventRecord(h->ev0, st));
+  if (record_span) CK(cudaEventRecord(h->ev0, st));
   {
     const size_t n_cat = r->cand_cat ? (size_t)b->n_q * r->cand_stride : 0;
     const size_t work = std::max<size_t>((size_t)b->n_q * FOT_N_STATS, n_cat);
@@ -516,7 +576,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   CK(cudaEventRecord(ring[2], st));
   fot_winner<<<b->n_q, 128, (size_t)kTT * h->plan.n_t_max * sizeof(double), st>>>(h->plan, B, O, g);
   CK(cudaEventRecord(ring[3], st));
-  CK(cudaEventRecord(h->ev1, st));
+  if (record_span) CK(cudaEventRecord(h->ev1, st));
   h->n_launch++;
   CK(cudaGetLastError());
   h->timed = true;
@@ -527,6 +587,7 @@ extern "C" int fot_plan_batch_device(fot_handle_t* h, const fot_batch_t* b, cons
   int rc = check_batch(h, b, r);
   if (rc != FOT_OK) return rc;
   CK(cudaSetDevice(h->device));
+  if (r->winner_samples != 0) return fail(FOT_ERR_ARG, "winner_samples applies to the host-result entry points only");
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   rc = launch_all(h, b, r, st);
   if (rc != FOT_OK) return rc;
@@ -534,15 +595,102 @@ extern "C" int fot_plan_batch_device(fot_handle_t* h, const fot_batch_t* b, cons
   return FOT_OK;
 }
 
+// First k samples of every winner series, packed [n][FOT_N_SERIES][k] (fot_result_t.winner_samples): a strided copy of
+// 16-byte rows is slow on the copy engines, a contiguous one is not.
+__global__ void fot_pack_heads(const double* __restrict__ winner, double* __restrict__ heads, long long n_rows, int NT, int k) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * k) return;
+  const long long row = i / k;
+  heads[i] = winner[row * NT + (i - row * k)];
+}
+
+// Read-back of one chunk's winner block into the caller's arrays on stream `ds` (after `st`'s kernels).
+static int read_back(fot_handle* h, const fot_result_t* r, const fot_result_t& dr, double* heads_d, int q0, int cq, int NT,
+                     cudaStream_t st, cudaStream_t ds, cudaEvent_t done) {
+  const int k = r->winner_samples > 0 ? std::min(r->winner_samples, NT) : 0;
+  if (k > 0) {
+    const long long n_rows = (long long)cq * FOT_N_SERIES;
+    fot_pack_heads<<<(unsigned)((n_rows * k + 255) / 256), 256, 0, st>>>(dr.winner, heads_d, n_rows, NT, k);
+  }
+  CK(cudaEventRecord(done, st));
+  CK(cudaStreamWaitEvent(ds, done, 0));
+  CK(cudaMemcpyAsync(r->best_idx + q0, dr.best_idx, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
+  CK(cudaMemcpyAsync(r->best_cost + q0, dr.best_cost, (size_t)cq * 8, cudaMemcpyDeviceToHost, ds));
+  CK(cudaMemcpyAsync(r->stats + (size_t)q0 * FOT_N_STATS, dr.stats, (size_t)cq * FOT_N_STATS * 4, cudaMemcpyDeviceToHost, ds));
+  CK(cudaMemcpyAsync(r->winner_len + q0, dr.winner_len, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
+  if (k > 0)
+    CK(cudaMemcpyAsync(r->winner + (size_t)q0 * FOT_N_SERIES * k, heads_d, (size_t)cq * FOT_N_SERIES * k * 8, cudaMemcpyDeviceToHost, ds));
+  else
+    CK(cudaMemcpyAsync(r->winner + (size_t)q0 * FOT_N_SERIES * NT, dr.winner, (size_t)cq * FOT_N_SERIES * NT * 8,
+                       cudaMemcpyDeviceToHost, ds));
+  if (r->cand_cat)
+    CK(cudaMemcpyAsync(r->cand_cat + (size_t)q0 * r->cand_stride, dr.cand_cat, (size_t)cq * r->cand_stride,
+                       cudaMemcpyDeviceToHost, ds));
+  if (r->cand_cost)
+    CK(cudaMemcpyAsync(r->cand_cost + (size_t)q0 * r->cand_stride, dr.cand_cost, (size_t)cq * r->cand_stride * 8,
+                       cudaMemcpyDeviceToHost, ds));
+  return FOT_OK;
+}
+
+// A failed multi-chunk call may leave earlier chunks in flight: kernels, upload slices and read-backs into the
+// CALLER's result arrays, and (gated mode) CTAs spinning on slice flags that will never be written.  Nothing of that
+// may still be running when the error is reported -- the caller is free to release its arrays, and the next call
+// reuses the handle's scratch and gate flags.  Releases the waiting CTAs (their results are discarded), waits for
+// every stream of the handle and clears the gate error word; keeps the error text of the failure.
+static void drain_after_failure(fot_handle* h) {
+  const std::string keep = g_err;
+  if (h->gate_d.p && h->gate_epoch) {
+    std::vector<uint32_t> w(kGateSlices, h->gate_epoch);
+    cudaMemcpy(h->gate_d.p, w.data(), kGateSlices * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  }
+  for (cudaStream_t s : {h->copy_stream, h->copy_stream2, h->stream, h->stream2, h->pstream[0], h->pstream[1], h->pstream[2],
+                         h->pstream[3], h->d2h_stream})
+    if (s) cudaStreamSynchronize(s);
+  if (h->gate_d.p) cudaMemset((uint32_t*)h->gate_d.p + kGateSlices, 0, sizeof(uint32_t));
+  cudaGetLastError();
+  g_err = keep;
+}
+
+// device-side span of a call that ran on several streams (fot_last_kernel_ms): `first` carries ev0; ev1 is recorded
+// on it after every other stream of the handle has been joined
+static int close_span(fot_handle* h, cudaStream_t first) {
+  for (cudaStream_t s : {h->stream, h->stream2, h->pstream[0], h->pstream[1], h->pstream[2], h->pstream[3]}) {
+    if (s == first) continue;
+    CK(cudaEventRecord(h->ev_join, s));
+    CK(cudaStreamWaitEvent(first, h->ev_join, 0));
+  }
+  CK(cudaEventRecord(h->ev1, first));
+  return FOT_OK;
+}
+
+static int plan_batch_host_impl(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r);
+static int plan_batch_device_to_host_impl(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r, void* stream);
+
+extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r) {
+  int rc = check_batch(h, b, r);
+  if (rc != FOT_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  rc = plan_batch_host_impl(h, b, r);
+  if (rc != FOT_OK) drain_after_failure(h);
+  return rc;
+}
+
+extern "C" int fot_plan_batch_device_to_host(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r, void* stream) {
+  int rc = check_batch(h, b, r);
+  if (rc != FOT_OK) return rc;
+  CK(cudaSetDevice(h->device));
+  rc = plan_batch_device_to_host_impl(h, b, r, stream);
+  if (rc != FOT_OK) drain_after_failure(h);
+  return rc;
+}
+
 // Host-pointer entry point.  Small per-query arrays go through one pinned blob; the obstacle tensor
 // is copied straight from the caller's memory (pinned memory makes that a true async DMA).  Large
 // batches are cut into chunks of queries: chunk c+1's obstacle upload runs on the copy stream while
 // chunk c's kernels run on the compute stream, and each chunk's winners go back as soon as its
 // kernels finish, directly into the caller's result arrays.
-extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r) {
-  int rc = check_batch(h, b, r);
-  if (rc != FOT_OK) return rc;
-  CK(cudaSetDevice(h->device));
+static int plan_batch_host_impl(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r) {
+  int rc = FOT_OK;
   cudaStream_t st = h->stream;
   const int nq = b->n_q, NT = h->plan.n_t_max;
   // ---- small per-query arrays: one pinned blob, one H2D -------------------------------
@@ -579,8 +727,12 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
                r_wl = rtake((size_t)nq * 4), r_w = rtake((size_t)nq * FOT_N_SERIES * NT * 8);
   const size_t r_cc = r->cand_cat ? rtake((size_t)nq * r->cand_stride) : 0;
   const size_t r_cs = r->cand_cost ? rtake((size_t)nq * r->cand_stride * 8) : 0;
+  const int k_head = r->winner_samples > 0 ? std::min(r->winner_samples, NT) : 0;
+  const size_t r_wh = k_head ? rtake((size_t)nq * FOT_N_SERIES * k_head * 8) : 0;
   CK(h->out_d.reserve(ro));
   char* od = (char*)h->out_d.p;
+  h->last_winner_d = (const double*)(od + r_w);     // fot_fetch_winners
+  h->last_winner_nq = nq;
 
   // chunking: only worth it when the obstacle upload is large.  The kernels are the longer leg of the
   // pipeline (the upload runs at PCIe speed), so the first chunks are small -- the sweep starts after
@@ -598,12 +750,13 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     n_chunks = 5;
     for (int c = 0; c < n_chunks; ++c) bounds[c + 1] = std::min(nq, std::max(cuts[c], bounds[c]));
   }
-  if (const char* env = getenv("FOT_HOST_CHUNKS")) {
-    n_chunks = std::max(1, std::min(kMaxChunks, atoi(env)));
+  if (h->opt.host_chunks > 0) {
+    n_chunks = std::max(1, std::min(kMaxChunks, h->opt.host_chunks));
     const int per_ = (nq + n_chunks - 1) / n_chunks;
     for (int c = 0; c <= n_chunks; ++c) bounds[c] = std::min(nq, c * per_);
   }
-  if (const char* env = getenv("FOT_CHUNK_WAVES")) {       // tuning: chunk sizes in sweep waves, "1,2,3,4,3" (+ the rest)
+  if (!h->opt.chunk_waves.empty()) {                       // tuning: chunk sizes in sweep waves, "1,2,3,4,3" (+ the rest)
+    const char* env = h->opt.chunk_waves.c_str();
     const int wave = 2 * h->sms;
     n_chunks = 0;
     int at = 0;
@@ -619,14 +772,13 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   // chunks alternate between two compute streams, so that the next chunk's CTAs fill the SMs the tail wave of
   // the previous chunk leaves idle (the chunks touch disjoint scratch, see launch_all)
   bool two_streams = n_chunks > 1;
-  if (const char* env = getenv("FOT_HOST_STREAMS")) two_streams = two_streams && atoi(env) >= 2;
+  two_streams = two_streams && h->opt.host_streams >= 2;
   if (two_streams) {
     ItemGeom ig{};
     size_t ismem = 0;
     fot_batch_t probe = *b;
     probe.n_q = bounds[1] - bounds[0];
-    const char* force = getenv("FOT_SWEEP");
-    if (!item_geometry(h, &probe, &ig, &ismem) || (force && !strcmp(force, "generic"))) two_streams = false;
+    if (!item_geometry(h, &probe, &ig, &ismem) || h->opt.sweep == 2) two_streams = false;
   }
   // Gated launches (large uploads through fot_sweep_items): the sweep does not wait for whole chunks.  The upload
   // is cut into fine slices, each followed by a 4-byte copy that publishes "queries uploaded so far"; the sweep
@@ -636,10 +788,7 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
   int n_up = 0, ub[kGateSlices + 1] = {0};
   Gate gate{};
   {
-    const char* env = getenv("FOT_GATED");
-    const char* force = getenv("FOT_SWEEP");
-    const bool want = env ? atoi(env) != 0 : true;
-    if (want && n_chunks > 1 && has_dyn && nq < (1 << 22) && !(force && !strcmp(force, "generic"))) {
+    if (h->opt.gated && n_chunks > 1 && has_dyn && nq < (1 << 22) && h->opt.sweep != 2) {
       ItemGeom ig{};
       size_t ismem = 0;
       gated = item_geometry(h, b, &ig, &ismem, true) && ig.fused_box;
@@ -653,15 +802,14 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     if (++h->gate_epoch == 0) h->gate_epoch = 1;             // 0 is the value of a fresh flag
     gate.word = (unsigned*)h->gate_d.p;
     gate.epoch = h->gate_epoch;
-    n_up = 16;
-    if (const char* env = getenv("FOT_GATE_UPLOADS")) n_up = std::max(1, std::min(kGateSlices, atoi(env)));
+    n_up = std::max(1, std::min(kGateSlices, h->opt.gate_uploads));
     gate.per = (nq + n_up - 1) / n_up;
     n_up = (nq + gate.per - 1) / gate.per;
     for (int u = 0; u <= n_up; ++u) ub[u] = std::min(nq, u * gate.per);
     // launch ranges: about 1/2, 5/16, 3/16 of the queries, in whole waves
     const int wave = 2 * h->sms;
     auto waves = [&](int frac16) { const int w = std::max(1, (int)((long long)nq * frac16 / 16 / wave)); return w * wave; };
-    if (!getenv("FOT_HOST_CHUNKS") && !getenv("FOT_CHUNK_WAVES")) {
+    if (h->opt.host_chunks <= 0 && h->opt.chunk_waves.empty()) {
       const int cuts[] = {waves(8), waves(13), nq};
       n_chunks = 3;
       for (int c = 0; c < n_chunks; ++c) bounds[c + 1] = std::min(nq, std::max(cuts[c], bounds[c]));
@@ -670,7 +818,7 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     two_streams = n_chunks > 1;
   }
   const auto t_wall0 = std::chrono::steady_clock::now();
-  static const bool dbg = getenv("FOT_DEBUG_TIMING") != nullptr;
+  const bool dbg = h->opt.debug_timing != 0;
   cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr, d3 = nullptr, d4 = nullptr;
   cudaEvent_t tl[kMaxChunks][4] = {};                    // debug timeline per chunk: upload done, kernels start / end, read-back done
   if (dbg) for (auto& row : tl) for (auto& ev : row) cudaEventCreate(&ev);
@@ -682,10 +830,8 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     // each slice is followed, in its stream, by the write of its flag (two alternating upload streams are a
     // tuning knob; measured slower than one)
     uint32_t* words = (uint32_t*)h->gate_h.p;
-    int n_cs = 1;
-    if (const char* env = getenv("FOT_GATE_COPY_STREAMS")) n_cs = atoi(env) >= 2 ? 2 : 1;
-    bool flag_stream = false;
-    if (const char* env = getenv("FOT_GATE_FLAG_STREAM")) flag_stream = atoi(env) != 0 && n_cs == 1;
+    const int n_cs = h->opt.gate_copy_streams;
+    const bool flag_stream = h->opt.gate_flag_stream && n_cs == 1;
     CK(cudaStreamWaitEvent(h->copy_stream2, h->ev_blob, 0));      // nothing of this call before the previous call's flags are history
     for (int u = 0; u < n_up; ++u) {
       const int q0 = ub[u], cq = ub[u + 1] - q0;
@@ -706,7 +852,7 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
         CK(cudaStreamWaitEvent(h->copy_stream2, h->ev_slice[u], 0));
         fs = h->copy_stream2;
       }
-      if (StreamWrite32 wr = stream_write32()) {
+      if (StreamWrite32 wr = h->opt.gate_memcpy ? nullptr : stream_write32()) {
         if (wr(fs, (unsigned long long)(uintptr_t)(gate.word + u), gate.epoch, 0u) != 0)
           return fail(FOT_ERR_CUDA, "cuStreamWriteValue32");
       } else {
@@ -731,6 +877,7 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     fprintf(stderr, "[fot] dyn pointer attr: err=%d type=%d (0 unregistered, 1 host, 2 device, 3 managed)\n", (int)pe, (int)pa.type);
   }
   int n_issued = 0;
+  cudaStream_t span_first = nullptr;
   for (int c = 0; c < n_chunks; ++c) {
     const int q0 = bounds[c], cq = bounds[c + 1] - q0;
     if (cq <= 0) continue;
@@ -740,6 +887,7 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     ++n_issued;
     if (has_dyn && !gated) CK(cudaStreamWaitEvent(st, h->ev_copy[c], 0));
     else CK(cudaStreamWaitEvent(st, h->ev_blob, 0));
+    if (!span_first) { span_first = st; CK(cudaEventRecord(h->ev0, st)); }
     if (dbg && c == 0) cudaEventRecord(d2, st);
     if (dbg) cudaEventRecord(tl[c][1], st);
     fot_batch_t db = *b;
@@ -764,28 +912,15 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     // (tuning knob: blocks per CTA of the last gated range; shorter CTAs there measured no better than the
     // rule of item_geometry)
     int tail_bpc = 0;
-    if (gated && bounds[c + 1] >= nq)
-      if (const char* env = getenv("FOT_GATE_TAIL_BPC")) tail_bpc = atoi(env);
-    rc = launch_all(h, &db, &dr, st, (size_t)q0, (size_t)nq, gate, tail_bpc);
+    if (gated && bounds[c + 1] >= nq) tail_bpc = h->opt.gate_tail_bpc;
+    rc = launch_all(h, &db, &dr, st, (size_t)q0, (size_t)nq, gate, tail_bpc, /*record_span=*/false);
     if (rc != FOT_OK) return rc;
     // winners of this chunk straight into the caller's arrays, on their own stream so the next
     // chunk's kernels never queue behind a copy engine that is busy with the uploads
     cudaStream_t ds = h->d2h_stream;
     if (dbg) cudaEventRecord(tl[c][2], st);
-    CK(cudaEventRecord(h->ev_done[c], st));
-    CK(cudaStreamWaitEvent(ds, h->ev_done[c], 0));
-    CK(cudaMemcpyAsync(r->best_idx + q0, dr.best_idx, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
-    CK(cudaMemcpyAsync(r->best_cost + q0, dr.best_cost, (size_t)cq * 8, cudaMemcpyDeviceToHost, ds));
-    CK(cudaMemcpyAsync(r->stats + (size_t)q0 * FOT_N_STATS, dr.stats, (size_t)cq * FOT_N_STATS * 4, cudaMemcpyDeviceToHost, ds));
-    CK(cudaMemcpyAsync(r->winner_len + q0, dr.winner_len, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
-    CK(cudaMemcpyAsync(r->winner + (size_t)q0 * FOT_N_SERIES * NT, dr.winner, (size_t)cq * FOT_N_SERIES * NT * 8,
-                       cudaMemcpyDeviceToHost, ds));
-    if (r->cand_cat)
-      CK(cudaMemcpyAsync(r->cand_cat + (size_t)q0 * r->cand_stride, dr.cand_cat, (size_t)cq * r->cand_stride,
-                         cudaMemcpyDeviceToHost, ds));
-    if (r->cand_cost)
-      CK(cudaMemcpyAsync(r->cand_cost + (size_t)q0 * r->cand_stride, dr.cand_cost, (size_t)cq * r->cand_stride * 8,
-                         cudaMemcpyDeviceToHost, ds));
+    rc = read_back(h, r, dr, (double*)(od + r_wh) + (size_t)q0 * FOT_N_SERIES * k_head, q0, cq, NT, st, ds, h->ev_done[c]);
+    if (rc != FOT_OK) return rc;
     if (dbg) cudaEventRecord(tl[c][3], ds);
   }
   if (dbg) {
@@ -793,6 +928,7 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
     for (auto ps : h->pstream) { cudaEventRecord(h->ev_join, ps); cudaStreamWaitEvent(st, h->ev_join, 0); }
     cudaEventRecord(d3, st);
   }
+  if (span_first) { rc = close_span(h, span_first); if (rc != FOT_OK) return rc; }
   CK(cudaStreamSynchronize(h->d2h_stream));   // the last read-backs wait for the last kernels of every compute stream
   CK(cudaStreamSynchronize(st));
   CK(cudaStreamSynchronize(h->stream2));
@@ -830,10 +966,8 @@ extern "C" int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* b, const 
 // ranges on the priority streams, and each range's winners go back over PCIe while the next range is swept, so
 // only the last range's read-back is exposed.  `stream` is the stream on which the inputs become ready (NULL:
 // they are ready now).  Returns when the results are in `res`.
-extern "C" int fot_plan_batch_device_to_host(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r, void* stream) {
-  int rc = check_batch(h, b, r);
-  if (rc != FOT_OK) return rc;
-  CK(cudaSetDevice(h->device));
+static int plan_batch_device_to_host_impl(fot_handle_t* h, const fot_batch_t* b, const fot_result_t* r, void* stream) {
+  int rc = FOT_OK;
   const int nq = b->n_q, NT = h->plan.n_t_max;
   size_t ro = 0;
   auto rtake = [&](size_t bytes) { size_t o = ro; ro = align_up(ro + bytes); return o; };
@@ -841,15 +975,18 @@ extern "C" int fot_plan_batch_device_to_host(fot_handle_t* h, const fot_batch_t*
                r_wl = rtake((size_t)nq * 4), r_w = rtake((size_t)nq * FOT_N_SERIES * NT * 8);
   const size_t r_cc = r->cand_cat ? rtake((size_t)nq * r->cand_stride) : 0;
   const size_t r_cs = r->cand_cost ? rtake((size_t)nq * r->cand_stride * 8) : 0;
+  const int k_head = r->winner_samples > 0 ? std::min(r->winner_samples, NT) : 0;
+  const size_t r_wh = k_head ? rtake((size_t)nq * FOT_N_SERIES * k_head * 8) : 0;
   CK(h->out_d.reserve(ro));
   char* od = (char*)h->out_d.p;
+  h->last_winner_d = (const double*)(od + r_w);     // fot_fetch_winners
+  h->last_winner_nq = nq;
   // ranges: about 1/2, 5/16, 3/16 of the queries in whole waves; one range for small batches or the fallback kernel
   int n_ranges = 1, bounds[4] = {0, nq, nq, nq};
   {
     ItemGeom ig{};
     size_t ismem = 0;
-    const char* force = getenv("FOT_SWEEP");
-    const bool items = item_geometry(h, b, &ig, &ismem) && !(force && !strcmp(force, "generic"));
+    const bool items = item_geometry(h, b, &ig, &ismem) && h->opt.sweep != 2;
     if (items && nq >= 1024) {
       const int wave = 2 * h->sms;
       auto waves = [&](int frac16) { const int w = std::max(1, (int)((long long)nq * frac16 / 16 / wave)); return w * wave; };
@@ -884,26 +1021,26 @@ extern "C" int fot_plan_batch_device_to_host(fot_handle_t* h, const fot_batch_t*
     dr.winner = (double*)(od + r_w) + (size_t)q0 * FOT_N_SERIES * NT;
     dr.cand_cat = r->cand_cat ? (uint8_t*)(od + r_cc) + (size_t)q0 * r->cand_stride : nullptr;
     dr.cand_cost = r->cand_cost ? (double*)(od + r_cs) + (size_t)q0 * r->cand_stride : nullptr;
-    rc = launch_all(h, &db, &dr, st, (size_t)q0, (size_t)nq);
+    if (c == 0) CK(cudaEventRecord(h->ev0, st));
+    rc = launch_all(h, &db, &dr, st, (size_t)q0, (size_t)nq, Gate{}, 0, /*record_span=*/false);
     if (rc != FOT_OK) return rc;
-    cudaStream_t ds = h->d2h_stream;
-    CK(cudaEventRecord(h->ev_done[c], st));
-    CK(cudaStreamWaitEvent(ds, h->ev_done[c], 0));
-    CK(cudaMemcpyAsync(r->best_idx + q0, dr.best_idx, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
-    CK(cudaMemcpyAsync(r->best_cost + q0, dr.best_cost, (size_t)cq * 8, cudaMemcpyDeviceToHost, ds));
-    CK(cudaMemcpyAsync(r->stats + (size_t)q0 * FOT_N_STATS, dr.stats, (size_t)cq * FOT_N_STATS * 4, cudaMemcpyDeviceToHost, ds));
-    CK(cudaMemcpyAsync(r->winner_len + q0, dr.winner_len, (size_t)cq * 4, cudaMemcpyDeviceToHost, ds));
-    CK(cudaMemcpyAsync(r->winner + (size_t)q0 * FOT_N_SERIES * NT, dr.winner, (size_t)cq * FOT_N_SERIES * NT * 8,
-                       cudaMemcpyDeviceToHost, ds));
-    if (r->cand_cat)
-      CK(cudaMemcpyAsync(r->cand_cat + (size_t)q0 * r->cand_stride, dr.cand_cat, (size_t)cq * r->cand_stride,
-                         cudaMemcpyDeviceToHost, ds));
-    if (r->cand_cost)
-      CK(cudaMemcpyAsync(r->cand_cost + (size_t)q0 * r->cand_stride, dr.cand_cost, (size_t)cq * r->cand_stride * 8,
-                         cudaMemcpyDeviceToHost, ds));
+    rc = read_back(h, r, dr, (double*)(od + r_wh) + (size_t)q0 * FOT_N_SERIES * k_head, q0, cq, NT, st, h->d2h_stream, h->ev_done[c]);
+    if (rc != FOT_OK) return rc;
   }
+  rc = close_span(h, h->pstream[0]);
+  if (rc != FOT_OK) return rc;
   CK(cudaStreamSynchronize(h->d2h_stream));
   for (int c = 0; c < n_ranges; ++c) CK(cudaStreamSynchronize(h->pstream[c & 3]));
+  return FOT_OK;
+}
+
+extern "C" int fot_fetch_winners(fot_handle_t* h, int q0, int n, double* out) {
+  if (!h || !out || q0 < 0 || n < 1) return fail(FOT_ERR_ARG, "fot_fetch_winners: bad argument");
+  if (!h->last_winner_d || q0 + n > h->last_winner_nq) return fail(FOT_ERR_ARG, "fot_fetch_winners: no such queries in the last host-result call");
+  CK(cudaSetDevice(h->device));
+  const size_t row = (size_t)FOT_N_SERIES * h->plan.n_t_max;
+  CK(cudaMemcpyAsync(out, h->last_winner_d + (size_t)q0 * row, (size_t)n * row * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+  CK(cudaStreamSynchronize(h->d2h_stream));
   return FOT_OK;
 }
 

@@ -101,7 +101,7 @@ class SweepResult:
         """The 15 winner sequences of query q truncated to their kept length, or None."""
         if self.best_idx[q] < 0:
             return None
-        n = int(self.winner_len[q])
+        n = min(int(self.winner_len[q]), self.winner.shape[2])      # winner_samples = k: the first k samples only
         return {name: self.winner[q, j, :n].copy() for j, name in enumerate(SERIES)}
 
 
@@ -196,9 +196,12 @@ class SweepEngine:
         return per_T * n_v.astype(np.int64) * self.n_d + has_brake * self.n_B * self.n_total
 
     def run_host(self, frenet, target_speed, limits, stop_dist=None, static=None, dyn=None,
-                 dyn_mode=_lib.FOT_DYN_NONE, static_per_query=False, want_candidates=False) -> SweepResult:
+                 dyn_mode=_lib.FOT_DYN_NONE, static_per_query=False, want_candidates=False,
+                 winner_samples: int = 0) -> SweepResult:
         """One fot_plan_batch_host call.  Shapes: frenet [n_q,6], target_speed [n_q], limits [n_q,4],
-        stop_dist [n_q] (NaN = none), static [M,2] or [n_q,M,2], dyn [n_q,S,P,T,2]."""
+        stop_dist [n_q] (NaN = none), static [M,2] or [n_q,M,2], dyn [n_q,S,P,T,2].
+        winner_samples = k > 0: only the first k samples of each winner series come back (`winner` is
+        [n_q,15,k]); `fetch_winners` reads full series of the last call from the device."""
         f64c = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         frenet = f64c(frenet).reshape(-1, 6)
         n_q = frenet.shape[0]
@@ -230,8 +233,10 @@ class SweepEngine:
             b.S, b.P, b.T_obs = dyn.shape[1], dyn.shape[2], dyn.shape[3]
             b.dyn, b.dyn_mode = _ptr(dyn), dyn_mode
             keep.append(dyn)
-        res = self._result_buffers(n_q, want_candidates, int(b.n_v_max))
+        k_head = min(int(winner_samples), self.n_t_max) if winner_samples and winner_samples > 0 else 0
+        res = self._result_buffers(n_q, want_candidates, int(b.n_v_max), k_head)
         r = _lib.FotResult()
+        r.winner_samples = k_head
         r.best_idx, r.best_cost, r.stats = _ptr(res.best_idx), _ptr(res.best_cost), _ptr(res.stats)
         r.winner_len, r.winner = _ptr(res.winner_len), _ptr(res.winner)
         if want_candidates:
@@ -241,19 +246,29 @@ class SweepEngine:
         res.kernel_ms = float(self.lib.fot_last_kernel_ms(self._h))
         return res
 
-    def _result_buffers(self, n_q: int, want_candidates: bool, n_v_max: int) -> SweepResult:
+    def fetch_winners(self, q0: int, n: int) -> np.ndarray:
+        """Full winner series [n,15,n_t_max] of queries q0..q0+n-1 of the last run_host call (fot_fetch_winners)."""
+        out = np.empty((n, _lib.FOT_N_SERIES, self.n_t_max), dtype=np.float64)
+        _lib.check(self.lib.fot_fetch_winners(self._h, int(q0), int(n), _ptr(out)), "fot_fetch_winners")
+        return out
+
+    def reload_options(self) -> None:
+        """Re-read the FOT_* tuning environment for this handle (tests / tuning; the planning calls never read it)."""
+        _lib.check(self.lib.fot_reload_options(self._h), "fot_reload_options")
+
+    def _result_buffers(self, n_q: int, want_candidates: bool, n_v_max: int, k_head: int = 0) -> SweepResult:
         """Result arrays in pinned host memory (torch is only the allocator), cached per batch size so
         the device->host copies are true async DMAs.  The arrays of a returned SweepResult stay valid
         until the next call on this engine with the same batch size."""
         import torch
         stride = self.lib.fot_candidate_count(self._h, n_v_max, 1) if want_candidates else 0
-        key = (n_q, stride)
+        key = (n_q, stride, k_head)
         cached = self._pinned.get(key)
         if cached is None:
             pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
             cached = dict(best_idx=pin((n_q,), torch.int32), best_cost=pin((n_q,), torch.float64),
                           stats=pin((n_q, _lib.FOT_N_STATS), torch.int32), winner_len=pin((n_q,), torch.int32),
-                          winner=pin((n_q, _lib.FOT_N_SERIES, self.n_t_max), torch.float64))
+                          winner=pin((n_q, _lib.FOT_N_SERIES, k_head or self.n_t_max), torch.float64))
             if want_candidates:
                 cached["cand_cat"] = pin((n_q, stride), torch.uint8)
                 cached["cand_cost"] = pin((n_q, stride), torch.float64)

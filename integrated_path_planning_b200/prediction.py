@@ -61,10 +61,10 @@ class DevicePredictionPostprocessor:
             s = s.expand(n_q)
         return s.to(self._dev).contiguous()
 
-    @staticmethod
-    def _stream():
+    def _stream(self):
+        """torch's current stream ON THIS OBJECT'S DEVICE (not on torch's current device)."""
         import torch
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
 
     # -- API -----------------------------------------------------------------------------------
     def predict_cv(self, p_curr, p_prev=None, staleness=None, current_positions=None, out=None,
@@ -160,7 +160,7 @@ def safety_metrics(ego, ped_pos, ped_vel, ego_radius: float, ped_radius: float, 
         o = np.ascontiguousarray(footprint.offsets, dtype=np.float64).reshape(-1)
         combined, offs, n_circ = float(footprint.radius) + float(ped_radius), o.ctypes.data_as(_lib.c_double_p), o.size
     out = torch.empty((n_q, 5), dtype=torch.float64, device=dev)
-    _lib.check(lib.fot_safety_metrics_device(int(device), C.c_void_p(torch.cuda.current_stream().cuda_stream), n_q, P,
+    _lib.check(lib.fot_safety_metrics_device(int(device), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), n_q, P,
                                              _p(ego_t), _p(pos_t) if P else None, _p(vel_t) if P else None, _p(np_t),
                                              combined, offs, n_circ, _p(out)), "fot_safety_metrics_device")
     return {"min_distance": out[:, 0], "collision": out[:, 1] > 0.5, "ttc": out[:, 2], "clearance": out[:, 3],

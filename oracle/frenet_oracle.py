@@ -669,6 +669,44 @@ def classify(k: Knobs, cands, static, dyn, overrides, dist):
             c.category = CAT_OK
 
 
+def threshold_margins(k: Knobs, cands, overrides=None) -> Dict[str, np.ndarray]:
+    """How close the checked quantities come to their limits ("parity tests should log
+    threshold-margin histograms"): for every candidate that reaches a test of the priority chain
+    (frenet_planner.py:964-984), the smallest relative distance |x_n - limit| / limit over its checked samples
+    n >= 1.  The CUDA sweep evaluates these tests in algebraically equal, squared forms that differ from the
+    reference's values by a few ulp (~1e-15 relative); a margin below that is where a category could flip.
+    Call after to_global / classify.  Returns {test: margins of the candidates that evaluate it}."""
+    vmax, amax, kmax, latmax = k.max_speed, k.max_accel, k.max_curvature, k.max_lat_accel
+    if overrides:
+        vmax = overrides.get("max_speed", vmax)
+        amax = overrides.get("max_accel", amax)
+        kmax = overrides.get("max_curvature", kmax)
+        latmax = overrides.get("max_lat_accel", latmax)
+    out = {"speed": [], "accel": [], "curvature": [], "lat_accel": [], "road": []}
+
+    def rel(x, lim):
+        return float(np.min(np.abs(x - lim))) / abs(lim) if len(x) and lim != 0 else np.inf
+
+    for c in cands:
+        if c.category == CAT_DROP or c.keep < 2:
+            continue
+        out["speed"].append(rel(c.v[1:], vmax))
+        if c.category == CAT_SPEED:
+            continue
+        out["accel"].append(rel(np.abs(c.a[1:]), amax))
+        if c.category == CAT_ACCEL:
+            continue
+        fast = c.v[1:] > LOW_SPEED_GATE
+        out["curvature"].append(rel(np.abs(c.c[1:])[fast], kmax))
+        if c.category == CAT_CURV:
+            continue
+        out["lat_accel"].append(rel(c.v[1:] * c.v[1:] * np.abs(c.c[1:]), latmax))
+        if c.category == CAT_LAT:
+            continue
+        out["road"].append(rel(np.abs(c.d[1:]), k.max_road_width + 1e-9))
+    return {name: np.asarray(v, dtype=float) for name, v in out.items()}
+
+
 def stop_filter(cands, max_stop_distance):
     """frenet_planner.py:307-324."""
     for c in cands:
@@ -716,6 +754,7 @@ class OraclePlanner:
         to_global(self.sp, cands)
         static = None if static is None else np.asarray(static, dtype=float)
         classify(k, cands, static, dyn, overrides, dist)
+        self.last_candidates = cands                                    # diagnostics (threshold_margins)
         if max_stop_distance is not None:
             stop_filter(cands, max_stop_distance)
         cats = np.array([c.category for c in cands], dtype=np.int8)

@@ -16,3 +16,14 @@ def pytest_configure(config):
 def has_gpu():
     import torch
     return torch.cuda.is_available()
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests marked `gpu` need a CUDA device: skipped (not failed) on a machine without one."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

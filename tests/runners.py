@@ -16,6 +16,35 @@ class _Ego:
         self.x, self.y, self.yaw, self.v, self.a = x, y, yaw, v, a
 
 
+def reload_options():
+    """The FOT_* tuning variables are resolved when a handle is created; tests that switch variants on a live
+    planner change the environment and then ask every live handle to re-read it (fot_reload_options(NULL))."""
+    from integrated_path_planning_b200 import _lib
+    _lib.check(_lib.load().fot_reload_options(None), "fot_reload_options")
+
+
+class fot_env:
+    """with fot_env(FOT_SWEEP="generic"): ...   -- environment change + option reload, restored on exit."""
+
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        import os
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update({k: str(v) for k, v in self.kv.items()})
+        reload_options()
+
+    def __exit__(self, *a):
+        import os
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        reload_options()
+
+
 def make_footprint(spec):
     """EgoFootprint.multi_circle restated (reference src/core/footprint.py:66-81)."""
     if spec is None:

@@ -26,6 +26,7 @@ def _env(**kv):
         def __enter__(self):
             self.old = {k: os.environ.get(k) for k in kv}
             os.environ.update({k: str(v) for k, v in kv.items()})
+            runners.reload_options()
 
         def __exit__(self, *a):
             for k, v in self.old.items():
@@ -33,6 +34,7 @@ def _env(**kv):
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
+            runners.reload_options()
     return _Ctx()
 
 

@@ -13,15 +13,9 @@ pytestmark = pytest.mark.gpu
 
 
 def _run(kernel, fn):
-    old = os.environ.get("FOT_SWEEP")
-    os.environ["FOT_SWEEP"] = kernel
-    try:
+    from tests import runners
+    with runners.fot_env(FOT_SWEEP=kernel):      # options are resolved per handle: reload after the switch
         return fn()
-    finally:
-        if old is None:
-            os.environ.pop("FOT_SWEEP", None)
-        else:
-            os.environ["FOT_SWEEP"] = old
 
 
 def _assert_same(a, b):

@@ -45,12 +45,14 @@ fs = np.array([[5.0, 5.0, 0.0, 0.0, 0.0, 0.0]])
 res3 = {}
 for kern in ("items", "generic"):
     os.environ["FOT_SWEEP"] = kern
+    bp.engine.reload_options()
     ms = []
     for _ in range(6):
         r = bp.plan_batch(fs, 6.2, distribution=dist[None])
         ms.append(r.kernel_ms)
     res3[kern + "_kernel_ms"] = float(np.median(ms[1:]))
 os.environ.pop("FOT_SWEEP")
+bp.engine.reload_options()
 from integrated_path_planning_b200.engine import speed_grid
 pts = int(bp.engine.points_per_query(fs, np.array([len(speed_grid(6.2, knobs["d_t_s"]))])).sum())
 res3.update({"candidates": int(r.n_cand[0]), "dense_evals": pts * 4000, "stats": r.stats[0].tolist()})

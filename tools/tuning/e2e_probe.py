@@ -18,6 +18,7 @@ for v in variants:
     for kv in v.split():
         k, val = kv.split("=")
         os.environ[k] = val
+    planner.engine.reload_options()
     for _ in range(4):
         res = planner.plan_batch(frenet, bench.TARGET_SPEED, dynamic_obstacles=dyn_host[:, 0])
     ts = []
@@ -32,3 +33,4 @@ for v in variants:
     print(f"{v or 'default':60s} median {np.median(ts):.3f} ms  min {min(ts):.3f}  same_winners {same}", flush=True)
     for kv in v.split():
         os.environ.pop(kv.split("=")[0], None)
+    planner.engine.reload_options()
