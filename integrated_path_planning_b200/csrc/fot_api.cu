@@ -13,6 +13,7 @@
 
 #include "fot_kernels.cuh"
 #include "fot_sweep_items.cuh"
+#include "fot_sweep_warp.cuh"
 #include "fot_predict.cuh"
 
 using namespace fot;
@@ -67,7 +68,9 @@ struct Options {
   int qcap = 1024;             // FOT_QCAP           collision queue entries (tests force the queue-full path)
   int fused_box = 0;           // FOT_FUSED_BOX      1: trajectory boxes in the sweep even for a resident tensor
   int stage_dyn = 1;           // FOT_STAGE_DYN      0: never stage the obstacle block in shared memory
-  int sweep = 0;               // FOT_SWEEP          0 auto, 1 "items" (fail if unsupported), 2 "generic" (candidate-major kernel)
+  int sweep = 0;               // FOT_SWEEP          0 auto (warp -> items -> generic, the first that covers the shape), 1 "items"
+                               //                    (block-queue kernel; fail if unsupported), 2 "generic" (candidate-major
+                               //                    kernel), 3 "warp" (warp-local kernel; fail if unsupported)
   int host_chunks = 0;         // FOT_HOST_CHUNKS    equal chunks of the host-pointer call (0: rule)
   std::string chunk_waves;     // FOT_CHUNK_WAVES    chunk sizes in sweep waves, "1,2,3" (+ the rest)
   int host_streams = 2;        // FOT_HOST_STREAMS   1: chunks on one compute stream
@@ -86,7 +89,7 @@ struct Options {
     qcap = std::max(1, std::min(1 << 15, geti("FOT_QCAP", 1024)));
     fused_box = geti("FOT_FUSED_BOX", 0) != 0;
     stage_dyn = geti("FOT_STAGE_DYN", 1) != 0;
-    if (const char* e = getenv("FOT_SWEEP")) sweep = !strcmp(e, "generic") ? 2 : !strcmp(e, "items") ? 1 : 0;
+    if (const char* e = getenv("FOT_SWEEP")) sweep = !strcmp(e, "generic") ? 2 : !strcmp(e, "items") ? 1 : !strcmp(e, "warp") ? 3 : 0;
     host_chunks = geti("FOT_HOST_CHUNKS", 0);
     if (const char* e = getenv("FOT_CHUNK_WAVES")) chunk_waves = e;
     host_streams = geti("FOT_HOST_STREAMS", 2);
@@ -224,6 +227,8 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   CK(cudaFuncSetAttribute(fot_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_items<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   { std::lock_guard<std::mutex> lk(g_live_mu); g_live.insert(h); }
   guard.h = nullptr;
   *out = h;
@@ -420,6 +425,85 @@ static bool item_geometry(const fot_handle* h, const fot_batch_t* b, ItemGeom* g
   return true;
 }
 
+// Geometry of the warp-local kernel (fot_sweep_warp): the block decomposition of fot_sweep_items, per-warp obstacle
+// lists and survivor queues, and the per-block state in two copies.  False when the shape is outside its range
+// (more than kWarpListCap obstacle entries per query, long time grids): fot_sweep_items then runs.
+static bool warp_geometry(const fot_handle* h, const fot_batch_t* b, WarpGeom* g, size_t* smem_bytes,
+                          bool want_fused_box = false, int bpc_override = 0) {
+  const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B, nx = h->plan.cfg.nx;
+  const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
+  const long long SPl = has_dyn ? (long long)b->S * b->P : 0;
+  if (NT > 128 || nd > 8192 || SPl + b->n_static > kWarpListCap) return false;
+  const int SP = (int)SPl;
+  int max_threads = kItemThreads;
+  if (h->opt.item_threads > 0) max_threads = std::max(NT, std::min(kItemThreads, h->opt.item_threads));
+  const int ppc_max = max_threads / NT;
+  WarpGeom G{};
+  G.chunks = (b->n_v_max + ppc_max - 1) / ppc_max;
+  G.ppc = (b->n_v_max + G.chunks - 1) / G.chunks;
+  G.grid_blocks = h->plan.cfg.n_T * G.chunks;
+  G.ppb = nB > 0 ? std::min(nB, ppc_max) : 0;
+  G.brake_blocks = nB > 0 ? (nB + G.ppb - 1) / G.ppb : 0;
+  G.blocks_per_query = G.grid_blocks + G.brake_blocks;
+  {
+    const long long total = (long long)b->n_q * G.blocks_per_query;
+    long long bpc = total / ((long long)h->sms * 2 * 4);
+    bpc = std::max<long long>(1, std::min<long long>(bpc, G.blocks_per_query));
+    if (bpc_override > 0) bpc = std::max(1, std::min(bpc_override, (int)G.blocks_per_query));
+    if (h->opt.bpc > 0) bpc = std::max(1, std::min(h->opt.bpc, (int)G.blocks_per_query));
+    G.ctas_per_query = (int)((G.blocks_per_query + bpc - 1) / bpc);
+    G.bpc = (G.blocks_per_query + G.ctas_per_query - 1) / G.ctas_per_query;
+  }
+  G.pcap = std::max(G.ppc, std::max(G.ppb, 1));
+  G.threads = (G.pcap * NT + 31) / 32 * 32;
+  G.ct_lcap = std::max(nd, std::max(G.ppb, 1));
+  G.nw4 = (nd + 3) / 4;
+  G.nwc = (nd + 31) / 32;
+  const int max_viol = b->dyn_mode == FOT_DYN_DISTRIBUTION ? (int)std::floor(h->plan.cfg.chance_epsilon * (double)b->S) : 0;
+  G.vwords = max_viol > 0 ? (b->S + 31) / 32 : 0;
+  G.lcap = std::max(1, SP + b->n_static);
+  G.spline_smem = nx <= 128 ? 1 : 0;
+  const size_t dyn_bytes = (size_t)SP * b->T_obs * 16;
+  const bool fuse = want_fused_box || h->opt.fused_box;
+  auto layout = [&](bool stage) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
+    G.o_row = take((size_t)G.pcap * NT * kRowW * 8);
+    G.o_dgrid = take((size_t)nd * 8);
+    G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);
+    G.o_dyn = take(stage ? dyn_bytes : 0);
+    G.o_box = take(stage && fuse ? (size_t)SP * 16 : 0);
+    G.o_wlist = take((size_t)(G.threads / 32) * G.lcap * 4);
+    G.o_wq = take((size_t)(G.threads / 32) * kWarpQueue * 4);
+    G.o_buf = take(0);
+    size_t bo = 0;
+    auto btake = [&](size_t bytes) { size_t o = bo; bo = (bo + bytes + 15) / 16 * 16; return (int32_t)o; };
+    G.b_fnr = btake((size_t)G.pcap * 4);
+    G.b_flags = btake((size_t)G.pcap * G.nw4 * 4);
+    G.b_hit = btake((size_t)G.pcap * G.nwc * 4);
+    G.b_viol = btake((size_t)G.pcap * nd * G.vwords * 4);
+    G.b_dirty = btake((size_t)G.pcap * G.nwc * 4);
+    G.n_zero = (int32_t)((bo - (size_t)G.b_fnr) / 4);
+    G.b_sdl = btake((size_t)G.pcap * 8);
+    G.b_ct = btake((size_t)(G.pcap + 2 * G.ct_lcap) * 8);
+    G.b_vlast = btake((size_t)G.pcap * nd * 8);
+    G.b_span = btake((size_t)G.pcap * 8);
+    G.buf_bytes = (int32_t)bo;
+    off += 2 * bo;
+    G.stage_dyn = stage ? 1 : 0;
+    G.fused_box = stage && fuse ? 1 : 0;
+    return off;
+  };
+  bool stage = has_dyn && dyn_bytes > 0 && dyn_bytes <= 64 * 1024 && ((uintptr_t)b->dyn & 15) == 0;
+  stage = stage && h->opt.stage_dyn;
+  size_t bytes = layout(stage);
+  if (stage && bytes > 110 * 1024) { stage = false; bytes = layout(false); }
+  if (bytes > (size_t)h->smem_optin) return false;
+  *g = G;
+  *smem_bytes = bytes;
+  return true;
+}
+
 static int check_batch(const fot_handle* h, const fot_batch_t* b, const fot_result_t* r) {
   if (!h || !b || !r) return fail(FOT_ERR_ARG, "null argument");
   if (b->n_q < 1 || b->n_v_max < 1) return fail(FOT_ERR_ARG, "n_q and n_v_max must be >= 1");
@@ -473,8 +557,23 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   size_t ismem = 0;
   bool use_items = item_geometry(h, b, &ig, &ismem, gate.word != nullptr, bpc_override);
   if (h->opt.sweep == 2) use_items = false;
-  if (gate.word && !(use_items && ig.fused_box)) return fail(FOT_ERR_ARG, "gated launch needs fot_sweep_items with a staged obstacle block");
-  if (gate.word) { ig.gate = gate.word; ig.gate_epoch = gate.epoch; ig.gate_per = gate.per; ig.gate_q0 = (int32_t)q_off; }
+  // the warp-local kernel where its shape range allows (and nothing asks for another kernel)
+  WarpGeom wg{};
+  size_t wsmem = 0;
+  bool use_warp = (h->opt.sweep == 0 || h->opt.sweep == 3) && warp_geometry(h, b, &wg, &wsmem, gate.word != nullptr, bpc_override);
+  if (use_warp && gate.word && !wg.fused_box) use_warp = false;
+  if (h->opt.sweep == 3 && !use_warp) return fail(FOT_ERR_ARG, "FOT_SWEEP=warp: shape not supported by fot_sweep_warp");
+  if (use_warp) {
+    // same block decomposition and scratch as fot_sweep_items: the code below sizes everything from `ig`
+    use_items = true;
+    ig.blocks_per_query = wg.blocks_per_query; ig.ctas_per_query = wg.ctas_per_query; ig.threads = wg.threads;
+    ig.fused_box = wg.fused_box;
+  }
+  if (gate.word && !(use_items && ig.fused_box)) return fail(FOT_ERR_ARG, "gated launch needs a sample-major sweep with a staged obstacle block");
+  if (gate.word) {
+    ig.gate = gate.word; ig.gate_epoch = gate.epoch; ig.gate_per = gate.per; ig.gate_q0 = (int32_t)q_off;
+    wg.gate = gate.word; wg.gate_epoch = gate.epoch; wg.gate_per = gate.per; wg.gate_q0 = (int32_t)q_off;
+  }
   if (h->opt.sweep == 1 && !use_items) return fail(FOT_ERR_ARG, "FOT_SWEEP=items: shape not supported by fot_sweep_items");
   SweepGeom g{};
   size_t smem = 0;
@@ -569,10 +668,12 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
                                                                (const double2*)b->dyn, dyn_box, n_traj, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
-  if (use_items && ig.fused_box) fot_sweep_items<true><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
+  if (use_warp && wg.fused_box) fot_sweep_warp<true><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
+  else if (use_warp) fot_sweep_warp<false><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
+  else if (use_items && ig.fused_box) fot_sweep_items<true><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
   else if (use_items) fot_sweep_items<false><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
   else fot_sweep<<<(unsigned)n_part, kSweepThreads, smem, st>>>(h->plan, B, O, g);
-  h->last_sweep_kind = use_items ? 1 : 2;
+  h->last_sweep_kind = use_warp ? 3 : use_items ? 1 : 2;
   CK(cudaEventRecord(ring[2], st));
   fot_winner<<<b->n_q, 128, (size_t)kTT * h->plan.n_t_max * sizeof(double), st>>>(h->plan, B, O, g);
   CK(cudaEventRecord(ring[3], st));

@@ -187,10 +187,19 @@ class BatchedClosedLoop:
     knobs        : SimulationConfig fields by name (dt, obs_len, ego_*, planner and state-machine knobs)
     ped_tracks   : [N, T_frames, P, 2] replayed pedestrian positions, one frame per dt
     ego0         : [N, 5] initial (x, y, yaw, v, a)
+    sampler      : None = the constant-velocity predictor.  Otherwise the stand-in for the reference's trajectory
+                   generator (SGAN; outside the hot path): `sampler(obs [n, obs_len, P, 2], idx) -> raw [n, S, pred_len,
+                   P, 2]`, the generator's absolute predictions at the 0.4 s cadence for the active simulations `idx`,
+                   S = knobs["num_samples"].  Everything after the generator runs on the device: resampling onto the
+                   planner grid, closest-to-mean selection, t = 0 column (trajectory_predictor.py:233-353,
+                   integrated_simulator.py:503-525).  With knobs["distribution_aware_planning"] the planner sweeps
+                   against the whole sample set under the chance constraint knobs["chance_epsilon"]
+                   (integrated_simulator.py:457-460, :582; frenet_planner.py:1076-1124), else against the
+                   representative sample.
     """
 
     def __init__(self, waypoints_x, waypoints_y, knobs: Dict[str, float], ped_tracks: np.ndarray, ego0: np.ndarray,
-                 device: int = 0, static_obstacles=None, record: bool = False):
+                 device: int = 0, static_obstacles=None, record: bool = False, sampler=None):
         k = {key: (None if (isinstance(v, float) and math.isnan(v)) else v) for key, v in knobs.items()}
         self.k = k
         self.dt = float(k["dt"])
@@ -214,6 +223,9 @@ class BatchedClosedLoop:
         self.device = device
         self.post = DevicePredictionPostprocessor(pred_len=int(_knob(k, "pred_len", 12)), sgan_dt=SGAN_DT, sim_dt=self.dt,
                                                   plan_horizon=_knob(k, "max_t", 5.0), device=device)
+        self.sampler = sampler
+        self.num_samples = int(_knob(k, "num_samples", 1))
+        self.distribution_aware = bool(_knob(k, "distribution_aware_planning", 0)) and self.num_samples >= 2 and sampler is not None
         self.fsm = _StateMachines(self.n, k)
         # per-simulation planner state: ego curvature cache and the two nearest-point caches (the planner's
         # converter and the simulator's own goal-check converter are separate objects in the reference)
@@ -259,7 +271,7 @@ class BatchedClosedLoop:
             self._ped_step()
 
     # -- one planning attempt for the simulations `idx` -------------------------------------------
-    def _plan(self, idx, target, limits, msd, dyn_dev):
+    def _plan(self, idx, target, limits, msd, dyn_dev, mode=_lib.FOT_DYN_SINGLE):
         import torch
         t0 = time.perf_counter()
         # ok False = conversion failure: plan() returns None (frenet_planner.py:346-374)
@@ -267,7 +279,7 @@ class BatchedClosedLoop:
         self.n_plan_calls += len(idx)
         t1 = time.perf_counter()
         sel = torch.as_tensor(np.asarray(idx), device=dyn_dev.device)
-        batch = DeviceBatch(self.planner, frenet, target, dyn_dev.index_select(0, sel), _lib.FOT_DYN_SINGLE,
+        batch = DeviceBatch(self.planner, frenet, target, dyn_dev.index_select(0, sel), mode,
                             limits=limits, max_stop_distance=msd,
                             static_obstacles=self.static_points if len(self.static_points) else None)
         batch.launch(None)
@@ -290,7 +302,33 @@ class BatchedClosedLoop:
         ts = self.ped_time
         # prediction (integrated_simulator.py:424-527): CV from the observer's last two float32 samples, or the
         # current positions alone while the observer is still filling
-        if len(self.hist) >= self.obs_len:
+        ready = len(self.hist) >= self.obs_len
+        mode, dist_dense, best_dense = _lib.FOT_DYN_SINGLE, None, None
+        if ready and self.sampler is not None:
+            # sample sets from the generator stand-in; everything behind it on the device
+            import torch
+            stale = max(ts - self.hist_t[-1], 0.0)
+            obs = np.stack(self.hist, axis=1)                                  # [N, obs_len, P, 2]
+            raw = np.asarray(self.sampler(obs[idx], idx), dtype=np.float64)    # [n, S, pred_len, P, 2]
+            if raw.shape[0] != len(idx) or raw.shape[1] != self.num_samples:
+                raise ValueError(f"sampler returned {raw.shape}, expected [{len(idx)}, {self.num_samples}, pred_len, P, 2]")
+            full = np.zeros((self.n,) + raw.shape[1:])
+            full[idx] = raw
+            anchor = self.hist[-1].astype(np.float32).astype(np.float64)       # obs_traj[-1] is a float32 tensor (observer.py:131)
+            if self.num_samples == 1:                                          # predict_single_best :336-338
+                dense = self.post.process_prediction(full, anchor, stale)
+                dyn = self.post.prepend_current(dense, pos, pick=torch.zeros(self.n, dtype=torch.int32, device=dense.device), conditional=True)
+                best_dense = dense[:, 0]
+            else:
+                dense = self.post.process_prediction(full, anchor, stale)
+                best, _ = self.post.select_best(dense)
+                dyn = self.post.prepend_current(dense, pos, pick=best, conditional=True)
+                best_dense = dense[torch.arange(self.n, device=dense.device), best.long()]
+                dist_dense = dense
+                if self.distribution_aware:
+                    dyn = self.post.prepend_current(dense, pos, pick=None, conditional=False)
+                    mode = _lib.FOT_DYN_DISTRIBUTION
+        elif ready:
             stale = max(ts - self.hist_t[-1], 0.0)
             dyn = self.post.predict_cv(self.hist[-1], self.hist[-2], stale, pos, obs_float32=True)
         else:
@@ -298,9 +336,13 @@ class BatchedClosedLoop:
             dyn = torch.from_numpy(np.ascontiguousarray(pos[:, None, :, None, :])).to(self.post._dev)
         rec = None
         if self.record:
-            ready = len(self.hist) >= self.obs_len
-            pred = self.post.predict_cv(self.hist[-1], self.hist[-2], stale, None, obs_float32=True)[:, 0].cpu().numpy() if ready else None
-            rec = {"time": self.time, "pred": pred, "old_a": self.ego[:, 4].copy()}
+            if ready and self.sampler is not None:
+                pred = best_dense.cpu().numpy()
+                dist = dist_dense.cpu().numpy() if dist_dense is not None else None
+            else:
+                pred = self.post.predict_cv(self.hist[-1], self.hist[-2], stale, None, obs_float32=True)[:, 0].cpu().numpy() if ready else None
+                dist = None
+            rec = {"time": self.time, "pred": pred, "dist": dist, "old_a": self.ego[:, 4].copy()}
         t_pred = time.perf_counter()
         m = safety_metrics(self.ego, pos, vel, self.ego_radius, self.ped_radius, footprint=self.footprint, device=self.device)
         clearance, ahead = m["clearance"].cpu().numpy(), m["clearance_ahead"].cpu().numpy()
@@ -311,7 +353,7 @@ class BatchedClosedLoop:
         # planning cycle with escalation retries (:529-653)
         state_before = self.fsm.state[idx].copy()
         target, limits, msd = self.fsm.planner_config(idx)
-        found, wlen, win = self._plan(idx, target, limits, msd, dyn)
+        found, wlen, win = self._plan(idx, target, limits, msd, dyn, mode)
         if self.record:
             full_w, full_c = (a.copy() for a in self._last_full)
         self.fsm.update(idx, found, clearance[idx], ahead[idx], self.ego[idx, 3])
@@ -325,7 +367,7 @@ class BatchedClosedLoop:
             calls[retry] += 1
             sub = idx[retry]
             t2, l2, m2 = self.fsm.planner_config(sub)
-            f2, w2, win2 = self._plan(sub, t2, l2, m2, dyn)
+            f2, w2, win2 = self._plan(sub, t2, l2, m2, dyn, mode)
             found[retry], wlen[retry], win[retry] = f2, w2, win2
             if self.record:
                 full_w[retry], full_c[retry] = self._last_full
@@ -371,17 +413,23 @@ class BatchedClosedLoop:
                 self.history[i].append({
                     "time": rec["time"], "ego": self.ego[i].copy(), "jerk": (self.ego[i, 4] - rec["old_a"][i]) / dt,
                     "state": names[int(self.fsm.state[i])], "min_distance": float(md[i]), "ttc": float(ttc[i]),
+                    "collision": bool(collided[i]), "n_samples": self.num_samples,
+                    "dist": None if rec["dist"] is None else rec["dist"][i],
                     "ped_pos": pos[i].copy(), "ped_vel": vel[i].copy(), "pred": None if rec["pred"] is None else rec["pred"][i],
                     "path": full_w[j][:, :n_w].copy() if found[j] else None, "cost": float(full_c[j]) if found[j] else float("inf")})
         self.time += dt
         self.timers["total"] += time.perf_counter() - t_step
         return idx, found, calls
 
-    def save_results(self, i: int, output_dir: str) -> str:
-        """trajectory.npz of simulation `i` with the keys, shapes and construction of
-        IntegratedSimulator.save_results (integrated_simulator.py:906-985); needs record=True.  (The reference's
-        metrics_summary.csv / metrics_report.txt come from its own metrics module and are not written here.)"""
+    def save_results(self, i: int, output_dir: str, context: Optional[dict] = None) -> str:
+        """The result files of simulation `i` as IntegratedSimulator.save_results writes them
+        (integrated_simulator.py:894-1065): trajectory.npz with the same keys, shapes and construction,
+        metrics_summary.csv and metrics_report.txt (results.py: the aggregate metrics of src/core/metrics.py and the
+        context block; the four wall-clock entries avg/max_prediction/planning_time hold this driver's per-step
+        times divided by the batch size).  Needs record=True.  `context` overrides entries of the context block
+        (prediction_method, sgan_model, scenario_file, seed)."""
         import os
+        from .results import aggregate_metrics, write_metrics_files
         if not self.record:
             raise RuntimeError("BatchedClosedLoop(record=True) is needed to write result files")
         h = self.history[i]
@@ -407,6 +455,18 @@ class BatchedClosedLoop:
             planned_v=np.array(planned("v"), dtype=object), planned_a=np.array(planned("a"), dtype=object),
             planned_yaw=np.array(planned("yaw"), dtype=object),
             planned_cost=np.array([r["cost"] for r in h]))
+        metrics = aggregate_metrics(h, self.dt, prediction_dt=SGAN_DT, prediction_steps=int(_knob(self.k, "pred_len", 12)))
+        steps_run = max(1, len(h))
+        per_sim = 1.0 / (self.n * steps_run)
+        metrics["avg_prediction_time"] = metrics["max_prediction_time"] = self.timers["prediction"] * per_sim
+        metrics["avg_planning_time"] = metrics["max_planning_time"] = (self.timers["frenet_host"] + self.timers["sweep"]) * per_sim
+        ctx = {"prediction_method": "cv" if self.sampler is None else "sgan", "sgan_model": None,
+               "ego_target_speed": self.k["ego_target_speed"], "scenario_file": None, "seed": "not_set",
+               "termination_reason": str(self.reason[i]), "total_time": h[-1]["time"] + self.dt if h else 0.0,
+               "steps": len(h)}
+        if context:
+            ctx.update(context)
+        write_metrics_files(output_dir, ctx, metrics, any(r["collision"] for r in h))
         return path
 
     def run(self, n_steps: Optional[int] = None):

@@ -27,7 +27,7 @@ from loguru import logger  # noqa: E402
 
 logger.remove()
 
-KNOB_KEYS = ("dt", "total_time", "obs_len", "ego_target_speed", "ego_max_speed", "ego_max_accel", "ego_max_curvature",
+KNOB_KEYS = ("num_samples", "distribution_aware_planning", "pred_len", "dt", "total_time", "obs_len", "ego_target_speed", "ego_max_speed", "ego_max_accel", "ego_max_curvature",
              "ego_max_lat_accel", "ego_radius", "ped_radius", "obstacle_radius", "d_road_w", "max_road_width", "min_t",
              "max_t", "d_t_s", "k_j", "k_t", "k_d", "k_s_dot", "k_lat", "k_lon",
              "state_machine_trigger_clearance_caution", "state_machine_trigger_time_headway",
@@ -39,7 +39,19 @@ KNOB_KEYS = ("dt", "total_time", "obs_len", "ego_target_speed", "ego_max_speed",
              "chance_epsilon", "collision_margin_inflation", "vehicle_length", "vehicle_width", "ego_footprint_n_circles")
 
 
-def run_variant(seed, scenario="scenario_01_cv", footprint=False):
+def _install_stub(sim, sgan):
+    """Seeded stand-in generator in the unmodified predictor: predictor.predict() then runs its SGAN branch
+    (trajectory_predictor.py:164-186: generator -> relative_to_abs -> process_prediction) and predict_single_best its
+    multi-sample branch (:338-353)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from tests.stub_sampler import StubGenerator
+    sim.predictor.method = "sgan"
+    sim.predictor.generator = StubGenerator(sgan["gen_seed"], sim.predictor.pred_len, sgan.get("sigma", 0.05))
+    assert sim.predictor.num_samples == sgan["num_samples"]
+    assert sim.distribution_aware_planning == bool(sgan["distribution_aware"])
+
+
+def run_variant(seed, scenario="scenario_01_cv", footprint=False, sgan=None):
     import yaml
     from src.config import SimulationConfig, validate_config
     from src.core.data_structures import VehicleState
@@ -55,6 +67,10 @@ def run_variant(seed, scenario="scenario_01_cv", footprint=False):
     d["prediction_method"] = "cv"
     if footprint:
         d["ego_footprint"] = "multi_circle"
+    if sgan:
+        d["num_samples"] = sgan["num_samples"]
+        d["distribution_aware_planning"] = bool(sgan["distribution_aware"])
+        d["chance_epsilon"] = sgan["chance_epsilon"]
     if seed > 0:
         rng = np.random.default_rng(seed)
         peds[:, 0:2] += rng.normal(0, 1.5, peds[:, 0:2].shape)
@@ -68,6 +84,8 @@ def run_variant(seed, scenario="scenario_01_cv", footprint=False):
     validate_config(cfg)
     sim = IntegratedSimulator(cfg)
     assert (sim.ego_footprint is not None) == bool(footprint)
+    if sgan:
+        _install_stub(sim, sgan)
     n_frames = int(cfg.total_time / cfg.dt) + 200
     t = np.arange(n_frames)[:, None, None] * cfg.dt
     traj = peds[None, :, 0:2] + peds[None, :, 2:4] * t
@@ -109,7 +127,7 @@ def run_variant(seed, scenario="scenario_01_cv", footprint=False):
                 wx=np.array(cfg.reference_waypoints_x, dtype=float), wy=np.array(cfg.reference_waypoints_y, dtype=float))
 
 
-def record_trajectory_file(n_steps=80, n_pred=5):
+def record_trajectory_file(n_steps=80, n_pred=5, sgan=None, out_name="rollout_s01_trajectory.npz"):
     """The reference's own result file: scenario_01_cv for `n_steps` steps, IntegratedSimulator.save_results(), and
     the first `n_steps` entries of every array of its trajectory.npz (predictions: first `n_pred` steps only) ->
     rollout_s01_trajectory.npz.  Ragged per-step arrays are stored padded with NaN plus their lengths."""
@@ -125,9 +143,15 @@ def record_trajectory_file(n_steps=80, n_pred=5):
     d["sgan_model_path"] = None
     d["visualization_enabled"] = False
     d["prediction_method"] = "cv"
+    if sgan:
+        d["num_samples"] = sgan["num_samples"]
+        d["distribution_aware_planning"] = bool(sgan["distribution_aware"])
+        d["chance_epsilon"] = sgan["chance_epsilon"]
     cfg = SimulationConfig(**d)
     validate_config(cfg)
     sim = IntegratedSimulator(cfg)
+    if sgan:
+        _install_stub(sim, sgan)
     n_frames = int(cfg.total_time / cfg.dt) + 200
     t = np.arange(n_frames)[:, None, None] * cfg.dt
     sim.pedestrian_sim = ReplayPedestrianSource(peds[None, :, 0:2] + peds[None, :, 2:4] * t, dt=cfg.dt)
@@ -139,6 +163,12 @@ def record_trajectory_file(n_steps=80, n_pred=5):
     sim.save_results(out)
     z = np.load(os.path.join(out, "trajectory.npz"), allow_pickle=True)
     store = {"keys": np.array(sorted(z.files))}
+    # the reference's own metrics files (integrated_simulator.py:1019-1065), verbatim
+    store["metrics_csv"] = np.array(open(os.path.join(out, "metrics_summary.csv")).read())
+    store["metrics_txt"] = np.array(open(os.path.join(out, "metrics_report.txt")).read())
+    if sgan is not None:
+        for key, val in sgan.items():
+            store["sgan/" + key] = np.array(val, dtype=float)
     for key in z.files:
         a = z[key]
         if a.dtype == object:
@@ -155,15 +185,15 @@ def record_trajectory_file(n_steps=80, n_pred=5):
             store[key] = a.astype("U16")
         else:
             store[key] = a
-    np.savez_compressed(os.path.join(HERE, "rollout_s01_trajectory.npz"), **store)
-    print("wrote rollout_s01_trajectory.npz", os.path.getsize(os.path.join(HERE, "rollout_s01_trajectory.npz")) // 1024, "KiB",
+    np.savez_compressed(os.path.join(HERE, out_name), **store)
+    print("wrote", out_name, os.path.getsize(os.path.join(HERE, out_name)) // 1024, "KiB",
           {k: (z[k].shape, str(z[k].dtype)) for k in z.files})
 
 
-def record(scenario, out_name, seeds, footprint=False):
+def record(scenario, out_name, seeds, footprint=False, sgan=None):
     store = {}
     for k, seed in enumerate(seeds):
-        r = run_variant(seed, scenario, footprint)
+        r = run_variant(seed, scenario, footprint, None if sgan is None else dict(sgan, gen_seed=sgan["gen_seed"] + 1000 * k))
         for name in ("traj", "ego0", "ego", "fsm", "found", "calls", "wx", "wy"):
             store[f"v{k}/{name}"] = r[name]
         store[f"v{k}/reason"] = np.array(r["reason"])
@@ -175,8 +205,15 @@ def record(scenario, out_name, seeds, footprint=False):
         print(f"{scenario} variant {k}: {len(r['ego'])} steps, {r['reason']}, plan calls {int(r['calls'].sum())}, "
               f"states N/C/E {states.tolist()}, failed steps {int((~r['found']).sum())}, static points {len(r['static_points'])}")
     store["n_variants"] = np.array(len(seeds))
+    if sgan is not None:
+        for key, val in sgan.items():
+            store["sgan/" + key] = np.array(val, dtype=float)
     np.savez_compressed(os.path.join(HERE, out_name), **store)
     print("wrote", out_name, os.path.getsize(os.path.join(HERE, out_name)) // 1024, "KiB")
+
+
+SGAN_DIST = dict(num_samples=6, distribution_aware=1, chance_epsilon=0.2, gen_seed=4242, sigma=0.05)
+SGAN_BEST = dict(num_samples=4, distribution_aware=0, chance_epsilon=0.0, gen_seed=777, sigma=0.05)
 
 
 def main():
@@ -188,6 +225,12 @@ def main():
         record("scenario_02_cv", "rollout_s02.npz", (0, 1))
     if "trajfile" in which:
         record_trajectory_file()
+    if "sgan" in which:         # distribution-aware planning on sample sets of a seeded stub generator (6 samples, epsilon 0.2)
+        record("scenario_01_cv", "rollout_s01_dist.npz", (0, 2), sgan=SGAN_DIST)
+    if "sgan_single" in which:  # 4 samples, the representative sample only (distribution_aware_planning off)
+        record("scenario_01_cv", "rollout_s01_best.npz", (0,), sgan=SGAN_BEST)
+    if "sgan_trajfile" in which:
+        record_trajectory_file(sgan=dict(SGAN_DIST), out_name="rollout_s01_dist_trajectory.npz")
     if "s02fp" in which:          # the same corridor with the three-circle footprint of the 4.5 m x 2.0 m vehicle
         record("scenario_02_cv", "rollout_s02fp.npz", (0, 2), footprint=True)
     if "s03" in which:

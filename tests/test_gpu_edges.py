@@ -91,14 +91,18 @@ def test_full_collision_queue_degrades_to_in_place_tests():
     wall = scenarios.wall(x=33.0, half=1.5, n=13)
     pl = _planner()
     run = lambda: pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn, static_obstacles=wall, want_candidates=True)
-    base = run()
-    with _env(FOT_QCAP=4):
+    base = run()                                           # the warp-local kernel (73 entries per query)
+    with _env(FOT_SWEEP="items"):
+        items = run()
+    with _env(FOT_SWEEP="items", FOT_QCAP=4):
         capped = run()
-    with _env(FOT_STAGE_DYN=0, FOT_BPC=1):
+    with _env(FOT_SWEEP="items", FOT_STAGE_DYN=0, FOT_BPC=1):
         unstaged = run()
+    with _env(FOT_STAGE_DYN=0, FOT_BPC=1):
+        unstaged_warp = run()
     with _env(FOT_SWEEP="generic"):
         generic = run()
-    for other in (capped, unstaged, generic):
+    for other in (items, capped, unstaged, unstaged_warp, generic):
         assert np.array_equal(base.cand_cat, other.cand_cat)
         assert np.array_equal(base.best_idx, other.best_idx) and np.array_equal(base.stats, other.stats)
         assert np.array_equal(base.best_cost.view(np.uint64), other.best_cost.view(np.uint64))
@@ -167,7 +171,7 @@ def test_gated_upload_pipeline_matches_the_single_launch():
         ref = run()
         ref = {k: getattr(ref, k).copy() for k in keys}
     assert len(set(ref["best_idx"].tolist())) > 20
-    variants = [dict(), dict(FOT_GATED=0), dict(FOT_GATED=0, FOT_HOST_STREAMS=1), dict(FOT_GATE_UPLOADS=7),
+    variants = [dict(), dict(FOT_SWEEP="items"), dict(FOT_SWEEP="items", FOT_GATED=0), dict(FOT_GATED=0), dict(FOT_GATED=0, FOT_HOST_STREAMS=1), dict(FOT_GATE_UPLOADS=7),
                 dict(FOT_GATE_UPLOADS=64, FOT_GATE_COPY_STREAMS=2), dict(FOT_GATE_MEMCPY=1, FOT_CHUNK_WAVES="1,1"),
                 dict(FOT_GATE_TAIL_BPC=1), dict(FOT_GATE_FLAG_STREAM=1), dict(FOT_STAGE_DYN=0), dict(FOT_STAGE_DYN=0, FOT_HOST_STREAMS=1), dict(FOT_GATED=0, FOT_HOST_CHUNKS=1, FOT_FUSED_BOX=1)]
     for env in variants:
@@ -227,3 +231,34 @@ def test_device_inputs_host_results_entry_point_matches_the_resident_launch():
                 continue
             same = np.array_equal(a.view(np.uint64), b.view(np.uint64)) if a.dtype == np.float64 else np.array_equal(a, b)
             assert same, (count * tile, k)
+
+
+def test_compact_winner_read_back_and_fetch():
+    """fot_result_t.winner_samples = k: the host-result calls copy back only the first k samples of every winner series
+    (a closed-loop caller consumes sample 1, integrated_simulator.py:660-667); fot_fetch_winners reads full series of the
+    last call from the device.  Both must be the bits of the full read-back, for a gated batch, a chunked one and a
+    single plan()-sized call."""
+    import bench
+    for count, tile in ((230, 6), (3, 1)):
+        _, frenet, dyn = bench.make_queries(11000, count)
+        frenet, dyn = np.tile(frenet, (tile, 1)), np.tile(dyn, (tile, 1, 1, 1, 1))
+        pl = _planner()
+        full = pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn[:, 0])
+        want = {k: getattr(full, k).copy() for k in ("best_idx", "best_cost", "stats", "winner_len", "winner")}
+        for env in (dict(), dict(FOT_GATED=0)):
+            with _env(**env):
+                for k in (2, 7):
+                    res = pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn[:, 0], winner_samples=k)
+                    assert res.winner.shape == (len(frenet), 15, k)
+                    for key in ("best_idx", "stats", "winner_len"):
+                        assert np.array_equal(getattr(res, key), want[key]), (env, k, key)
+                    assert np.array_equal(res.best_cost.view(np.uint64), want["best_cost"].view(np.uint64))
+                    keep = np.arange(k)[None, None, :] < np.minimum(want["winner_len"], k)[:, None, None]
+                    assert np.array_equal(np.where(keep, res.winner, 0.0).view(np.uint64),
+                                          np.where(keep, want["winner"][:, :, :k], 0.0).view(np.uint64)), (env, k)
+                    q0, n = len(frenet) // 3, min(5, len(frenet) - len(frenet) // 3)
+                    got = pl.engine.fetch_winners(q0, n)
+                    lens = want["winner_len"][q0:q0 + n]
+                    assert _same("winner", got, want["winner"][q0:q0 + n], lens), (env, k)
+                    series = res.series(int(np.argmax(want["best_idx"] >= 0))) if (want["best_idx"] >= 0).any() else None
+                    assert series is None or len(series["x"]) <= k
