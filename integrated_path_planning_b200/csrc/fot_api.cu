@@ -472,9 +472,10 @@ static bool warp_geometry(const fot_handle* h, const fot_batch_t* b, WarpGeom* g
     G.o_dgrid = take((size_t)nd * 8);
     G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);
     G.o_dyn = take(stage ? dyn_bytes : 0);
-    G.o_box = take(stage && fuse ? (size_t)SP * 16 : 0);
+    G.o_box = take((size_t)SP * 16);                      // trajectory boxes: built here (fused) or copied from fot_prepass
     G.o_wlist = take((size_t)(G.threads / 32) * G.lcap * 4);
     G.o_wq = take((size_t)(G.threads / 32) * kWarpQueue * 4);
+    G.o_bq = take((size_t)kBlockQueue * 4);
     G.o_buf = take(0);
     size_t bo = 0;
     auto btake = [&](size_t bytes) { size_t o = bo; bo = (bo + bytes + 15) / 16 * 16; return (int32_t)o; };
@@ -483,6 +484,7 @@ static bool warp_geometry(const fot_handle* h, const fot_batch_t* b, WarpGeom* g
     G.b_hit = btake((size_t)G.pcap * G.nwc * 4);
     G.b_viol = btake((size_t)G.pcap * nd * G.vwords * 4);
     G.b_dirty = btake((size_t)G.pcap * G.nwc * 4);
+    G.b_qctl = btake(16);
     G.n_zero = (int32_t)((bo - (size_t)G.b_fnr) / 4);
     G.b_sdl = btake((size_t)G.pcap * 8);
     G.b_ct = btake((size_t)(G.pcap + 2 * G.ct_lcap) * 8);

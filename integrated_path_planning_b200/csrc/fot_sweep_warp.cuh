@@ -1,27 +1,32 @@
-// fot_sweep_warp.cuh -- the sample-major sweep with warp-local collision work (sm_100a, fp64).
+// fot_sweep_warp.cuh -- the sample-major sweep with two barriers per block and a barrier-free collision queue
+// (sm_100a, fp64).
 //
 // Same contract, same work decomposition and the same arithmetic as fot_sweep_items (fot_sweep_items.cuh: block =
 // the pairs of one horizon, thread = one (pair, sample) item, loop = lateral targets, affine-in-d_i validity chain in
 // squared form, tangent-frame cull, exact `dx*dx + dy*dy <= r^2` for the survivors).  What changes is the
 // synchronisation.  fot_sweep_items runs every block through six block-wide barriers (reset | items | validity |
 // cull | exact tests | category) and ncu shows the price: 3.1 barrier-stall cycles per issued instruction, 30 % of all
-// warp time (profiles/r1).  Here a block has TWO:
+// warp time (profiles/r1) -- warps that skip the validity loop, or whose samples are far from every pedestrian, wait
+// for the ones that are busy.  Here a block has TWO barriers, and the imbalanced part runs between them without one:
 //
 //   B   per item: quartic solve, reference point, lateral basis -> item row in shared memory
 //   --- barrier (i): rows and the pairs' NaN prefixes are complete
-//   CD  per WARP, no further block-wide step: validity screens and loop (flags by shared atomics, as before), then the
-//       warp boxes its own 32 reference points, lists the obstacles whose trajectory box meets that box (ballot
-//       compaction into a warp-private list -- tighter than a block-wide list), culls them against its own items, and
-//       drains the survivors itself, 32 at a time, one (item, obstacle) entry per lane.  The low-speed units are
-//       handled the same way.  A warp works with the flags as they are at that moment: a candidate that another warp
-//       flags later may get an exact test it did not need -- harmless, the validity categories outrank the collision
-//       category (fp.py:964-991) -- and the lateral window of the cull only ever narrows as flags arrive.
+//   CD  per WARP: validity screens and loop (flags by shared atomics, as before), low-speed units of its own items;
+//       then the warp boxes its own 32 reference points, lists the obstacles whose trajectory box meets that box
+//       (ballot compaction into a warp-private list -- tighter than a block-wide list) and culls them against its own
+//       items.  Survivors go as (item, obstacle) entries into ONE block-wide queue, and every warp that has finished
+//       producing turns consumer: 32 tickets at a time, exact tests against the clean candidates of the entry's pair,
+//       until all warps have produced and the queue is empty.  A slot is valid when it is non-zero -- no barrier
+//       between producing and consuming, so the warps that had little to do take over the tests of the others.
+//       A consumer works with the flags as they are at that moment: a candidate that another warp flags later may
+//       get an exact test it did not need -- harmless, the validity categories outrank the collision category
+//       (fp.py:964-991) -- and the lateral window of the cull only ever narrows as flags arrive.
 //   --- barrier (ii): flags, hit words, violation bitmaps are final
 //   E   category, cost, arg-min, histogram (unchanged)
 //
 // and none between E of one block and B of the next: the per-block state (flags, hit words, first-NaN slots, staged
-// cost entries, terminal speeds) is double-buffered, and the buffer of block b+1 is cleared by the threads of block b
-// right after barrier (i), when every thread is provably done with block b-1.
+// cost entries, terminal speeds, queue counters) is double-buffered, and the buffer of block b+1 is cleared by the
+// threads of block b right after barrier (i), when every thread is provably done with block b-1.
 //
 // Shapes: obstacle entries per query (static + S*P) up to kWarpListCap; larger fields run fot_sweep_items, whose
 // block-wide lists and multi-round queue are made for them.
@@ -31,17 +36,18 @@
 namespace fot {
 
 constexpr int kWarpListCap = 512;    // obstacle entries a warp-private list can hold
-constexpr int kWarpQueue = 64;       // pending (lane, entry) survivors per warp: drained 32 at a time
+constexpr int kWarpQueue = 32;       // warp-private scratch words
+constexpr int kBlockQueue = 2048;    // slots of the block-wide (item, obstacle) queue; beyond it entries are tested in place
 
 struct WarpGeom {
   int32_t ppc, chunks, grid_blocks, ppb, brake_blocks, blocks_per_query, bpc, ctas_per_query, threads, pcap, ct_lcap;
   int32_t lcap;                // list capacity per warp (static + dynamic entries of one query)
   int32_t stage_dyn, spline_smem, vwords, nw4, nwc;
   // byte offsets into dynamic shared memory, once per CTA
-  int32_t o_row, o_dgrid, o_spl, o_dyn, o_box, o_wlist, o_wq;
+  int32_t o_row, o_dgrid, o_spl, o_dyn, o_box, o_wlist, o_wq, o_bq;
   // per-block state: two copies, buf_bytes apart, starting at o_buf; offsets inside one copy
   int32_t o_buf, buf_bytes;
-  int32_t b_fnr, b_flags, b_hit, b_viol, b_dirty, n_zero;   // zero-initialised region: fnr | flags | hit | viol | dirty
+  int32_t b_fnr, b_flags, b_hit, b_viol, b_dirty, b_qctl, n_zero;   // zero-initialised region: fnr | flags | hit | viol | dirty | queue counters
   int32_t b_sdl, b_ct, b_vlast, b_span;
   int32_t fused_box, gate_q0, gate_per;
   uint32_t gate_epoch;
@@ -82,7 +88,8 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
   const int b_first = cta * G.bpc, b_last = min(G.blocks_per_query, b_first + G.bpc);
   const bool state_ok = fabs(fs[0]) + fabs(fs[1]) + fabs(fs[2]) + fabs(fs[3]) + fabs(fs[4]) + fabs(fs[5]) < INFINITY;
   unsigned* wlist = reinterpret_cast<unsigned*>(smb + G.o_wlist) + warp * G.lcap;     // this warp's obstacle list
-  unsigned* wq = reinterpret_cast<unsigned*>(smb + G.o_wq) + warp * kWarpQueue;       // this warp's survivor queue
+  unsigned* wq = reinterpret_cast<unsigned*>(smb + G.o_wq) + warp * kWarpQueue;       // this warp's scratch (slow-item slots)
+  unsigned* bq = reinterpret_cast<unsigned*>(smb + G.o_bq);                           // block-wide queue of (item, obstacle) entries
 
   const bool has_dyn = B.dyn_raw != nullptr;
   const int SP = has_dyn ? B.S * B.P : 0;
@@ -137,6 +144,9 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
     // only the zero regions need it, but the buffers are small
     reinterpret_cast<unsigned*>(smb + G.o_buf)[i] = 0u;
   }
+  for (int i = tid; i < kBlockQueue; i += bd) bq[i] = 0u;          // an empty slot is zero; consumers hand slots back empty
+  if (!kFused && state_ok)
+    for (int j = tid; j < SP; j += bd) sbox[j] = B.dyn_box[(size_t)q * SP + j];      // fot_prepass boxes: read by every warp of every block
   if (kFused) {
     // box every predicted trajectory of the staged obstacle block once per CTA (what fot_prepass does for a resident
     // tensor): one warp per trajectory, fp32 rounded outward, NaN trajectory -> NaN box
@@ -242,6 +252,8 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
   double* ctb = reinterpret_cast<double*>(buf + G.b_ct);            // [pcap + 2 max(n_d, ppb)] cost-table entries: Js | Jp | d_end
   double* vlast = reinterpret_cast<double*>(buf + G.b_vlast);       // [pcap][n_d] v^2 at the last kept sample
   double* sspan = reinterpret_cast<double*>(buf + G.b_span);        // [pcap] s[keep - 1] - s[0]
+  unsigned* qctl = reinterpret_cast<unsigned*>(buf + G.b_qctl);     // block queue: [0] slots reserved, [1] tickets taken, [2] warps done producing
+  const unsigned magicN = ((1u << 20) + (unsigned)N - 1u) / (unsigned)N;   // item / N = (item * magicN) >> 20, exact for item < 512, N <= 128
 
   // ---- phase B: one item per thread ---------------------------------------------------------------
   {
@@ -466,9 +478,11 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
       }
     }
   };
+  FOT_PHASE_MARK(2);
   if (skip) { }
   else if (lite) sweep_targets(std::true_type{});
   else sweep_targets(std::false_type{});
+  FOT_PHASE_MARK(3);
   // Samples beyond the NaN prefix that are inside the spline domain again still count for the candidate-wide
   // singularity guard (fp.py:826-833 runs before the truncation).  Essentially never.
   if (active && !valid && i_rx == i_rx && keep > 0) {
@@ -491,56 +505,115 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
   __syncwarp();
 
   // Low-speed regime (fp.py:1022-1032): the warp redoes the two low-speed tests for its own items that saw a
-  // candidate with v <= 0.5, one (item, candidate) unit per lane.
+  // candidate with v <= 0.5, one (item, candidate) unit per lane, candidate-major over the compacted slow items.
   {
     const unsigned slow_mask = __ballot_sync(0xffffffffu, anyslow && chk);
     if (slow_mask) {
-      const int n_units = __popc(slow_mask) * n_dl;
-      for (int u = lane; u < n_units; u += 32) {
-        const int k = u / n_dl, i = u - k * n_dl;
-        const int it = (tid & ~31) + (int)__fns(slow_mask, 0, k + 1);
-        const int sp = it / N, sn = it - sp * N;
+      const int n_slow = __popc(slow_mask);
+      if (anyslow && chk) wq[__popc(slow_mask & lt_mask)] = (unsigned)tid;
+      __syncwarp();
+      int k = lane % n_slow, i = lane / n_slow;            // unit u = i * n_slow + k for u = lane, lane + 32, ...
+      const int dk = 32 % n_slow, di_step = 32 / n_slow;
+      while (i < n_dl) {
+        const int it = (int)wq[k];
+        const int sp = (int)(((unsigned)it * magicN) >> 20), sn = it - sp * N;
         // a candidate that already carries a flag of curvature priority or higher cannot change category
-        if ((flags[sp * G.nw4 + (i >> 2)] >> (8 * (i & 3))) & (F_DROP | F_SPEED | F_ACCEL | F_CURV)) continue;
-        const double* r1 = row + (sp * NT + sn) * kRowW;                       // sample n
-        const double* r0 = r1 - kRowW;                                         // sample n - 1 (only checked samples queue)
-        const double di = brake_blk ? 0.0 : dgrid[i];
-        const double d = fma(di, r1[9], r1[8]), dprev = fma(di, r0[9], r0[8]);
-        const double qq = fma(-r1[4], d, 1.0), dpr = fma(di, r1[11], r1[10]) * r1[6];
-        const double ssd = r1[7];
-        if (ssd * ssd * fma(qq, qq, dpr * dpr) > 0.25) continue;               // this candidate is in the fast regime here
-        bool badc;
-        if (fabs(d - dprev) > fmax(1.5 * fabs(r1[5] - r0[5]), 0.02)) {
-          badc = true;
-        } else {
-          // |wrap(yaw_n - yaw_{n-1})| is the angle between the heading vectors u = R(theta_r)(q, d')
-          const double kmax = lim[2];
-          const double q_prev = fma(-r0[4], dprev, 1.0);
-          const double dp_prev = fma(di, r0[11], r0[10]) * r0[6];
-          const double ux = r1[2] * qq - r1[3] * dpr, uy = r1[3] * qq + r1[2] * dpr;
-          const double uxp = r0[2] * q_prev - r0[3] * dp_prev, uyp = r0[3] * q_prev + r0[2] * dp_prev;
-          const double cr = uxp * uy - uyp * ux, dt_ = uxp * ux + uyp * uy;
-          const double ex = fma(-r1[3], d, r1[0]) - fma(-r0[3], dprev, r0[0]);
-          const double ey = fma(r1[2], d, r1[1]) - fma(r0[2], dprev, r0[1]);
-          const double step2 = fma(ex, ex, ey * ey);
-          if (kmax * kmax * step2 <= 0.01)
-            // the threshold is the 0.1 rad floor: angle > 0.1 <=> dot <= 0 or cross^2 > tan(0.1)^2 dot^2
-            badc = dt_ <= 0.0 || cr * cr > kTan01Sq * dt_ * dt_;
-          else
-            badc = fabs(atan2(cr, dt_)) > kmax * sqrt(step2);
+        if (!((flags[sp * G.nw4 + (i >> 2)] >> (8 * (i & 3))) & (F_DROP | F_SPEED | F_ACCEL | F_CURV))) {
+          const double* r1 = row + (sp * NT + sn) * kRowW;                     // sample n
+          const double* r0 = r1 - kRowW;                                       // sample n - 1 (only checked samples queue)
+          const double di = brake_blk ? 0.0 : dgrid[i];
+          const double d = fma(di, r1[9], r1[8]), dprev = fma(di, r0[9], r0[8]);
+          const double qq = fma(-r1[4], d, 1.0), dpr = fma(di, r1[11], r1[10]) * r1[6];
+          const double ssd = r1[7];
+          if (!(ssd * ssd * fma(qq, qq, dpr * dpr) > 0.25)) {                  // else: this candidate is in the fast regime here
+            bool badc;
+            if (fabs(d - dprev) > fmax(1.5 * fabs(r1[5] - r0[5]), 0.02)) {
+              badc = true;
+            } else {
+              // |wrap(yaw_n - yaw_{n-1})| is the angle between the heading vectors u = R(theta_r)(q, d')
+              const double kmax = lim[2];
+              const double q_prev = fma(-r0[4], dprev, 1.0);
+              const double dp_prev = fma(di, r0[11], r0[10]) * r0[6];
+              const double ux = r1[2] * qq - r1[3] * dpr, uy = r1[3] * qq + r1[2] * dpr;
+              const double uxp = r0[2] * q_prev - r0[3] * dp_prev, uyp = r0[3] * q_prev + r0[2] * dp_prev;
+              const double cr = uxp * uy - uyp * ux, dt_ = uxp * ux + uyp * uy;
+              const double ex = fma(-r1[3], d, r1[0]) - fma(-r0[3], dprev, r0[0]);
+              const double ey = fma(r1[2], d, r1[1]) - fma(r0[2], dprev, r0[1]);
+              const double step2 = fma(ex, ex, ey * ey);
+              if (kmax * kmax * step2 <= 0.01)
+                // the threshold is the 0.1 rad floor: angle > 0.1 <=> dot <= 0 or cross^2 > tan(0.1)^2 dot^2
+                badc = dt_ <= 0.0 || cr * cr > kTan01Sq * dt_ * dt_;
+              else
+                badc = fabs(atan2(cr, dt_)) > kmax * sqrt(step2);
+            }
+            if (badc) {
+              atomicOr(&flags[sp * G.nw4 + (i >> 2)], F_CURV << (8 * (i & 3)));
+              atomicOr(&dirty[sp * G.nwc + (i >> 5)], 1u << (i & 31));
+            }
+          }
         }
-        if (badc) {
-          atomicOr(&flags[sp * G.nw4 + (i >> 2)], F_CURV << (8 * (i & 3)));
-          atomicOr(&dirty[sp * G.nwc + (i >> 5)], 1u << (i & 31));
-        }
+        k += dk; i += di_step;
+        if (k >= n_slow) { k -= n_slow; ++i; }
       }
       __syncwarp();
     }
   }
 
-  // ---- collision (fp.py:1035-1233), warp-local ------------------------------------------------------
+  FOT_PHASE_MARK(4);
+  // ---- collision (fp.py:1035-1233) ------------------------------------------------------------------
+  // Every warp PRODUCES (item, obstacle) entries from the cull of its own items into one block-wide queue and then
+  // CONSUMES entries of the whole block, 32 tickets at a time, until every warp has finished producing and the queue
+  // is drained: warps that skipped the validity loop or have no obstacle near their samples take over the exact
+  // tests of the others.  No barrier separates the two halves: a slot is valid as soon as it is non-zero.
   if (has_dyn || M > 0) {
-    // box of this warp's reference points (fp32 rounded outward, ordered-uint encoding, warp min / max by redux)
+    // exact test of one entry against every live clean candidate of the item's pair
+    auto process = [&](unsigned ent) {
+      const int it = (int)((ent >> 21) & 0x1ffu);
+      const bool is_dyn = (ent >> 20) & 1u;
+      const unsigned j = ent & 0xfffffu;
+      const int ep = (int)(((unsigned)it * magicN) >> 20), en = it - ep * N;
+      const unsigned off = is_dyn ? j * (unsigned)B.T_obs : j;
+      const unsigned ok_ = off + (unsigned)(B.T_obs > 0 ? min(en, B.T_obs - 1) : 0);
+      const double2 o = is_dyn ? (G.stage_dyn ? dynst[ok_] : dyn_q[ok_]) : stat_q[off];
+      const double r2 = is_dyn ? r2_dyn : P.cfg.collide_r2;
+      const bool use_budget = budget && is_dyn;
+      const double* r = row + (ep * NT + en) * kRowW;
+      const double cth = r[2], sth = r[3];
+      const double X0 = fma(-sth, r[8], r[0]) - o.x, X1 = -(sth * r[9]);       // x - ox = X0 + d_i X1
+      const double Y0 = fma(cth, r[8], r[1]) - o.y, Y1 = cth * r[9];
+      for (int w = 0; w < G.nwc; ++w) {
+        const int rem = n_dl - 32 * w;
+        unsigned mbits = ~dirty[ep * G.nwc + w] & (rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u));
+        if (!use_budget) mbits &= ~hitw[ep * G.nwc + w];
+        while (mbits) {
+          const int bit = __ffs(mbits) - 1;
+          mbits &= mbits - 1u;
+          const int i = w * 32 + bit;
+          const double di = brake_blk ? 0.0 : dgrid[i];
+          bool hit = false;
+          if (n_circ == 0) {
+            const double dx = fma(di, X1, X0), dy = fma(di, Y1, Y0);
+            hit = dx * dx + dy * dy <= r2;                                     // fp.py:1196-1198, :1231-1233
+          } else {                                                             // fp.py:1158-1167
+            const double d = fma(di, r[9], r[8]);
+            const double dpr = fma(di, r[11], r[10]) * r[6];
+            const double qq = fma(-r[4], d, 1.0);
+            const double rh = 1.0 / sqrt(fma(qq, qq, dpr * dpr));
+            const double hx = (cth * qq - sth * dpr) * rh, hy = (sth * qq + cth * dpr) * rh;   // (cos yaw, sin yaw)
+            for (int ci = 0; ci < n_circ && !hit; ++ci) {
+              const double dx = fma(di, X1, X0) + P.cfg.circle_offsets[ci] * hx, dy = fma(di, Y1, Y0) + P.cfg.circle_offsets[ci] * hy;
+              hit = dx * dx + dy * dy <= r2;
+            }
+          }
+          if (hit) {
+            if (!use_budget) atomicOr(&hitw[ep * G.nwc + w], 1u << bit);
+            else { const int sidx = (int)j / B.P; atomicOr(&viol[(ep * n_d + i) * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
+          }
+        }
+      }
+    };
+
+    // -- produce: box of this warp's reference points -> obstacle list -> tangent-frame cull of its own items
     const bool okb = valid && i_rx == i_rx && i_ry == i_ry;
     const unsigned uxlo = __reduce_min_sync(0xffffffffu, okb ? f2ord(__double2float_rd(i_rx)) : 0xffffffffu);
     if (uxlo != 0xffffffffu) {                           // warp-uniform
@@ -566,20 +639,20 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
       }
       if (SP > 0) {
         if (G.stage_dyn) mbar_wait(&s_bar, 0u);          // the staged obstacle block has landed
-        const float4* boxes = kFused ? sbox : B.dyn_box + (size_t)q * SP;
         for (int j0 = 0; j0 < SP; j0 += 32) {
           const int j = j0 + lane;
           bool in = false;
           if (j < SP) {
-            const float4 ob = boxes[j];                  // xmin xmax ymin ymax
+            const float4 ob = sbox[j];                   // xmin xmax ymin ymax
             in = ob.x <= bx1 && ob.y >= bx0 && ob.z <= by1 && ob.w >= by0;
           }
           const unsigned bal = __ballot_sync(0xffffffffu, in);
-          if (in) wlist[n_ws + n_wd + __popc(bal & lt_mask)] = (unsigned)(j * B.T_obs);
+          if (in) wlist[n_ws + n_wd + __popc(bal & lt_mask)] = (unsigned)j;
           n_wd += __popc(bal);
         }
       }
       __syncwarp();
+      FOT_PHASE_MARK(5);
       const int n_l = n_ws + n_wd;
       if (n_l > 0) {
         // this item's pair as it stands now: lowest / highest clean candidate -> lateral window of the cull
@@ -601,58 +674,12 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
           d_lo = A0 + fmin(ga * B0, gb * B0) - 1e-9;
           d_hi = A0 + fmax(ga * B0, gb * B0) + 1e-9;
         }
-        // exact test of entry (item, obstacle) against every live clean candidate of the item's pair
-        auto process = [&](unsigned ent) {
-          const int it = (tid & ~31) + (int)(ent >> 16), e = (int)(ent & 0xffffu);
-          const int ep = it / N, en = it - ep * N;
-          const bool is_dyn = e >= n_ws;
-          const unsigned off = wlist[e];
-          const unsigned ok_ = off + (unsigned)(B.T_obs > 0 ? min(en, B.T_obs - 1) : 0);
-          const double2 o = is_dyn ? (G.stage_dyn ? dynst[ok_] : dyn_q[ok_]) : stat_q[off];
-          const double r2 = is_dyn ? r2_dyn : P.cfg.collide_r2;
-          const bool use_budget = budget && is_dyn;
-          const double* r = row + (ep * NT + en) * kRowW;
-          const double cth = r[2], sth = r[3];
-          const double X0 = fma(-sth, r[8], r[0]) - o.x, X1 = -(sth * r[9]);     // x - ox = X0 + d_i X1
-          const double Y0 = fma(cth, r[8], r[1]) - o.y, Y1 = cth * r[9];
-          for (int w = 0; w < G.nwc; ++w) {
-            const int rem = n_dl - 32 * w;
-            unsigned mbits = ~dirty[ep * G.nwc + w] & (rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u));
-            if (!use_budget) mbits &= ~hitw[ep * G.nwc + w];
-            while (mbits) {
-              const int bit = __ffs(mbits) - 1;
-              mbits &= mbits - 1u;
-              const int i = w * 32 + bit;
-              const double di = brake_blk ? 0.0 : dgrid[i];
-              bool hit = false;
-              if (n_circ == 0) {
-                const double dx = fma(di, X1, X0), dy = fma(di, Y1, Y0);
-                hit = dx * dx + dy * dy <= r2;                                   // fp.py:1196-1198, :1231-1233
-              } else {                                                           // fp.py:1158-1167
-                const double d = fma(di, r[9], r[8]);
-                const double dpr = fma(di, r[11], r[10]) * r[6];
-                const double qq = fma(-r[4], d, 1.0);
-                const double rh = 1.0 / sqrt(fma(qq, qq, dpr * dpr));
-                const double hx = (cth * qq - sth * dpr) * rh, hy = (sth * qq + cth * dpr) * rh;   // (cos yaw, sin yaw)
-                for (int ci = 0; ci < n_circ && !hit; ++ci) {
-                  const double dx = fma(di, X1, X0) + P.cfg.circle_offsets[ci] * hx, dy = fma(di, Y1, Y0) + P.cfg.circle_offsets[ci] * hy;
-                  hit = dx * dx + dy * dy <= r2;
-                }
-              }
-              if (hit) {
-                if (!use_budget) atomicOr(&hitw[ep * G.nwc + w], 1u << bit);
-                else { const int sidx = (int)(off / (unsigned)B.T_obs) / B.P; atomicOr(&viol[(ep * n_d + i) * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
-              }
-            }
-          }
-        };
-        int qn = 0;                                      // pending survivors in this warp's queue (warp-uniform)
         for (int e = 0; e < n_l; ++e) {
           bool surv = false;
+          const bool is_dyn = e >= n_ws;
+          const unsigned j = wlist[e];
           if (cull) {
-            const bool is_dyn = e >= n_ws;
-            const unsigned off = wlist[e];
-            const double2 o = is_dyn ? (G.stage_dyn ? dynst[off + kob] : dyn_q[off + kob]) : stat_q[off];
+            const double2 o = is_dyn ? (G.stage_dyn ? dynst[j * (unsigned)B.T_obs + kob] : dyn_q[j * (unsigned)B.T_obs + kob]) : stat_q[j];
             const double rc = is_dyn ? rc_d : rc_s;
             const double al = fma(o.x, i_cth, fma(o.y, i_sth, -ca));
             const double ac = fma(o.y, i_cth, fma(-o.x, i_sth, -cn));
@@ -660,25 +687,57 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
           }
           const unsigned bal = __ballot_sync(0xffffffffu, surv);
           if (bal) {
-            if (surv) wq[qn + __popc(bal & lt_mask)] = ((unsigned)lane << 16) | (unsigned)e;
-            qn += __popc(bal);
-            if (qn >= 32) {                              // a full warp of entries: drain them, one per lane
-              __syncwarp();
-              process(wq[qn - 32 + lane]);
-              qn -= 32;
-              __syncwarp();
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&qctl[0], (unsigned)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (surv) {
+              const unsigned slot = base + __popc(bal & lt_mask);
+              const unsigned ent = 0x80000000u | ((unsigned)tid << 21) | ((unsigned)is_dyn << 20) | j;
+              if (slot < (unsigned)kBlockQueue) *reinterpret_cast<volatile unsigned*>(bq + slot) = ent;
+              else process(ent);                         // queue full: test right here
             }
           }
         }
-        __syncwarp();
-        if (lane < qn) process(wq[lane]);
       }
     }
+    FOT_PHASE_MARK(6);
+    // -- this warp has produced everything it will produce
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); atomicAdd(&qctl[2], 1u); }
+    // -- consume: 32 tickets at a time
+    const unsigned n_warps = (unsigned)(bd >> 5);
+    for (;;) {
+      unsigned h = 0;
+      if (lane == 0) h = atomicAdd(&qctl[1], 32u);
+      h = __shfl_sync(0xffffffffu, h, 0);
+      if (h >= (unsigned)kBlockQueue) break;             // beyond the queue: those entries were tested in place
+      const unsigned idx = h + lane;
+      unsigned ent = 0;
+      if (idx < (unsigned)kBlockQueue) {
+        volatile unsigned* slot = bq + idx;
+        for (;;) {
+          ent = *slot;
+          if (ent) break;
+          unsigned done;
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(done) : "r"(smem_u32(&qctl[2])) : "memory");
+          if (done == n_warps) { ent = *slot; break; }   // nobody will write this slot any more
+          __nanosleep(64);
+        }
+        if (ent) { process(ent); *slot = 0u; }           // (slots are handed back empty for the next block)
+      }
+      unsigned fin = 0;
+      if (lane == 0) {
+        unsigned done;
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(done) : "r"(smem_u32(&qctl[2])) : "memory");
+        fin = done == n_warps && h + 32u >= *reinterpret_cast<volatile unsigned*>(&qctl[0]);
+      }
+      if (__shfl_sync(0xffffffffu, fin, 0)) break;
+    }
   }
+  FOT_PHASE_MARK(7);
   asm volatile("cp.async.wait_all;" ::: "memory");   // this block's cost-table entries have landed (visible after the barrier)
-  FOT_PHASE_MARK(2);
   __syncthreads();                                       // ---- barrier (ii)
-  FOT_PHASE_MARK(3);
+  FOT_PHASE_MARK(8);
 
   // ---- phase E: category, cost, block arg-min, histogram ----------------------------------------
   for (int c = tid; c < n_cand; c += bd) {
@@ -726,7 +785,7 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
     if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + cand_idx] = cost;
     if (cat == FOT_CAT_OK && cost < INFINITY) argmin_merge(my_cost, my_idx, cost, cand_idx);
   }
-  FOT_PHASE_MARK(4);
+  FOT_PHASE_MARK(9);
   par ^= 1;                                              // no barrier: the next block works in the other buffer
   }  // blocks of this CTA
 

@@ -25,8 +25,13 @@ lib.fot_debug_phase_clocks(buf)
 batch.launch(None)
 lib.fot_debug_phase_clocks(buf)
 v = list(buf)
-names = ["A work", "A barrier", "B work (items, jerk)", "B barrier", "C work (lists, validity loop)", "C barrier",
-         "D cull", "D cull barrier", "D process+slow", "D process barrier", "E work", "E barrier"]
+import os
+if os.environ.get("FOT_SWEEP", "warp") in ("warp", ""):
+    names = ["B work (items)", "barrier (i)", "CD item consts + screens", "CD validity loop", "CD slow units, vlast", "CD warp list build",
+             "CD cull (produce)", "CD exact tests (consume, incl. waiting for entries)", "barrier (ii)", "E work", "-", "-"]
+else:
+    names = ["A work", "A barrier", "B work (items, jerk)", "B barrier", "C work (lists, validity loop)", "C barrier",
+             "D cull", "D cull barrier", "D process+slow", "D process barrier", "E work", "E barrier"]
 tot = sum(v[:12])
 for n, x in zip(names, v[:12]):
     print(f"{n:32s} {x / tot * 100:6.2f} %   {x / (nq * 12 * 10):9.0f} cycles per warp per block")
