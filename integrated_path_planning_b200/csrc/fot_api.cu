@@ -68,9 +68,10 @@ struct Options {
   int qcap = 1024;             // FOT_QCAP           collision queue entries (tests force the queue-full path)
   int fused_box = 0;           // FOT_FUSED_BOX      1: trajectory boxes in the sweep even for a resident tensor
   int stage_dyn = 1;           // FOT_STAGE_DYN      0: never stage the obstacle block in shared memory
-  int sweep = 0;               // FOT_SWEEP          0 auto (warp -> items -> generic, the first that covers the shape), 1 "items"
-                               //                    (block-queue kernel; fail if unsupported), 2 "generic" (candidate-major
-                               //                    kernel), 3 "warp" (warp-local kernel; fail if unsupported)
+  int sweep = 0;               // FOT_SWEEP          0 auto (fot_sweep_items, else the candidate-major kernel), 1 "items" (fail if
+                               //                    unsupported), 2 "generic" (candidate-major kernel), 3 "warp" (fot_sweep_warp: two
+                               //                    barriers per block + barrier-free collision queue; measured equal to "items",
+                               //                    DESIGN.md section 4c; fail if unsupported)
   int host_chunks = 0;         // FOT_HOST_CHUNKS    equal chunks of the host-pointer call (0: rule)
   std::string chunk_waves;     // FOT_CHUNK_WAVES    chunk sizes in sweep waves, "1,2,3" (+ the rest)
   int host_streams = 2;        // FOT_HOST_STREAMS   1: chunks on one compute stream
@@ -559,12 +560,12 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   size_t ismem = 0;
   bool use_items = item_geometry(h, b, &ig, &ismem, gate.word != nullptr, bpc_override);
   if (h->opt.sweep == 2) use_items = false;
-  // the warp-local kernel where its shape range allows (and nothing asks for another kernel)
+  // the two-barrier kernel on request (FOT_SWEEP=warp)
   WarpGeom wg{};
   size_t wsmem = 0;
-  bool use_warp = (h->opt.sweep == 0 || h->opt.sweep == 3) && warp_geometry(h, b, &wg, &wsmem, gate.word != nullptr, bpc_override);
+  bool use_warp = h->opt.sweep == 3 && warp_geometry(h, b, &wg, &wsmem, gate.word != nullptr, bpc_override);
   if (use_warp && gate.word && !wg.fused_box) use_warp = false;
-  if (h->opt.sweep == 3 && !use_warp) return fail(FOT_ERR_ARG, "FOT_SWEEP=warp: shape not supported by fot_sweep_warp");
+  if (h->opt.sweep == 3 && !use_warp && !gate.word) return fail(FOT_ERR_ARG, "FOT_SWEEP=warp: shape not supported by fot_sweep_warp");
   if (use_warp) {
     // same block decomposition and scratch as fot_sweep_items: the code below sizes everything from `ig`
     use_items = true;

@@ -37,6 +37,10 @@ for n, x in zip(names, v[:12]):
     print(f"{n:32s} {x / tot * 100:6.2f} %   {x / (nq * 12 * 10):9.0f} cycles per warp per block")
 print("total cycles per warp per block", tot / (nq * 12 * 10))
 
+if os.environ.get("FOT_SWEEP", "warp") in ("warp", ""):
+    print(f"warp lists: {v[13]:.3e} warp-blocks with a list, mean length {v[12] / max(v[13], 1):.1f}; queue entries per block "
+          f"{v[14] / (nq * 12):.1f}; slow items per block {v[15] / (nq * 12):.1f}")
+    sys.exit(0)
 print(f"validity screen: valid items {v[12]:.3e}, dirty items {v[13]:.3e} ({v[13] / max(v[12], 1) * 100:.1f} %), warps with valid items "
       f"{v[14] & 0xffffffff:.3e}, of them skipped {v[15]:.3e} ({v[15] / max(v[14] & 0xffffffff, 1) * 100:.1f} %), full-chain warps "
       f"{v[14] >> 32:.3e} ({(v[14] >> 32) / max(v[14] & 0xffffffff, 1) * 100:.1f} %)")
