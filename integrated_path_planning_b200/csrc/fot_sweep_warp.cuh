@@ -148,6 +148,7 @@ fot_sweep_warp(const Plan P, const Batch B, const Out O, const WarpGeom G) {
   if (!kFused && state_ok)
     for (int j = tid; j < SP; j += bd) sbox[j] = B.dyn_box[(size_t)q * SP + j];      // fot_prepass boxes: read by every warp of every block
   if (kFused) {
+    __syncthreads();                                     // the mbarrier thread 0 initialised is visible to every warp
     // box every predicted trajectory of the staged obstacle block once per CTA (what fot_prepass does for a resident
     // tensor): one warp per trajectory, fp32 rounded outward, NaN trajectory -> NaN box
     if (state_ok && G.stage_dyn) {

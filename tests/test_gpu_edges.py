@@ -173,7 +173,8 @@ def test_gated_upload_pipeline_matches_the_single_launch():
     assert len(set(ref["best_idx"].tolist())) > 20
     variants = [dict(), dict(FOT_SWEEP="warp"), dict(FOT_SWEEP="warp", FOT_GATED=0), dict(FOT_GATED=0), dict(FOT_GATED=0, FOT_HOST_STREAMS=1), dict(FOT_GATE_UPLOADS=7),
                 dict(FOT_GATE_UPLOADS=64, FOT_GATE_COPY_STREAMS=2), dict(FOT_GATE_MEMCPY=1, FOT_CHUNK_WAVES="1,1"),
-                dict(FOT_GATE_TAIL_BPC=1), dict(FOT_GATE_FLAG_STREAM=1), dict(FOT_STAGE_DYN=0), dict(FOT_STAGE_DYN=0, FOT_HOST_STREAMS=1), dict(FOT_GATED=0, FOT_HOST_CHUNKS=1, FOT_FUSED_BOX=1)]
+                dict(FOT_GATE_TAIL_BPC=1), dict(FOT_GATE_FLAG_STREAM=1), dict(FOT_STAGE_DYN=0), dict(FOT_STAGE_DYN=0, FOT_HOST_STREAMS=1), dict(FOT_GATED=0, FOT_HOST_CHUNKS=1, FOT_FUSED_BOX=1),
+                dict(FOT_SWEEP="warp", FOT_GATED=0, FOT_HOST_CHUNKS=1, FOT_FUSED_BOX=1)]
     for env in variants:
         with _env(**env):
             got = run()
