@@ -461,7 +461,7 @@ class BatchedClosedLoop:
         metrics["avg_prediction_time"] = metrics["max_prediction_time"] = self.timers["prediction"] * per_sim
         metrics["avg_planning_time"] = metrics["max_planning_time"] = (self.timers["frenet_host"] + self.timers["sweep"]) * per_sim
         ctx = {"prediction_method": "cv" if self.sampler is None else "sgan", "sgan_model": None,
-               "ego_target_speed": self.k["ego_target_speed"], "scenario_file": None, "seed": "not_set",
+               "ego_target_speed": self.k["ego_target_speed"], "scenario_file": str(None), "seed": "not_set",   # :1013 str(getattr(config, 'config_path', ...))
                "termination_reason": str(self.reason[i]), "total_time": h[-1]["time"] + self.dt if h else 0.0,
                "steps": len(h)}
         if context:
