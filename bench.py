@@ -261,6 +261,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU sample (0 = 4 x cores, 2 x cores for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gather", action="store_true", help="tuning: no winner gather in the timed loop")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: winners stored into the root's memory by the winner kernel over NVLink peer memory (default; "
+                         "falls back to nccl when CUDA IPC is unavailable), or one all_gather_into_tensor of the packed block")
     ap.add_argument("--gather-priority", type=int, default=0, help="tuning: CUDA priority of the gather stream (0 default, -1 high)")
     ap.add_argument("--brief", action="store_true", help="resident + e2e legs only (scaling experiments)")
     args = ap.parse_args()
@@ -303,7 +306,7 @@ def main():
     # ---------------- B200 arm -----------------------------------------------------------
     import torch
     import torch.distributed as dist
-    from integrated_path_planning_b200 import BatchFrenetPlanner, DeviceBatch, WinnerBlock, _lib, shard_bounds
+    from integrated_path_planning_b200 import BatchFrenetPlanner, DeviceBatch, PeerGather, WinnerBlock, _lib, shard_bounds
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the sweep has no CPU path")
@@ -352,17 +355,34 @@ def main():
 
     class ResidentLeg:
         """Inputs in HBM; per step: prepass + sweep + winner kernels and, at N > 1, the gather of the FULL winner block
-        (one contiguous buffer, one all_gather_into_tensor) on a side stream behind the sweep that produced it, N_GBUF
-        staging buffers deep, so that the next step's sweep does not wait for the slowest rank of this one.  The timed
-        region ends after the last gather has completed on every rank."""
+        (best_idx, winner_len, stats, best_cost, 15 winner series: 6.2 KB per query), inside the timed region.
+
+        gather = "peer" (default): the winner kernel itself stores the block a second time, into this rank's slice of a
+        buffer in the ROOT's memory mapped over NVLink peer memory (PeerGather / fot_set_result_mirror) -- no collective
+        call, no staging copy, nothing between two steps but the launches; the root waits on the ranks' sequence flags.
+        gather = "nccl": block copied to a staging buffer, ONE all_gather_into_tensor on a side stream behind the sweep
+        that produced it, N_GBUF buffers deep.  Either way the timed region ends when the last step's blocks are
+        complete at their destination."""
         N_GBUF = 3
 
         def __init__(self, frenet, dyn, gather=True):
             self.batch = DeviceBatch(planner, frenet, TARGET_SPEED, dyn, _lib.FOT_DYN_SINGLE)
-            self.gather = gather and world > 1
+            self.mode = (args.gather if gather and world > 1 else None)
             self.step_no = 0
-            if self.gather:
-                self.per = int(all_max(self.batch.n_q))
+            self.per = int(all_max(self.batch.n_q)) if world > 1 else self.batch.n_q
+            self.peer = None
+            if self.mode == "peer":
+                ok = 1.0
+                try:
+                    self.peer = PeerGather(eng, self.per, depth=self.N_GBUF)
+                except Exception as exc:                     # CUDA IPC not available in this container: one rank fails, all fall back
+                    print(f"[bench] rank {rank}: peer gather unavailable ({exc!r}); falling back to nccl", file=sys.stderr)
+                    ok = 0.0
+                if all_max(1.0 - ok) > 0.0:
+                    if self.peer is not None:
+                        self.peer.close()
+                    self.peer, self.mode = None, "nccl"
+            if self.mode == "nccl":
                 self.gstream = torch.cuda.Stream(device=local_rank, priority=args.gather_priority)
                 self.stage = [WinnerBlock(self.per, eng.n_t_max, device="cuda") for _ in range(self.N_GBUF)]
                 for s in self.stage:
@@ -370,10 +390,18 @@ def main():
                 self.gathered = [torch.empty((world, self.stage[0].nbytes), dtype=torch.uint8, device="cuda")
                                  for _ in range(self.N_GBUF)]
                 self.g_done = [None] * self.N_GBUF
+            self.gather = self.mode is not None
+            self.n_mirrored = 0
 
         def step(self):
+            if self.mode == "peer":
+                self.peer.attach(self.step_no)               # this launch's winners also go to buffer step_no % depth on the root
+                self.batch.launch(stream.cuda_stream)
+                self.step_no += 1
+                self.n_mirrored += 1
+                return
             self.batch.launch(stream.cuda_stream)
-            if not self.gather:
+            if self.mode != "nccl":
                 return
             k = self.step_no % self.N_GBUF
             self.step_no += 1
@@ -407,8 +435,11 @@ def main():
             for _ in range(steps):
                 self.step()
             with torch.cuda.stream(stream):
-                if self.gather:
+                if self.mode == "nccl":
                     stream.wait_stream(self.gstream)             # the timed region ends after the last gather
+                if self.mode == "peer" and rank == self.peer.root:
+                    # ... on the root: after every rank's last block has arrived (device-side wait on the sequence flags)
+                    self.peer.await_step(self.n_mirrored, stream.cuda_stream)
                 e1.record()
             sync_all()
             clocks = sampler.snapshot()
@@ -417,19 +448,48 @@ def main():
             return all_max(e0.elapsed_time(e1)) / steps, stage, clocks
 
         def verify_gather(self):
-            """Rank-order check of the last gathered block: every rank's slice must be that rank's own winners."""
+            """The last step's gathered blocks, slice by slice, against what each rank computed itself."""
             if not self.gather:
                 return None
+            n = self.batch.n_q
             k = (self.step_no - 1) % self.N_GBUF
-            mine = self.stage[k].unpack(self.gathered[k])
-            ok = all(torch.equal(mine[key][rank, :self.batch.n_q], self.batch.out[key]) for key in ("best_idx", "winner_len", "stats"))
-            ok = ok and torch.equal(mine["best_cost"][rank, :self.batch.n_q].view(torch.int64), self.batch.out["best_cost"].view(torch.int64))
-            # checksums of every rank's block as seen by this rank must agree across ranks
-            sums = mine["best_idx"].to(torch.int64).sum(dim=1) * 7 + mine["stats"].to(torch.int64).sum(dim=(1, 2))
-            ref = sums.clone()
-            dist.broadcast(ref, src=0)
-            ok = ok and bool(torch.equal(ref, sums))
+            # every rank's own (best_idx, winner_len, stats) checksum and cost bits, gathered the plain way
+            def digest(o, c):
+                # (winner rows are written up to winner_len only: the first two x samples count where a path exists)
+                head = torch.where((o["winner_len"][:c] >= 2)[:, None], o["winner"][:c, 9, :2], 0.0)
+                return torch.stack([o["best_idx"][:c].to(torch.int64).sum(), o["winner_len"][:c].to(torch.int64).sum(),
+                                    o["stats"][:c].to(torch.int64).sum(), o["best_cost"][:c].contiguous().view(torch.int64).sum(),
+                                    head.contiguous().view(torch.int64).sum()])
+            own = digest(self.batch.out, n)
+            all_own = torch.empty((world, 5), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(all_own.view(-1), own)
+            ok = True
+            if self.mode == "peer":
+                if rank == self.peer.root:
+                    ok = not self.peer.timed_out()
+                    got = self.peer.views(self.step_no - 1)
+            else:
+                got = self.stage[k].unpack(self.gathered[k])
+            if self.mode == "nccl" or rank == self.peer.root:
+                counts = [int(c) for c in all_list(n)]
+                for r in range(world):
+                    c = counts[r]
+                    seen = digest({key: v[r] for key, v in got.items()}, c)
+                    ok = ok and bool(torch.equal(seen, all_own[r]))
+                mine = got["winner"][rank, :n]
+                lens = self.batch.out["winner_len"]
+                keep = torch.arange(mine.shape[-1], device="cuda")[None, None, :] < lens[:, None, None]
+                ok = ok and bool(torch.equal(torch.where(keep, mine, 0.0).view(torch.int64),
+                                             torch.where(keep, self.batch.out["winner"], 0.0).view(torch.int64)))
+            else:
+                all_list(n)
             return bool(all_max(0.0 if ok else 1.0) == 0.0)
+
+        def close(self):
+            if self.peer is not None:
+                sync_all()
+                self.peer.close()
+                self.peer = None
 
     leg = ResidentLeg(frenet, dyn, gather=not args.no_gather)
     evals_local = leg.batch.dense_evals()
@@ -441,7 +501,9 @@ def main():
     per_rank_ms = all_list(float(stage.sum(axis=1).mean()))
     per_rank_mhz = all_list(float(clocks.get("sm_mhz") or 0.0))
     per_rank_w = all_list(float(clocks.get("power_w") or 0.0))
-    gather_bytes = leg.stage[0].nbytes if leg.gather else 0
+    gather_bytes = WinnerBlock(leg.per, eng.n_t_max, device="meta").nbytes if leg.gather else 0
+    gather_mode = leg.mode
+    leg.close()
     resident_best = leg.batch.out["best_idx"].cpu().numpy()
     resident_cost = leg.batch.out["best_cost"].cpu().numpy()
 
@@ -461,6 +523,7 @@ def main():
                  "value": ev_o / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o,
                  "per_rank_kernel_ms_per_step": all_list(float(stage_o.sum(axis=1).mean())),
                  "gather_ok": leg_o.verify_gather()}
+        leg_o.close()
         del leg_o
 
     # e2e leg: host-pointer C-ABI call, pinned inputs, H2D + kernels + D2H inside the timed region
@@ -623,9 +686,12 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "winners_match_resident": same},
             "gpu_launches": 4 * args.steps, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-            "gather": {"bytes_per_rank_per_step": int(gather_bytes), "collectives_per_step": 1 if gather_bytes else 0,
-                       "what": "full winner block (best_idx, winner_len, stats, best_cost, 15 winner series) in one "
-                               "contiguous buffer, one all_gather_into_tensor, inside the timed region",
+            "gather": {"bytes_per_rank_per_step": int(gather_bytes), "mode": gather_mode,
+                       "collectives_per_step": 1 if gather_mode == "nccl" else 0,
+                       "what": "full winner block (best_idx, winner_len, stats, best_cost, 15 winner series) of every rank, inside "
+                               "the timed region: " + ("stored into the root's memory by each rank's winner kernel over NVLink peer "
+                               "memory (fot_set_result_mirror), sequence flags awaited on the root" if gather_mode == "peer" else
+                               "one contiguous buffer, one all_gather_into_tensor"),
                        "verified": gather_ok} if world > 1 else None,
             "per_rank_kernel_ms_per_step": per_rank_ms, "per_rank_sm_mhz": per_rank_mhz, "per_rank_power_w": per_rank_w,
             "other_scaling": other,

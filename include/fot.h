@@ -27,8 +27,9 @@
 extern "C" {
 #endif
 
-#define FOT_ABI_VERSION 4   /* 2: + prediction post-processing and safety metrics; 3: + fot_plan_batch_device_to_host;
-                               4: + fot_result_t.winner_samples, fot_fetch_winners, fot_reload_options */
+#define FOT_ABI_VERSION 5   /* 2: + prediction post-processing and safety metrics; 3: + fot_plan_batch_device_to_host;
+                               4: + fot_result_t.winner_samples, fot_fetch_winners, fot_reload_options;
+                               5: + fot_set_result_mirror, fot_peer_* (gather of a sharded sweep over peer memory) */
 #define FOT_MAX_CIRCLES 8
 #define FOT_N_STATS 8    /* ok, max_speed, max_accel, max_curvature, max_lat_accel, road_bound, collision, stop_distance */
 #define FOT_N_SERIES 15  /* t s s_d s_dd s_ddd d d_d d_dd d_ddd x y yaw c v a  (data_structures.py:149-181) */
@@ -169,6 +170,27 @@ int fot_plan_batch_device_to_host(fot_handle_t* h, const fot_batch_t* batch, con
  * first queries come back while the last are still swept.  Page-locked (pinned) `batch->dyn` and
  * result arrays make those copies true asynchronous DMAs; pageable memory works but serialises. */
 int fot_plan_batch_host(fot_handle_t* h, const fot_batch_t* batch, const fot_result_t* res);
+
+/* ---- multi-GPU: the one gather of a query-sharded sweep, without a collective call -----------
+ * Queries shard over GPUs with no traffic during compute; the winners (6.2 KB per query) have to reach one place.
+ * fot_set_result_mirror gives a handle a SECOND destination for the winner block of every following
+ * fot_plan_batch_device launch: five DEVICE pointers laid out like fot_result_t's (best_idx, best_cost, stats,
+ * winner_len, winner; cand_* ignored), typically a slice of a buffer on the gather root mapped into this process over
+ * NVLink peer memory (fot_peer_open).  The winner kernel stores every value twice, locally and into the mirror, so the
+ * block is on the root when the launch completes; `flag` (device pointer, may be peer memory, or NULL) receives the
+ * number of mirrored launches since this flag word was set -- 1, 2, 3, ... -- behind each of them (a system-scope fence
+ * precedes the write).
+ * mirror = NULL switches it off. */
+int fot_set_result_mirror(fot_handle_t* h, const fot_result_t* mirror, void* flag);
+/* Peer-memory plumbing (CUDA IPC; one process per GPU): the root allocates a buffer with fot_peer_alloc and hands the
+ * 64-byte handle to the other ranks (any byte transport), which map it with fot_peer_open.  The buffer is zeroed. */
+int fot_peer_alloc(int device, size_t bytes, void** ptr, unsigned char handle[64]);
+int fot_peer_open(int device, const unsigned char handle[64], void** ptr);
+int fot_peer_close(void* ptr);
+int fot_peer_free(void* ptr);
+/* Root side: enqueue on `stream` a wait until flags[0 .. world) have all reached sequence number `seq` (what the
+ * ranks' mirrored launches publish); gives up after 2 s and sets *err_word (device pointer, 4 bytes) to 1. */
+int fot_peer_await(int device, void* stream, const void* flags, int world, unsigned seq, void* err_word);
 
 /* Full winner series of queries [q0, q0 + n) of the LAST fot_plan_batch_host / _device_to_host call on this handle,
  * from the device-resident result block into out[n][FOT_N_SERIES][n_t_max] (HOST pointer).  For callers that asked for

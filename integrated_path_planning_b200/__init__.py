@@ -6,7 +6,7 @@ plus the boundary dataclasses.  The sweep runs only through the CUDA library (in
 from .types import EgoVehicleState, FrenetPath, FrenetState
 from .spline import CubicSpline1D, CubicSpline2D
 from .planner import FrenetPlanner
-from .batch import BatchFrenetPlanner, DeviceBatch, WinnerBlock, gather_winners, shard_bounds
+from .batch import BatchFrenetPlanner, DeviceBatch, PeerGather, WinnerBlock, gather_winners, shard_bounds
 
 __all__ = ["FrenetPlanner", "BatchFrenetPlanner", "DeviceBatch", "CubicSpline1D", "CubicSpline2D",
-           "EgoVehicleState", "FrenetPath", "FrenetState", "WinnerBlock", "gather_winners", "shard_bounds"]
+           "EgoVehicleState", "FrenetPath", "FrenetState", "PeerGather", "WinnerBlock", "gather_winners", "shard_bounds"]

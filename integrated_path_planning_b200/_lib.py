@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfot.so")
 
-FOT_ABI_VERSION = 4
+FOT_ABI_VERSION = 5
 FOT_MAX_CIRCLES = 8
 FOT_N_STATS = 8
 FOT_N_SERIES = 15
@@ -78,6 +78,12 @@ SYMBOLS = (
     ("fot_plan_batch_device", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult), C.c_void_p)),
     ("fot_plan_batch_host", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult))),
     ("fot_plan_batch_device_to_host", C.c_int, (C.c_void_p, C.POINTER(FotBatch), C.POINTER(FotResult), C.c_void_p)),
+    ("fot_set_result_mirror", C.c_int, (C.c_void_p, C.POINTER(FotResult), C.c_void_p)),
+    ("fot_peer_alloc", C.c_int, (C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p)),
+    ("fot_peer_open", C.c_int, (C.c_int, C.c_char_p, C.POINTER(C.c_void_p))),
+    ("fot_peer_close", C.c_int, (C.c_void_p,)),
+    ("fot_peer_free", C.c_int, (C.c_void_p,)),
+    ("fot_peer_await", C.c_int, (C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_void_p)),
     ("fot_fetch_winners", C.c_int, (C.c_void_p, C.c_int, C.c_int, C.c_void_p)),
     ("fot_reload_options", C.c_int, (C.c_void_p,)),
     ("fot_last_kernel_ms", C.c_float, (C.c_void_p,)),

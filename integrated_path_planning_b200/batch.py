@@ -203,3 +203,101 @@ def gather_winners(out: dict, group=None, counts=None) -> dict:
     if all(c == per for c in counts):
         return {k: v.reshape((world * per,) + tuple(v.shape[2:])) for k, v in parts.items()}
     return {k: torch.cat([v[r, :counts[r]] for r in range(world)], dim=0) for k, v in parts.items()}
+
+
+class _RawCuda:
+    """A raw device pointer as something torch can wrap (`torch.as_tensor(obj, device=...)`)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather:
+    """The one gather of the query-sharded sweep without a collective call: every rank's winner block lands in the
+    ROOT's memory, stored there by that rank's own `fot_winner` kernel through NVLink peer memory
+    (fot_set_result_mirror), while the rank's next sweep is already running.
+
+    The root owns `depth` buffers of `world x WinnerBlock(cap)` bytes (fot_peer_alloc) and a flag word per rank; the
+    other ranks map them (CUDA IPC handle -> fot_peer_open; the 64-byte handles travel through torch.distributed).
+    Step k of every rank is mirrored into buffer k % depth, slice `rank`; behind it the rank publishes k + 1 in its flag
+    word.  `await_step(k)` on the root enqueues a device-side wait for all flags; `views(k)` are typed tensors
+    [world, cap, ...] into the buffer.  One process per GPU, one handle per process.
+    """
+
+    def __init__(self, engine: SweepEngine, cap: int, group=None, root: int = 0, depth: int = 2):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.engine, self.lib, self.root, self.depth = engine, engine.lib, int(root), int(depth)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dev = torch.device("cuda", engine.device)
+        self.layout = WinnerBlock(cap, engine.n_t_max, device="meta")             # offsets only
+        self.nbytes = self.layout.nbytes
+        self.flag_bytes = 256 * ((4 * self.world + 255) // 256)
+        total = self.depth * self.world * self.nbytes + self.flag_bytes + 256
+        handle = torch.zeros(64, dtype=torch.uint8)
+        self._base = C.c_void_p()
+        self._owned = self.rank == self.root
+        if self._owned:
+            buf = C.create_string_buffer(64)
+            _lib.check(self.lib.fot_peer_alloc(engine.device, total, C.byref(self._base), buf), "fot_peer_alloc")
+            handle = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        h_dev = handle.to(self.dev)
+        dist.broadcast(h_dev, src=dist.get_global_rank(group, self.root) if group is not None else self.root, group=group)
+        if not self._owned:
+            raw = bytes(h_dev.cpu().numpy().tobytes())
+            _lib.check(self.lib.fot_peer_open(engine.device, raw, C.byref(self._base)), "fot_peer_open")
+        self.base = int(self._base.value)
+        self.flags_ptr = self.base + self.depth * self.world * self.nbytes
+        self.err_ptr = self.flags_ptr + self.flag_bytes
+        self.step = 0
+
+    def _slice_ptr(self, k: int, rank: int) -> int:
+        return self.base + ((k % self.depth) * self.world + rank) * self.nbytes
+
+    def attach(self, k: Optional[int] = None) -> None:
+        """The engine's next fot_plan_batch_device launch mirrors its winner block into buffer k % depth (default: the
+        running step counter, which then advances)."""
+        import ctypes as C
+        if k is None:
+            k = self.step
+            self.step += 1
+        p = self._slice_ptr(k, self.rank)
+        m = _lib.FotResult()
+        off = self.layout.offsets
+        m.best_idx, m.winner_len, m.stats = p + off["best_idx"][0], p + off["winner_len"][0], p + off["stats"][0]
+        m.best_cost, m.winner = p + off["best_cost"][0], p + off["winner"][0]
+        _lib.check(self.lib.fot_set_result_mirror(self.engine._h, C.byref(m), C.c_void_p(self.flags_ptr + 4 * self.rank)),
+                   "fot_set_result_mirror")
+
+    def detach(self) -> None:
+        _lib.check(self.lib.fot_set_result_mirror(self.engine._h, None, None), "fot_set_result_mirror")
+
+    def await_step(self, seq: int, stream: Optional[int] = None) -> None:
+        """Root: enqueue a wait until every rank has published launch number `seq` (1-based count of its mirrored
+        launches)."""
+        import ctypes as C
+        assert self._owned, "await_step is a root-side call"
+        _lib.check(self.lib.fot_peer_await(self.engine.device, C.c_void_p(stream) if stream else None, C.c_void_p(self.flags_ptr),
+                                           self.world, int(seq), C.c_void_p(self.err_ptr)), "fot_peer_await")
+
+    def views(self, k: int) -> dict:
+        """Root: the gathered blocks of step k as tensors [world, cap, ...] (views into the peer buffer)."""
+        import torch
+        assert self._owned
+        raw = torch.as_tensor(_RawCuda(self._slice_ptr(k, 0), self.world * self.nbytes), device=self.dev)
+        return self.layout.unpack(raw.view(self.world, self.nbytes))
+
+    def timed_out(self) -> bool:
+        import torch
+        assert self._owned
+        return bool(torch.as_tensor(_RawCuda(self.err_ptr, 4), device=self.dev).view(torch.int32).item())
+
+    def close(self) -> None:
+        if self._base is not None and self._base.value:
+            self.detach()
+            if self._owned:
+                self.lib.fot_peer_free(self._base)
+            else:
+                self.lib.fot_peer_close(self._base)
+            self._base = None

@@ -131,6 +131,9 @@ struct fot_handle {
   int sms = 148;                     // SM count of the device (block-per-CTA grouping, host chunk sizes)
   Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_box, cost_tab;   // device scratch
   int last_sweep_kind = 0;           // 1: fot_sweep_items, 2: fot_sweep (generic)
+  fot_result_t mirror{};             // fot_set_result_mirror: second destination of the winner block (all null: none)
+  unsigned* mirror_flag = nullptr;   // word published behind each mirrored launch (fot_set_result_mirror), or null
+  unsigned mirror_seq = 0;
   const double* last_winner_d = nullptr;   // full winner series of the last host-result call (device, in out_d)
   int last_winner_nq = 0;
   Buf stage_h, stage_d, out_d, dyn_d, stat_d;   // host-API staging
@@ -634,6 +637,10 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   O.best_idx = r->best_idx; O.best_cost = r->best_cost; O.stats = r->stats; O.winner_len = r->winner_len;
   O.winner = r->winner; O.cand_cat = r->cand_cat; O.cand_cost = r->cand_cost; O.cand_stride = r->cand_stride;
   O.part_cost = (double*)h->part_cost.p + q_off * part_stride; O.part_idx = (int32_t*)h->part_idx.p + q_off * part_stride;
+  if (h->mirror.winner && q_off == 0 && q_total == (size_t)b->n_q) {     // whole-batch launches only (fot_plan_batch_device)
+    O.m_best_idx = h->mirror.best_idx; O.m_best_cost = h->mirror.best_cost; O.m_stats = h->mirror.stats;
+    O.m_winner_len = h->mirror.winner_len; O.m_winner = h->mirror.winner;
+  }
 
   cudaEvent_t* ring = h->ring.data() + (size_t)(h->n_launch % fot_handle::kRing) * 4;
   if (record_span) CK(cudaEventRecord(h->ev0, st));
@@ -679,6 +686,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
   h->last_sweep_kind = use_warp ? 3 : use_items ? 1 : 2;
   CK(cudaEventRecord(ring[2], st));
   fot_winner<<<b->n_q, 128, (size_t)kTT * h->plan.n_t_max * sizeof(double), st>>>(h->plan, B, O, g);
+  if (O.m_winner && h->mirror_flag) fot_publish_kernel<<<1, 1, 0, st>>>(h->mirror_flag, ++h->mirror_seq);
   CK(cudaEventRecord(ring[3], st));
   if (record_span) CK(cudaEventRecord(h->ev1, st));
   h->n_launch++;
@@ -1135,6 +1143,58 @@ static int plan_batch_device_to_host_impl(fot_handle_t* h, const fot_batch_t* b,
   if (rc != FOT_OK) return rc;
   CK(cudaStreamSynchronize(h->d2h_stream));
   for (int c = 0; c < n_ranges; ++c) CK(cudaStreamSynchronize(h->pstream[c & 3]));
+  return FOT_OK;
+}
+
+// ---- the gather of a sharded sweep over peer memory ---------------------------------------------------------------
+extern "C" int fot_set_result_mirror(fot_handle_t* h, const fot_result_t* mirror, void* flag) {
+  if (!h) return fail(FOT_ERR_ARG, "fot_set_result_mirror: null handle");
+  if (!mirror) { h->mirror = fot_result_t{}; h->mirror_flag = nullptr; h->mirror_seq = 0; return FOT_OK; }
+  if (!mirror->best_idx || !mirror->best_cost || !mirror->stats || !mirror->winner_len || !mirror->winner)
+    return fail(FOT_ERR_ARG, "fot_set_result_mirror: null mirror array");
+  h->mirror = *mirror;
+  if ((unsigned*)flag != h->mirror_flag) h->mirror_seq = 0;     // a new flag word starts a new sequence: 1, 2, 3, ...
+  h->mirror_flag = (unsigned*)flag;
+  return FOT_OK;
+}
+
+extern "C" int fot_peer_alloc(int device, size_t bytes, void** ptr, unsigned char handle[64]) {
+  if (!ptr || !handle || bytes == 0) return fail(FOT_ERR_ARG, "fot_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaSetDevice(device));
+  CK(cudaMalloc(ptr, bytes));
+  CK(cudaMemset(*ptr, 0, bytes));
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, *ptr);
+  if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return fail(FOT_ERR_CUDA, "cudaIpcGetMemHandle", e); }
+  memcpy(handle, &hd, 64);
+  return FOT_OK;
+}
+
+extern "C" int fot_peer_open(int device, const unsigned char handle[64], void** ptr) {
+  if (!ptr || !handle) return fail(FOT_ERR_ARG, "fot_peer_open: bad argument");
+  CK(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  CK(cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return FOT_OK;
+}
+
+extern "C" int fot_peer_close(void* ptr) {
+  if (ptr) CK(cudaIpcCloseMemHandle(ptr));
+  return FOT_OK;
+}
+
+extern "C" int fot_peer_free(void* ptr) {
+  if (ptr) CK(cudaFree(ptr));
+  return FOT_OK;
+}
+
+extern "C" int fot_peer_await(int device, void* stream, const void* flags, int world, unsigned seq, void* err_word) {
+  if (!flags || !err_word || world < 1 || world > 1024) return fail(FOT_ERR_ARG, "fot_peer_await: bad argument");
+  CK(cudaSetDevice(device));
+  fot_await_kernel<<<1, (world + 31) / 32 * 32, 0, (cudaStream_t)stream>>>((const unsigned*)flags, world, seq, 2000000000ll, (unsigned*)err_word);
+  CK(cudaGetLastError());
   return FOT_OK;
 }
 

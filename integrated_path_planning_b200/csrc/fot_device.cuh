@@ -46,6 +46,9 @@ struct Out {
   int32_t* best_idx; double* best_cost; int32_t* stats; int32_t* winner_len; double* winner;
   uint8_t* cand_cat; double* cand_cost; int32_t cand_stride;
   double* part_cost; int32_t* part_idx;   // [n_q][blocks_per_query] partial arg-min
+  // Mirror of the winner block (fot_set_result_mirror): a second set of result arrays -- typically PEER memory on the
+  // gather root of a multi-GPU job, mapped over NVLink -- that fot_winner writes together with the local ones.  All null: none.
+  int32_t* m_best_idx; double* m_best_cost; int32_t* m_stats; int32_t* m_winner_len; double* m_winner;
 };
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }

@@ -801,8 +801,13 @@ fot_winner(const Plan P, const Batch B, const Out O, const SweepGeom G) {
   c = s_cost[0]; i = s_idx[0];
   for (int w = 1; w < (int)(blockDim.x >> 5); ++w) argmin_merge(c, i, s_cost[w], s_idx[w]);
   double* W = O.winner + (size_t)q * FOT_N_SERIES * NT;
+  double* MW = O.m_winner ? O.m_winner + (size_t)q * FOT_N_SERIES * NT : nullptr;       // mirror (peer memory), see Out
+  if (O.m_stats && tid < FOT_N_STATS) O.m_stats[(size_t)q * FOT_N_STATS + tid] = O.stats[(size_t)q * FOT_N_STATS + tid];   // final since the sweep
   if (i == 0x7fffffff) {
-    if (tid == 0) { O.best_idx[q] = -1; O.best_cost[q] = INFINITY; O.winner_len[q] = 0; }
+    if (tid == 0) {
+      O.best_idx[q] = -1; O.best_cost[q] = INFINITY; O.winner_len[q] = 0;
+      if (O.m_best_idx) { O.m_best_idx[q] = -1; O.m_best_cost[q] = INFINITY; O.m_winner_len[q] = 0; }
+    }
     return;
   }
   const double* fs = B.frenet + 6 * (size_t)q;
@@ -835,12 +840,42 @@ fot_winner(const Plan P, const Batch B, const Out O, const SweepGeom G) {
     W[5 * NT + n] = d;   W[6 * NT + n] = dd;  W[7 * NT + n] = ddd; W[8 * NT + n] = lat_p3(lat, tt, n);
     W[9 * NT + n] = cp.x; W[10 * NT + n] = cp.y; W[11 * NT + n] = wrap_angle(cp.ang);
     W[12 * NT + n] = cp.kappa; W[13 * NT + n] = cp.v; W[14 * NT + n] = cp.a;
+    if (MW) {
+      // the same values into the mirror: plain stores, which the memory system carries over NVLink when the mirror is
+      // a peer's memory -- the gather of the sharded sweep happens here, without a collective call
+#pragma unroll
+      for (int r = 0; r < FOT_N_SERIES; ++r) MW[r * NT + n] = W[r * NT + n];
+    }
   }
   __syncthreads();
   if (tid == 0) {
     O.best_idx[q] = i;
     O.best_cost[q] = c;
     O.winner_len[q] = s_first_nan < N ? s_first_nan : N;
+    if (O.m_best_idx) { O.m_best_idx[q] = i; O.m_best_cost[q] = c; O.m_winner_len[q] = s_first_nan < N ? s_first_nan : N; }
+  }
+}
+
+// One word per rank in the gather root's memory: the sequence number of the last step whose winner block is complete
+// there.  Launched behind fot_winner in stream order; the fence makes the mirror stores visible system-wide first.
+__global__ void fot_publish_kernel(unsigned* flag, unsigned seq) {
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned*>(flag) = seq;
+}
+// Root side: wait (bounded) until every rank has published `seq` or later.  err: set to 1 on time-out.
+__global__ void fot_await_kernel(const unsigned* flags, int world, unsigned seq, long long timeout_ns, unsigned* err) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+    if ((int)(v - seq) >= 0) break;
+    long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (now - t0 > timeout_ns) { *err = 1u; break; }
+    __nanosleep(200);
   }
 }
 
