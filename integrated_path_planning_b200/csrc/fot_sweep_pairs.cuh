@@ -1,0 +1,797 @@
+// fot_sweep_pairs.cuh -- the pair-per-warp sweep kernel (sm_100a, fp64).
+//
+// Same contract and the same arithmetic as fot_sweep_items (fot_sweep_items.cuh): every candidate's validity
+// flags, collision verdict, category and cost come out bit-identical.  What changes is who waits for whom.
+// fot_sweep_items cuts a query into blocks of six longitudinal profiles and walks its 320 threads through six
+// block-wide barriers per block; ncu charges 3.1 stall cycles per issued instruction to those barriers, and
+// fot_sweep_warp (fewer barriers, a shared producer/consumer queue) only moved the wait into the queue.  Here the
+// unit of work is ONE PAIR = one longitudinal profile (horizon T_j, terminal speed v_k) or one brake horizon,
+// and a pair belongs to ONE WARP from its first instruction to its last:
+//
+//   CTA    = one query (or 1/ctas_per_query of its pairs for small batches): obstacle block staged once by a
+//            bulk copy, spline tables, lateral grid and the query's scalars in shared memory;
+//   warp   = fetches the next pair of the query from a shared counter (longest horizons first) and does everything
+//            for it -- item set-up, validity chain, low-speed tests, obstacle list, window cull, exact distance
+//            tests, category, cost, arg-min -- out of a private slice of shared memory;
+//   lane   = sample t_n of the pair (passes of 32 samples); the loop runs over the lateral targets d_i.
+//
+// There is no __syncthreads() between the CTA's set-up and its final arg-min: warps never wait for each other,
+// the phases of different warps decorrelate (one warp's latency-bound set-up chain overlaps another's FP64-bound
+// validity loop), and an expensive pair delays nobody.  Because all 32 lanes of a warp work on the same pair,
+// the per-candidate state is warp-uniform: flags are OR-reduced by one `redux` and stored by one lane without
+// atomics, the clean masks and decisive-hit words are plain words, the survivor queue is filled by ballot +
+// prefix count, and the exact tests run a uniform loop over the live candidates with one ballot each.
+//
+// Reference citations as in fot_sweep_items.cuh (fp.py = src/planning/frenet_planner.py, cs.py = cubic_spline.py,
+// cc.py = src/core/coordinate_converter.py).
+#pragma once
+#include <type_traits>
+#include "fot_sweep_items.cuh"
+
+namespace fot {
+
+#ifndef FOT_PAIR_THREADS
+#define FOT_PAIR_THREADS 320
+#endif
+#ifndef FOT_PAIR_MIN_CTAS
+#define FOT_PAIR_MIN_CTAS 2
+#endif
+constexpr int kPairThreads = FOT_PAIR_THREADS;   // largest CTA of fot_sweep_pairs
+constexpr int kPairList = 64;                    // obstacle list entries per cull chunk (per warp)
+constexpr int kPairQueue = 64;                   // survivor queue entries (per warp): < 32 pending + <= 32 new
+
+struct PairGeom {
+  int32_t warps;             // warps per CTA
+  int32_t ctas_per_query;    // CTAs that share one query's pairs (1 in large batches)
+  int32_t nw4, nwc, vwords;  // flag words (4 candidates each) / mask words (32 candidates each) / violation words per candidate
+  int32_t stage_dyn;         // 1: the query's obstacle block is staged in shared memory by one bulk copy
+  int32_t spline_smem;       // 1: spline tables copied to shared memory
+  int32_t box_smem;          // 1: trajectory boxes in shared memory (copied from fot_prepass, or built here when fused_box)
+  int32_t fused_box;         // 1: boxes built by the CTA from its staged block (gated host-pointer call)
+  int32_t n_zero;            // u32 words zeroed per pair, starting at w_flags (flags | hit words | violation bitmaps)
+  int32_t wbytes;            // bytes of one warp's private slice
+  // byte offsets into dynamic shared memory (CTA-wide)
+  int32_t o_qc, o_dgrid, o_spl, o_dyn, o_box, o_warp;
+  // byte offsets inside a warp's slice
+  int32_t w_row, w_flags, w_hit, w_viol, w_clean, w_list, w_qoff, w_qn, w_slow;
+  // gated launch (see ItemGeom)
+  int32_t gate_q0, gate_per;
+  uint32_t gate_epoch;
+  unsigned* gate;
+};
+
+template <bool kFused>
+__global__ void __launch_bounds__(kPairThreads, FOT_PAIR_MIN_CTAS)
+fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
+  extern __shared__ __align__(16) unsigned char smb[];
+  double* qc = reinterpret_cast<double*>(smb + G.o_qc);        // fs[6] | limits[4] | target | stop_dist | v_grid[n_v_max]
+  double* dgrid = reinterpret_cast<double*>(smb + G.o_dgrid);  // [n_d]
+  double* spl = reinterpret_cast<double*>(smb + G.o_spl);      // [9][nx] when spline_smem
+  const double2* dynst = reinterpret_cast<const double2*>(smb + G.o_dyn);   // [SP][T_obs] when stage_dyn
+  float4* sbox = reinterpret_cast<float4*>(smb + G.o_box);     // [SP] trajectory boxes when box_smem
+  __shared__ int s_next;                 // next pair of this CTA
+  __shared__ int s_stats[FOT_N_STATS];
+  __shared__ double s_cost[kPairThreads / 32];
+  __shared__ int s_idx[kPairThreads / 32];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_abort;
+
+  const int NT = P.n_t_max;
+  const int q = blockIdx.x / G.ctas_per_query;
+  const int cta = blockIdx.x - q * G.ctas_per_query;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, bd = blockDim.x;
+  const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+  const double* fsg = B.frenet + 6 * (size_t)q;
+  const int n_v = B.n_v[q];
+  const int n_d = P.cfg.n_d;
+  const double dt = P.cfg.dt;
+  const size_t part = (size_t)q * G.ctas_per_query + cta;
+  // A non-finite Frenet state makes every sample of every candidate non-finite: the reference drops
+  // them all silently (empty / non-finite guards fp.py:933-946).
+  const bool state_ok = fabs(fsg[0]) + fabs(fsg[1]) + fabs(fsg[2]) + fabs(fsg[3]) + fabs(fsg[4]) + fabs(fsg[5]) < INFINITY;
+
+  const bool has_dyn = B.dyn_raw != nullptr;
+  const int SP = has_dyn ? B.S * B.P : 0;
+  const int M = B.static_raw ? B.n_static : 0;
+  const double2* dyn_q = has_dyn ? reinterpret_cast<const double2*>(B.dyn_raw) + (size_t)q * SP * B.T_obs : nullptr;
+  const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
+
+  // this warp's private slice
+  unsigned char* wb = smb + G.o_warp + (size_t)wid * G.wbytes;
+  double* row = reinterpret_cast<double*>(wb + G.w_row);            // [kRowW][NT] item rows of the current pair, field-major:
+                                                                    // lane = sample reads and writes are conflict-free
+  auto R = [&](int f, int n_) -> double& { return row[f * NT + n_]; };   // rx ry cos sin | kappa s 1/s_dot s_dot | A0 B0 A1 B1
+  unsigned* flags = reinterpret_cast<unsigned*>(wb + G.w_flags);    // [nw4]
+  unsigned* hitw = reinterpret_cast<unsigned*>(wb + G.w_hit);       // [nwc] decisive collision
+  unsigned* viol = reinterpret_cast<unsigned*>(wb + G.w_viol);      // [n_d][vwords]
+  unsigned* cleanw = reinterpret_cast<unsigned*>(wb + G.w_clean);   // [nwc] kinematically clean
+  unsigned* wl = reinterpret_cast<unsigned*>(wb + G.w_list);        // [kPairList] element offsets (bit 31: static)
+  unsigned* q_off = reinterpret_cast<unsigned*>(wb + G.w_qoff);     // [kPairQueue] survivor: obstacle element offset
+  unsigned short* q_n = reinterpret_cast<unsigned short*>(wb + G.w_qn);      // [kPairQueue] survivor: sample
+  unsigned short* slowq = reinterpret_cast<unsigned short*>(wb + G.w_slow);  // [NT] samples with a low-speed candidate
+
+  // ---- once per CTA ---------------------------------------------------------------------------------
+  if (kFused && G.gate) {
+    // this query's slice of the obstacle tensor has been uploaded once the slice flag carries the call's epoch
+    if (tid == 0) {
+      const unsigned* flag = G.gate + (G.gate_q0 + q) / G.gate_per;
+      int abort_ = 0;
+      long long t0 = 0;
+      for (unsigned spins = 0;; ++spins) {
+        unsigned seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (seen == G.gate_epoch) break;
+        __nanosleep(spins < 64 ? 100 : FOT_GATE_SLEEP_NS);
+        long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (now - t0 > kGateTimeoutNs) { abort_ = 1; G.gate[kGateSlices] = 1u; break; }
+      }
+      asm volatile("fence.proxy.async.global;" ::: "memory");      // the bulk copy below reads what the upload wrote
+      s_abort = abort_;
+    }
+    __syncthreads();
+    if (s_abort) return;
+  }
+  const bool staged = G.stage_dyn && state_ok;
+  if (tid == 0) {
+    if (staged) {
+      mbar_init(&s_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t bytes = (uint32_t)SP * (uint32_t)B.T_obs * 16u;
+      mbar_expect_tx(&s_bar, bytes);
+      tma_bulk_g2s(smb + G.o_dyn, dyn_q, bytes, &s_bar);
+    }
+    s_next = 0;
+  }
+  if (tid < FOT_N_STATS) s_stats[tid] = 0;
+  for (int i = tid; i <= n_d; i += bd) dgrid[i] = i < n_d ? P.d_grid[i] : 0.0;   // [n_d]: the brake ladder's single target
+  if (tid < 6) qc[tid] = fsg[tid];
+  else if (tid < 10) qc[tid] = B.limits[4 * (size_t)q + tid - 6];
+  else if (tid == 10) qc[10] = B.target[q];
+  else if (tid == 11) qc[11] = B.stop_dist[q];
+  for (int i = tid; i < n_v; i += bd) qc[12 + i] = B.v_grid[(size_t)q * B.n_v_max + i];
+  if (G.spline_smem) {
+    const int nx = P.cfg.nx;
+    for (int i = tid; i < nx; i += bd) {
+      spl[i] = P.knots[i];
+      spl[nx + i] = P.xa[i];      spl[3 * nx + i] = P.xc[i];
+      spl[5 * nx + i] = P.ya[i];  spl[7 * nx + i] = P.yc[i];
+      if (i < nx - 1) {
+        spl[2 * nx + i] = P.xb[i]; spl[4 * nx + i] = P.xd[i];
+        spl[6 * nx + i] = P.yb[i]; spl[8 * nx + i] = P.yd[i];
+      }
+    }
+  }
+  if (G.box_smem && !G.fused_box && state_ok)
+    for (int j = tid; j < SP; j += bd) sbox[j] = B.dyn_box[(size_t)q * SP + j];
+  __syncthreads();
+  if (kFused && G.fused_box && staged) {
+    // box every predicted trajectory of the staged obstacle block (what fot_prepass does for a resident tensor):
+    // one warp per trajectory, fp32 rounded outward, NaN trajectory -> NaN box
+    mbar_wait(&s_bar, 0u);
+    for (int j = wid; j < SP; j += bd >> 5) {
+      const double2* src = dynst + (size_t)j * B.T_obs;
+      double xlo = INFINITY, xhi = -INFINITY, ylo = INFINITY, yhi = -INFINITY;
+      bool bad = false;
+      for (int k = lane; k < B.T_obs; k += 32) {
+        const double2 o = src[k];
+        bad |= (o.x != o.x) || (o.y != o.y);
+        xlo = fmin(xlo, o.x); xhi = fmax(xhi, o.x); ylo = fmin(ylo, o.y); yhi = fmax(yhi, o.y);
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        xlo = fmin(xlo, __shfl_xor_sync(full, xlo, off)); xhi = fmax(xhi, __shfl_xor_sync(full, xhi, off));
+        ylo = fmin(ylo, __shfl_xor_sync(full, ylo, off)); yhi = fmax(yhi, __shfl_xor_sync(full, yhi, off));
+      }
+      bad = __any_sync(full, bad);
+      if (lane == 0) {
+        const float nanf_ = __int_as_float(0x7fc00000);
+        sbox[j] = bad ? make_float4(nanf_, nanf_, nanf_, nanf_)
+                      : make_float4(__double2float_rd(xlo), __double2float_ru(xhi), __double2float_rd(ylo), __double2float_ru(yhi));
+      }
+    }
+    __syncthreads();
+  }
+
+  const double* fs = qc;                 // the query's Frenet state, from shared memory
+  const double* lim = qc + 6;
+  const bool brake_on = fs[1] > 0.1 && P.cfg.n_B > 0;                          // fp.py:469 BRAKE_MIN_SPEED
+  const int n_grid = P.cfg.n_T * n_v;
+  const int n_units = n_grid + (brake_on ? P.cfg.n_B : 0);
+  const float rcp_nv = 1.0f / (float)n_v;
+
+  if (!state_ok) {
+    if (O.cand_cat || O.cand_cost) {
+      const int n_all = n_grid * n_d + (brake_on ? P.cfg.n_B : 0);
+      for (int c = cta * bd + tid; c < n_all; c += G.ctas_per_query * bd) {
+        if (O.cand_cat) O.cand_cat[(size_t)q * O.cand_stride + c] = (uint8_t)FOT_CAT_DROP;
+        if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + c] = qnan();
+      }
+    }
+    if (tid == 0) { O.part_cost[part] = INFINITY; O.part_idx[part] = -1; }
+    return;
+  }
+
+  // ---- per-CTA constants of the validity chain and the collision tests -----------------------------
+  const int n_circ = P.cfg.n_circles;
+  double max_off = 0.0;                                  // footprint circles sit within max|offset| of the path point
+  for (int i = 0; i < n_circ; ++i) max_off = fmax(max_off, fabs(P.cfg.circle_offsets[i]));
+  const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
+  const double r2_dyn = dist_mode ? P.cfg.collide_r2 : P.cfg.collide_r2_single;   // fp.py:1099-1104, :1173
+  const double rc_s = sqrt(P.cfg.collide_r2) * (1.0 + 1e-9) + 1e-9 + max_off;
+  const double rc_d = sqrt(r2_dyn) * (1.0 + 1e-9) + 1e-9 + max_off;
+  const double wroad = fmax(P.cfg.max_road_width + 1e-9, fabs(fs[3]));
+  const float pad = __double2float_ru(wroad + fmax(rc_s, rc_d));
+  const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
+  const bool budget = dist_mode && max_viol > 0;
+  const double inf = INFINITY;
+  // squared limits; a negative limit rejects every checked sample, as `x > negative` does in the reference
+  // (warp-uniform: pushed through redux so that they live in uniform registers)
+  auto uni = [&](double x) {
+    const unsigned lo = __reduce_or_sync(full, (unsigned)__double2loint(x));
+    const unsigned hi = __reduce_or_sync(full, (unsigned)__double2hiint(x));
+    return __hiloint2double((int)hi, (int)lo);
+  };
+  const double vmax2 = uni(lim[0] < 0.0 ? -inf : lim[0] * lim[0]);
+  const double amax2 = uni(lim[1] < 0.0 ? -inf : lim[1] * lim[1]);
+  const double kmax2 = uni(lim[2] < 0.0 ? -inf : lim[2] * lim[2]);
+  const double latmax2 = uni(lim[3] < 0.0 ? -inf : lim[3] * lim[3]);
+  const double road_thr = P.cfg.max_road_width + 1e-9;                         // fp.py:982
+  const double tele_thr = fmax(lim[0], P.cfg.max_speed) * dt * 3.0;            // fp.py:955
+  const double tele2 = uni(tele_thr * tele_thr);
+  const double fast2 = 0.25;                                                   // v > 0.5 (fp.py:1019)
+  const double stop_dist = qc[11];
+  const double kTan01Sq = 0.010067046422495888;                                // tan(0.1)^2
+  SplineView V;
+  V.nx = P.cfg.nx;
+  if (G.spline_smem) {
+    const int nx = V.nx;
+    V.knots = spl; V.xa = spl + nx; V.xb = spl + 2 * nx; V.xc = spl + 3 * nx; V.xd = spl + 4 * nx;
+    V.ya = spl + 5 * nx; V.yb = spl + 6 * nx; V.yc = spl + 7 * nx; V.yd = spl + 8 * nx;
+  } else {
+    V.knots = P.knots; V.xa = P.xa; V.xb = P.xb; V.xc = P.xc; V.xd = P.xd;
+    V.ya = P.ya; V.yb = P.yb; V.yc = P.yc; V.yd = P.yd;
+  }
+  const float4* boxes = G.box_smem ? sbox : B.dyn_box + (size_t)q * SP;
+
+  double my_cost = INFINITY;             // running arg-min over every pair this lane has seen
+  int my_idx = 0x7fffffff;
+  int my_stat = 0;                       // lane k < FOT_N_STATS: candidates of category k
+  bool dyn_ready = !(G.stage_dyn && SP > 0) || (kFused && G.fused_box);
+
+  for (;;) {
+    // ---- next pair of this CTA: longest horizons first, the brake ladder last ----------------------
+    int fetch = 0;
+    if (lane == 0) fetch = atomicAdd(&s_next, 1);
+    fetch = __shfl_sync(full, fetch, 0);
+    const int ord = cta + fetch * G.ctas_per_query;
+    if (ord >= n_units) break;
+    const bool brake = ord >= n_grid;
+    int jT = 0, kk, N, n_dl;
+    if (!brake) {
+      const int u = n_grid - 1 - ord;
+      jT = __float2int_rz(((float)u + 0.5f) * rcp_nv);      // u / n_v (exact: u < 2^20)
+      kk = u - jT * n_v;
+      N = P.n_steps[jT] + 1;
+      n_dl = n_d;
+    } else {
+      kk = ord - n_grid;
+      N = P.cfg.n_total;
+      n_dl = 1;
+    }
+    const int cand0 = brake ? n_grid * n_d + kk : (jT * n_v + kk) * n_d;      // generation order (fp.py:398-449)
+    const double* dg = dgrid + (brake ? n_d : 0);             // lateral targets of this pair (brake: the single 0.0 slot)
+
+    // ---- phase A: the pair's private state -----------------------------------------------------------
+#pragma unroll 1
+    for (int i = lane; i < G.n_zero; i += 32) flags[i] = 0u;                   // flags | hit words | violation bitmaps
+    __syncwarp();
+
+    // ---- phases B + C, 32 samples at a time ---------------------------------------------------------
+    int fn = 0x7fffffff;                                   // first sample with a NaN reference point
+    int nslow = 0;
+    unsigned bxlo = 0xffffffffu, bxhi = 0u, bylo = 0xffffffffu, byhi = 0u;    // box of the reference points (ordered-uint floats)
+    for (int n0 = 0; n0 < N; n0 += 32) {
+      const int n = n0 + lane;
+      const bool active = n < N;
+      double i_rx = 0, i_ry = 0, i_cth = 0, i_sth = 0, i_rk = 0, i_rdk = 0, i_sd = 0, i_sdd = 0, i_isd = 0;
+      double A0 = 0, B0 = 0, A1 = 0, B1 = 0, A2 = 0, B2 = 0;
+      if (active) {
+        // quartic solve of the pair (fp.py:619-647) -- a dozen flops per lane, all lanes alike
+        Lon L;
+        if (!brake)
+          L = lon_solve(fs, qc[12 + kk], P.T[jT], P.inv4 + 4 * jT, n_v == 1, N - 1);
+        else
+          L = lon_solve(fs, 0.0, P.Tb[kk], P.inv4b + 4 * kk, true, P.n_steps_b[kk]);
+        const bool held = n > L.hold;                                              // fp.py:487-499 brake padding
+        const TPow tp = tpow(held ? L.hold : n, dt);
+        const double s = L.a0 + L.a1 * tp.t + L.a2 * tp.t2 + L.a3 * tp.t3 + L.a4 * tp.t4;             // fp.py:644
+        i_sd = held ? 0.0 : L.a1 + 2.0 * L.a2 * tp.t + 3.0 * L.a3 * tp.t2 + 4.0 * L.a4 * tp.t3;      // fp.py:645
+        i_sdd = held ? 0.0 : 2.0 * L.a2 + 6.0 * L.a3 * tp.t + 12.0 * L.a4 * tp.t2;                    // fp.py:646
+        const RefFast rp = spline_ref_fast(V, s);
+        i_rx = rp.rx; i_ry = rp.ry; i_cth = rp.cth; i_sth = rp.sth; i_rk = rp.rk; i_rdk = rp.rdk;
+        i_isd = fabs(i_sd) > 1e-3 ? rcp_nr(i_sd) : 0.0;                            // fp.py:792 EPS_S_DOT
+        // lateral basis at this sample: d_i(t) = A(t) + d_i * B(t) (the quintic's right-hand side is linear
+        // in the target, fp.py:676-683); Horner with running derivatives
+        double c0, c1, c2, c3, c4, c5, b3, b4, b5;
+        if (!brake) {
+          const double T = P.T[jT];
+          const double* Ai = P.inv5 + 9 * jT;
+          c0 = fs[3]; c1 = fs[4]; c2 = fs[5] / 2.0;
+          const double r0 = -c0 - c1 * T - c2 * T * T, r1 = -c1 - 2.0 * c2 * T, r2 = -2.0 * c2;
+          c3 = fma(r2, Ai[2], fma(r1, Ai[1], r0 * Ai[0]));
+          c4 = fma(r2, Ai[5], fma(r1, Ai[4], r0 * Ai[3]));
+          c5 = fma(r2, Ai[8], fma(r1, Ai[7], r0 * Ai[6]));
+          b3 = Ai[0]; b4 = Ai[3]; b5 = Ai[6];
+        } else {                                                                   // one lateral profile per brake horizon (fp.py:480-482)
+          const Lat Lb = lat_solve(fs, fs[3], P.Tb[kk], P.inv5b + 9 * kk, true, P.n_steps_b[kk]);
+          c0 = Lb.a0; c1 = Lb.a1; c2 = Lb.a2; c3 = Lb.a3; c4 = Lb.a4; c5 = Lb.a5;
+          b3 = b4 = b5 = 0.0;
+        }
+        {
+          const double t = tp.t;
+          double pA = fma(c5, t, c4), dA = c5, ddA;
+          ddA = dA;               dA = fma(dA, t, pA);  pA = fma(pA, t, c3);
+          ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c2);
+          ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c1);
+          ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c0);
+          double pB = fma(b5, t, b4), dB = b5, ddB;
+          ddB = dB;               dB = fma(dB, t, pB);  pB = fma(pB, t, b3);
+          ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
+          ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
+          ddB = fma(ddB, t, dB);  dB = fma(dB, t, pB);  pB = pB * t;
+          A0 = pA; B0 = pB;
+          A1 = held ? 0.0 : dA;        B1 = held ? 0.0 : dB;
+          A2 = held ? 0.0 : 2.0 * ddA; B2 = held ? 0.0 : 2.0 * ddB;
+        }
+        R(0, n) = i_rx; R(1, n) = i_ry; R(2, n) = i_cth; R(3, n) = i_sth; R(4, n) = i_rk; R(5, n) = s; R(6, n) = i_isd; R(7, n) = i_sd;
+        R(8, n) = A0; R(9, n) = B0; R(10, n) = A1; R(11, n) = B1;
+      }
+      {
+        const bool okp = active && i_rx == i_rx && i_ry == i_ry;
+        const unsigned nanm = __ballot_sync(full, active && !okp);                // fp.py:851-866
+        if (nanm && fn == 0x7fffffff) fn = n0 + __ffs(nanm) - 1;
+        if (has_dyn || M > 0) {
+          // box of the pair's reference points (for the obstacle list), fp32 rounded outward
+          bxlo = min(bxlo, __reduce_min_sync(full, okp ? f2ord(__double2float_rd(i_rx)) : 0xffffffffu));
+          bxhi = max(bxhi, __reduce_max_sync(full, okp ? f2ord(__double2float_ru(i_rx)) : 0u));
+          bylo = min(bylo, __reduce_min_sync(full, okp ? f2ord(__double2float_rd(i_ry)) : 0xffffffffu));
+          byhi = max(byhi, __reduce_max_sync(full, okp ? f2ord(__double2float_ru(i_ry)) : 0u));
+        }
+      }
+      __syncwarp();                                          // rows of this pass (and of the previous one) are visible
+
+      // ---- phase C: validity chain, lane = sample, loop = lateral targets ----------------------------
+      const int keep = fn == 0x7fffffff ? N : (fn >= 2 ? fn : 0);                  // fp.py:866 (final for every sample it excludes)
+      const bool valid = active && n < keep;
+      const bool chk = valid && n >= 1;                                            // limits skip index 0 (fp.py:964-983)
+      const unsigned keep4 = chk ? 0xffffffffu : F_DROP * 0x01010101u;             // n = 0: only the drop guards apply
+      // per-item affine coefficients in d_i
+      const int np_ = chk ? n - 1 : (active ? n : 0);                             // the previous sample (itself at n = 0)
+      const double p_rx = R(0, np_), p_ry = R(1, np_), p_cth = R(2, np_), p_sth = R(3, np_), p_A0 = R(8, np_), p_B0 = R(9, np_);
+      const double sd2 = i_sd * i_sd, isd2 = i_isd * i_isd;
+      const double Q0 = fma(-i_rk, A0, 1.0), Q1 = -(i_rk * B0);                    // q = 1 - kappa_r d
+      const double P0 = A1 * i_isd, P1 = B1 * i_isd;                               // d' (fp.py:792-799)
+      const double R0 = (A2 - P0 * i_sdd) * isd2, R1 = (B2 - P1 * i_sdd) * isd2;   // d''
+      const double M0 = fma(i_rdk, A0, i_rk * P0), M1 = fma(i_rdk, B0, i_rk * P1); // kappa_r' d + kappa_r d'
+      const double S0 = i_sdd * Q0, S1 = i_sdd * Q1;                               // s_ddot q
+      // step vector to the previous sample (x = rx - sin d, y = ry + cos d; cc.py:131-132)
+      const double E0x = (i_rx - p_rx) - (i_sth * A0 - p_sth * p_A0), E1x = -(i_sth * B0 - p_sth * p_B0);
+      const double E0y = (i_ry - p_ry) + (i_cth * A0 - p_cth * p_A0), E1y = i_cth * B0 - p_cth * p_B0;
+      const double sd4 = sd2 * sd2;
+      unsigned anyslow = 0u;
+      // per-item screens for the whole grid of lateral targets (see fot_sweep_items.cuh): `lite` -- no lane needs the
+      // road / teleport / speed / singularity / non-finite tests; `skip` -- no lane needs any test
+      bool lite, skip;
+      {
+        const double ga = brake ? 0.0 : P.d_min, gb = brake ? 0.0 : P.d_max, gabs = fmax(fabs(ga), fabs(gb));
+        const double bx = fabs(E0x) + gabs * fabs(E1x), by = fabs(E0y) + gabs * fabs(E1y);
+        const bool ok_tele = fma(bx, bx, by * by) <= 0.99 * tele2;
+        const bool ok_road = fabs(fma(ga, B0, A0)) <= road_thr && fabs(fma(gb, B0, A0)) <= road_thr;
+        const double qa = fma(ga, Q1, Q0), pa = fma(ga, P1, P0), qb = fma(gb, Q1, Q0), pb = fma(gb, P1, P0);
+        const double vcap = vmax2 * (1.0 - 1e-12);
+        const bool ok_speed = sd2 * fma(qa, qa, pa * pa) <= vcap && sd2 * fma(qb, qb, pb * pb) <= vcap;
+        const bool ok_sing = fmin(qa, qb) > 0.05;
+        const double mag = fabs(Q0) + fabs(P0) + fabs(R0) + fabs(M0) + fabs(S0) + sd2 + fabs(i_rk) +
+                           gabs * (fabs(Q1) + fabs(P1) + fabs(R1) + fabs(M1) + fabs(S1));
+        const bool ok_fin = mag <= 1e40;
+        const bool lite_ok = ok_tele && ok_road && ok_speed && ok_sing && ok_fin;
+        lite = __all_sync(full, !valid || lite_ok);                                // NaN anywhere: full chain
+        const double qmin = fmin(qa, qb), qmax = fmax(qa, qb), Pm = fmax(fabs(pa), fabs(pb));
+        const double Rm = fmax(fabs(fma(ga, R1, R0)), fabs(fma(gb, R1, R0)));
+        const double Mm = fmax(fabs(fma(ga, M1, M0)), fabs(fma(gb, M1, M0)));
+        const double Sm = fmax(fabs(fma(ga, S1, S0)), fabs(fma(gb, S1, S0)));
+        const double h2lo = qmin * qmin, h2hi = fma(qmax, qmax, Pm * Pm), ark = fabs(i_rk);
+        const double Wm = fma(ark, h2hi, fma(Rm, qmax, Mm * Pm));                  // |kappa h^3|
+        const double Tm = fma(Pm, fma(ark, h2hi, Wm), Mm * h2hi);
+        const double Zm = fma(sd2, Tm, Sm * h2hi);                                 // |a h q|
+        const double slack = 1.0 + 1e-9, Wm2 = Wm * Wm * slack;
+        const bool ok_rest = Wm2 <= kmax2 * (h2lo * h2lo * h2lo) && sd4 * Wm2 <= latmax2 * h2lo &&
+                             Zm * Zm * slack <= amax2 * (h2lo * h2lo) && sd2 * h2lo > 0.25 * slack;
+        skip = __all_sync(full, !valid || (lite_ok && (!chk || ok_rest)));
+      }
+      // one candidate sample, straight-line: flags of candidate i0 + U into byte U of acc
+      auto sample = [&](auto lite_tag, double di, unsigned& acc, unsigned sh) {
+        constexpr bool kLite = decltype(lite_tag)::value;
+        const double qq = fma(di, Q1, Q0), dpr = fma(di, P1, P0), dpp = fma(di, R1, R0);
+        const double m = fma(di, M1, M0), sq = fma(di, S1, S0);
+        const double h2 = fma(qq, qq, dpr * dpr);                                  // hypot(q, d')^2 = (q / cos delta)^2
+        const double w = fma(i_rk, h2, fma(dpp, qq, m * dpr));                     // kappa h^3   (cc.py:144-147)
+        const double h6 = h2 * h2 * h2;
+        const double w2 = w * w;
+        const double v2 = sd2 * h2;                                                // v^2         (cc.py:150-152)
+        const double T = fma(dpr, fma(-i_rk, h2, w), -(m * h2));
+        const double Z = fma(sd2, T, sq * h2);                                     // a h q       (cc.py:155-157)
+        const double acc_rhs = amax2 * (qq * qq * h2), curv_rhs = kmax2 * h6, lat_lhs = sd4 * w2, lat_rhs = latmax2 * h2;
+        const double Z2 = Z * Z;
+        if constexpr (kLite) {
+          asm("{\n .reg .pred p, f;\n"
+              " setp.gt.f64 f, %2, %3;\n"                                             // v > 0.5 (fp.py:1019)
+              " @!f or.b32 %1, %1, 1;\n"
+              " setp.gt.and.f64 p, %4, %5, f;\n"                                      // |kappa| > k_max when fast (fp.py:1020)
+              " @p or.b32 %0, %0, %6;\n"
+              "}"
+              : "+r"(acc), "+r"(anyslow)
+              : "d"(v2), "d"(fast2), "d"(w2), "d"(curv_rhs), "r"(F_CURV << sh));
+        } else {
+          const double ex = fma(di, E1x, E0x), ey = fma(di, E1y, E0y);
+          const double step2 = fma(ex, ex, ey * ey);                               // fp.py:954 (squared)
+          const double fin = fabs(Z) + fabs(w) + h6;
+          asm("{\n .reg .pred p, f;\n .reg .f64 t;\n"
+              " abs.f64 t, %2;\n setp.lt.f64 p, t, 0d7FF0000000000000;\n setp.le.and.f64 p, %2, 0d3FA999999999999A, p;\n"   // q <= 0.05 and finite (fp.py:826-833)
+              " setp.geu.or.f64 p, %3, 0d7FF0000000000000, p;\n"                      // non-finite v / a / kappa (fp.py:944-946)
+              " setp.gt.or.f64 p, %4, %5, p;\n"                                       // teleport (fp.py:953-956)
+              " @p or.b32 %0, %0, %6;\n"
+              " setp.gt.f64 f, %7, %8;\n"                                             // v > 0.5 (fp.py:1019)
+              " @!f or.b32 %1, %1, 1;\n"
+              " setp.gt.and.f64 p, %9, %10, f;\n"                                     // |kappa| > k_max when fast (fp.py:1020)
+              " @p or.b32 %0, %0, %11;\n"
+              "}"
+              : "+r"(acc), "+r"(anyslow)
+              : "d"(qq), "d"(fin), "d"(step2), "d"(tele2), "r"(F_DROP << sh), "d"(v2), "d"(fast2), "d"(w2), "d"(curv_rhs), "r"(F_CURV << sh));
+          flag_gt(acc, v2, vmax2, F_SPEED << sh);                                  // fp.py:964
+          flag_abs_gt(acc, fma(di, B0, A0), road_thr, F_ROAD << sh);               // fp.py:982
+        }
+        flag_gt(acc, Z2, acc_rhs, F_ACCEL << sh);                                  // fp.py:966
+        flag_gt(acc, lat_lhs, lat_rhs, F_LAT << sh);                               // fp.py:975  v^2 |kappa| > a_lat
+      };
+      auto sweep_targets = [&](auto lite_tag) {
+#pragma unroll 1
+        for (int i0 = 0; i0 < n_dl; i0 += 4) {
+          unsigned acc = 0u;
+          if (valid) {
+            // the last quad repeats the last target (its bytes are masked off below): one code path for every grid size
+            const int l = n_dl - 1;
+            const double g0 = dg[i0], g1 = dg[min(i0 + 1, l)], g2 = dg[min(i0 + 2, l)], g3 = dg[min(i0 + 3, l)];
+            sample(lite_tag, g0, acc, 0u); sample(lite_tag, g1, acc, 8u); sample(lite_tag, g2, acc, 16u); sample(lite_tag, g3, acc, 24u);
+          }
+          const int left = n_dl - i0;
+          const unsigned tailm = left >= 4 ? 0xffffffffu : (1u << (8 * left)) - 1u;
+          const unsigned red = __reduce_or_sync(full, acc & keep4 & tailm);
+          if (lane == 0 && red) flags[i0 >> 2] |= red;           // the warp owns the pair: a plain read-modify-write
+        }
+      };
+      if (skip) { }
+      else if (lite) sweep_targets(std::true_type{});
+      else sweep_targets(std::false_type{});
+      // Low-speed regime (fp.py:1022-1032): samples that saw a candidate with v <= 0.5 are listed; the warp
+      // redoes the two low-speed tests for them below, one (sample, candidate) unit per lane.
+      {
+        const unsigned sm = __ballot_sync(full, anyslow && chk);
+        if (anyslow && chk) slowq[nslow + __popc(sm & lt_mask)] = (unsigned short)n;
+        nslow += __popc(sm);
+      }
+      // Samples beyond the NaN prefix that are inside the spline domain again still count for the
+      // candidate-wide singularity guard (fp.py:826-833 runs before the truncation).  Essentially never.
+      __syncwarp();
+      if (active && !valid && i_rx == i_rx && keep > 0) {
+        for (int i = 0; i < n_dl; ++i) {
+          const double qq = fma(dg[i], Q1, Q0);
+          if ((qq <= 0.05) & (fabs(qq) < inf)) atomicOr(&flags[i >> 2], F_DROP << (8 * (i & 3)));
+        }
+      }
+      __syncwarp();
+    }
+    const int keep = fn == 0x7fffffff ? N : (fn >= 2 ? fn : 0);
+
+    // this pair's cost pieces (fot_prepass tables: jerk sums, terminal offset), lane = candidate: issued here, used in phase E
+    const int nTv = P.cfg.n_T * B.n_v_max, nTd = P.cfg.n_T * n_d, nB = P.cfg.n_B;
+    const double* ct = B.cost_tab + (size_t)q * (nTv + 2 * nTd + 3 * nB);
+    const double* ct_s = brake ? ct + nTv + 2 * nTd + kk : ct + jT * B.n_v_max + kk;            // Js
+    const double* ct_p = brake ? ct + nTv + 2 * nTd + nB + kk : ct + nTv + jT * n_d;            // Jp[n_dl]
+    const double* ct_e = brake ? ct + nTv + 2 * nTd + 2 * nB + kk : ct + nTv + nTd + jT * n_d;  // d_end[n_dl]
+    const double e_Js = __ldg(ct_s);
+    const double e_Jp = lane < n_dl ? __ldg(ct_p + lane) : 0.0, e_dend = lane < n_dl ? __ldg(ct_e + lane) : 0.0;
+
+    // ---- low-speed tests of unit (listed sample, candidate i): lateral step vs longitudinal step, heading
+    // change vs the 0.1 rad / kappa_max * step floor (fp.py:1022-1032), from the item rows
+    if (nslow > 0) {
+      const int n_su = nslow * n_dl;
+      const float rcp_dl = 1.0f / (float)n_dl;
+#pragma unroll 1
+      for (int u = lane; u < n_su; u += 32) {
+        const int ks = __float2int_rz(((float)u + 0.5f) * rcp_dl), i = u - ks * n_dl;
+        const int sn = slowq[ks];
+        // a candidate that already carries a flag of curvature priority or higher cannot change category
+        if ((flags[i >> 2] >> (8 * (i & 3))) & (F_DROP | F_SPEED | F_ACCEL | F_CURV)) continue;
+        double r1[kRowW], r0[kRowW];                                             // sample n and sample n - 1 (only checked samples are listed)
+#pragma unroll
+        for (int f = 0; f < kRowW; ++f) { r1[f] = R(f, sn); r0[f] = R(f, sn - 1); }
+        const double di = dg[i];
+        const double d = fma(di, r1[9], r1[8]), dprev = fma(di, r0[9], r0[8]);
+        const double qq = fma(-r1[4], d, 1.0), dpr = fma(di, r1[11], r1[10]) * r1[6];
+        const double ssd = r1[7];
+        if (ssd * ssd * fma(qq, qq, dpr * dpr) > 0.25) continue;                 // this candidate is in the fast regime here
+        bool badc;
+        if (fabs(d - dprev) > fmax(1.5 * fabs(r1[5] - r0[5]), 0.02)) {
+          badc = true;
+        } else {
+          // |wrap(yaw_n - yaw_{n-1})| is the angle between the heading vectors u = R(theta_r)(q, d')
+          const double kmax = lim[2];
+          const double q_prev = fma(-r0[4], dprev, 1.0);
+          const double dp_prev = fma(di, r0[11], r0[10]) * r0[6];
+          const double ux = r1[2] * qq - r1[3] * dpr, uy = r1[3] * qq + r1[2] * dpr;
+          const double uxp = r0[2] * q_prev - r0[3] * dp_prev, uyp = r0[3] * q_prev + r0[2] * dp_prev;
+          const double cr = uxp * uy - uyp * ux, dt_ = uxp * ux + uyp * uy;
+          const double ex = fma(-r1[3], d, r1[0]) - fma(-r0[3], dprev, r0[0]);
+          const double ey = fma(r1[2], d, r1[1]) - fma(r0[2], dprev, r0[1]);
+          const double step2 = fma(ex, ex, ey * ey);
+          if (kmax * kmax * step2 <= 0.01)
+            // the threshold is the 0.1 rad floor: angle > 0.1 <=> dot <= 0 or cross^2 > tan(0.1)^2 dot^2
+            badc = dt_ <= 0.0 || cr * cr > kTan01Sq * dt_ * dt_;
+          else
+            badc = fabs(atan2(cr, dt_)) > kmax * sqrt(step2);
+        }
+        if (badc) atomicOr(&flags[i >> 2], F_CURV << (8 * (i & 3)));
+      }
+      __syncwarp();
+    }
+
+    // ---- phase D: collision (fp.py:1035-1233) ----------------------------------------------------------
+    const int n_obs = M + SP;
+    if (keep > 0 && n_obs > 0 && bxlo != 0xffffffffu) {
+      // kinematically clean candidates, lane = candidate: one ballot per word
+      int i_lo = -1, i_hi = -1;                            // lowest / highest clean candidate of the pair
+#pragma unroll 1
+      for (int w = 0; w < G.nwc; ++w) {
+        const int ci = 32 * w + lane;
+        const unsigned byte = ci < n_dl ? (flags[ci >> 2] >> (8 * (ci & 3))) & 0xffu : 0xffu;
+        const unsigned cwd = __ballot_sync(full, byte == 0u);
+        if (cwd) { if (i_lo < 0) i_lo = 32 * w + __ffs(cwd) - 1; i_hi = 32 * w + 31 - __clz(cwd); }
+        if (lane == 0) cleanw[w] = cwd;
+      }
+      __syncwarp();
+      if (i_lo >= 0) {
+        if (!dyn_ready) { mbar_wait(&s_bar, 0u); dyn_ready = true; }
+        // the obstacles whose (trajectory) box meets the box of the reference points padded by the widest reach
+        // of a clean candidate; a NaN box (fp.py:1211-1222) fails every comparison
+        const float bx0 = __fsub_rd(ord2f(bxlo), pad), bx1 = __fadd_ru(ord2f(bxhi), pad);
+        const float by0 = __fsub_rd(ord2f(bylo), pad), by1 = __fadd_ru(ord2f(byhi), pad);
+        const double ga = P.d_sorted ? dg[i_lo] : (brake ? 0.0 : P.d_min), gb = P.d_sorted ? dg[i_hi] : (brake ? 0.0 : P.d_max);
+        // One loop, three jobs, whichever is due: (1) list the next obstacles whose box meets the pair's, (2) window
+        // test of every kept sample against the listed obstacles, lane = sample, survivors -> queue by ballot + prefix
+        // count, (3) exact tests of 32 queued (sample, obstacle) entries, lane = entry, against every live clean candidate.
+        int j0 = 0;                                        // next obstacle to list
+        int nl = 0, e = 0, c0 = keep;                      // current list, next entry, first sample of the current pass (>= keep: list done)
+        int qn = 0;                                        // queued survivors
+        bool reload = true;
+        int cn_ = 0;
+        bool cv = false;
+        double c_cth = 0, c_sth = 0, ca = 0, cnn = 0, d_lo = 0, d_hi = 0;
+        const double2* obs_k = nullptr;
+#pragma unroll 1
+        for (;;) {
+          if (c0 >= keep && j0 < n_obs) {
+            // (1) obstacle list, lane = obstacle
+            nl = 0;
+#pragma unroll 1
+            do {
+              const int j = j0 + lane;
+              bool in = false;
+              unsigned ent = 0u;
+              if (j < M) {
+                const double2 o = stat_q[j];
+                in = o.x >= (double)bx0 && o.x <= (double)bx1 && o.y >= (double)by0 && o.y <= (double)by1;
+                ent = 0x80000000u | (unsigned)j;
+              } else if (j < n_obs) {
+                const float4 ob = boxes[j - M];                   // xmin xmax ymin ymax
+                in = ob.x <= bx1 && ob.y >= bx0 && ob.z <= by1 && ob.w >= by0;
+                ent = (unsigned)((j - M) * B.T_obs);
+              }
+              const unsigned m = __ballot_sync(full, in);
+              if (in) wl[nl + __popc(m & lt_mask)] = ent;
+              nl += __popc(m);
+              j0 += 32;
+            } while (j0 < n_obs && nl <= kPairList - 32);
+            __syncwarp();
+            if (nl > 0) { c0 = 0; e = 0; reload = true; }
+            continue;
+          }
+          // (2) window tests until a full drain is queued or the list is exhausted
+#pragma unroll 1
+          while (qn < 32 && c0 < keep) {
+            if (reload) {
+              // this pass's samples: tangent-frame window -- along = (o - ref).t within the collision radius,
+              // across = (o - ref).n within the radius of the lateral offsets the pair's clean candidates take here
+              cn_ = c0 + lane;
+              cv = cn_ < keep;
+              const int cs_ = cv ? cn_ : 0;
+              const double c_rx = R(0, cs_), c_ry = R(1, cs_), cA0 = R(8, cs_), cB0 = R(9, cs_);
+              c_cth = R(2, cs_); c_sth = R(3, cs_);
+              ca = fma(c_rx, c_cth, c_ry * c_sth); cnn = fma(c_ry, c_cth, -(c_rx * c_sth));
+              d_lo = cA0 + fmin(ga * cB0, gb * cB0) - 1e-9;
+              d_hi = cA0 + fmax(ga * cB0, gb * cB0) + 1e-9;
+              const int kob = B.T_obs > 0 ? min(cn_, B.T_obs - 1) : 0;             // clip(round(t/dt)) = n (fp.py:1226-1227)
+              obs_k = (G.stage_dyn ? dynst : dyn_q) + kob;                         // this sample's time step
+              reload = false;
+            }
+            const unsigned off = wl[e];
+            const bool is_st = off >> 31;
+            const double rc = is_st ? rc_s : rc_d;
+            bool rel = false;
+            if (cv) {
+              const double2 o = is_st ? stat_q[off & 0x7fffffffu] : obs_k[off];
+              const double al = fma(o.x, c_cth, fma(o.y, c_sth, -ca));
+              const double ac = fma(o.y, c_cth, fma(-o.x, c_sth, -cnn));
+              rel = (fabs(al) <= rc) & (ac >= d_lo - rc) & (ac <= d_hi + rc);      // NaN -> false
+            }
+            const unsigned m = __ballot_sync(full, rel);
+            if (m) {
+              if (rel) { const int slot = qn + __popc(m & lt_mask); q_off[slot] = off; q_n[slot] = (unsigned short)cn_; }
+              qn += __popc(m);
+            }
+            if (++e >= nl) { e = 0; c0 += 32; reload = true; }
+          }
+          const bool finished = c0 >= keep && j0 >= n_obs;
+          if (qn >= 32 || (finished && qn > 0)) {
+            // (3) exact tests of the first min(qn, 32) queued entries: uniform loop over the live clean candidates,
+            // one ballot per candidate
+            __syncwarp();
+            const int cnt = min(qn, 32);
+            const bool lv = lane < cnt;
+            const unsigned off = lv ? q_off[lane] : 0u;
+            const int en = lv ? (int)q_n[lane] : 0;
+            const bool is_dyn = !(off >> 31);
+            const unsigned el = off & 0x7fffffffu;
+            double2 o = make_double2(0.0, 0.0);
+            if (lv) {
+              const unsigned ok_ = el + (unsigned)(B.T_obs > 0 ? min(en, B.T_obs - 1) : 0);
+              o = is_dyn ? (G.stage_dyn ? dynst[ok_] : dyn_q[ok_]) : stat_q[el];
+            }
+            const double r2 = is_dyn ? r2_dyn : P.cfg.collide_r2;
+            const bool use_budget = budget && is_dyn;
+            const double cth = R(2, en), sth = R(3, en), eA0 = R(8, en), eB0 = R(9, en);
+            const double X0 = fma(-sth, eA0, R(0, en)) - o.x, X1 = -(sth * eB0);     // x - ox = X0 + d_i X1
+            const double Y0 = fma(cth, eA0, R(1, en)) - o.y, Y1 = cth * eB0;
+            bool alive = false;
+#pragma unroll 1
+            for (int w = 0; w < G.nwc; ++w) {
+              unsigned live = cleanw[w] & ~hitw[w];
+              unsigned nh = 0u;
+#pragma unroll 1
+              while (live) {
+                const int bit = __ffs(live) - 1;
+                live &= live - 1u;
+                const int i = w * 32 + bit;
+                const double di = dg[i];
+                bool hit = false;
+                if (n_circ == 0) {
+                  const double dx = fma(di, X1, X0), dy = fma(di, Y1, Y0);
+                  hit = dx * dx + dy * dy <= r2;                                     // fp.py:1196-1198, :1231-1233
+                } else {                                                             // fp.py:1158-1167
+                  const double d = fma(di, eB0, eA0);
+                  const double dpr = fma(di, R(11, en), R(10, en)) * R(6, en);
+                  const double qq = fma(-R(4, en), d, 1.0);
+                  const double rh = 1.0 / sqrt(fma(qq, qq, dpr * dpr));
+                  const double hx = (cth * qq - sth * dpr) * rh, hy = (sth * qq + cth * dpr) * rh;   // (cos yaw, sin yaw)
+                  for (int ci = 0; ci < n_circ && !hit; ++ci) {
+                    const double dx = fma(di, X1, X0) + P.cfg.circle_offsets[ci] * hx, dy = fma(di, Y1, Y0) + P.cfg.circle_offsets[ci] * hy;
+                    hit = dx * dx + dy * dy <= r2;
+                  }
+                }
+                hit = hit && lv;
+                if (use_budget) {
+                  if (hit) { const int sidx = (int)(el / (unsigned)B.T_obs) / B.P; atomicOr(&viol[i * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
+                  hit = false;
+                }
+                if (__ballot_sync(full, hit)) nh |= 1u << bit;
+              }
+              if (nh && lane == 0) hitw[w] |= nh;
+              alive |= (cleanw[w] & ~(hitw[w] | nh)) != 0u;
+            }
+            // the entries behind the drained ones move to the front
+            const int rest = qn - cnt;
+            const unsigned t_off = lane < rest ? q_off[32 + lane] : 0u;
+            const unsigned short t_n = lane < rest ? q_n[32 + lane] : (unsigned short)0;
+            __syncwarp();
+            if (lane < rest) { q_off[lane] = t_off; q_n[lane] = t_n; }
+            qn = rest;
+            reload = true;
+            __syncwarp();
+            if (!alive && !budget) break;                  // every clean candidate has its decisive hit
+          }
+          if (finished && qn == 0) break;
+        }
+      }
+    }
+
+    // ---- phase E: category, cost, arg-min, histogram: lane = candidate ------------------------------
+    __syncwarp();
+#pragma unroll 1
+    for (int c0 = 0; c0 < n_dl; c0 += 32) {
+      const int ci = c0 + lane;
+      int cat = -1;
+      if (ci < n_dl) {
+        // cost on the un-truncated profile (fp.py:703-734); jerk sums and terminal offsets from fot_prepass
+        const double Jp = c0 == 0 ? e_Jp : __ldg(ct_p + ci), d_end = c0 == 0 ? e_dend : __ldg(ct_e + ci);
+        const double Jd = d_end * d_end;
+        const double dv = qc[10] - R(7, N - 1);                                   // terminal speed (fp.py:724)
+        const double Jv = dv * dv;
+        const double Jt = (double)(N - 1) * dt;
+        const double lat_cost = P.cfg.k_j * Jp + P.cfg.k_t * Jt + P.cfg.k_d * Jd;
+        const double lon_cost = P.cfg.k_j * e_Js + P.cfg.k_t * Jt + P.cfg.k_s_dot * Jv;
+        const double cost = P.cfg.k_lat * lat_cost + P.cfg.k_lon * lon_cost;
+        const unsigned byte = (flags[ci >> 2] >> (8 * (ci & 3))) & 0xffu;
+        if (keep == 0 || (byte & F_DROP)) cat = FOT_CAT_DROP;                     // fp.py:831-833, :933, :944, :953
+        else if (byte & F_SPEED) cat = FOT_CAT_SPEED;
+        else if (byte & F_ACCEL) cat = FOT_CAT_ACCEL;
+        else if (byte & F_CURV) cat = FOT_CAT_CURV;
+        else if (byte & F_LAT) cat = FOT_CAT_LAT;
+        else if (byte & F_ROAD) cat = FOT_CAT_ROAD;
+        else {
+          bool hit = (hitw[ci >> 5] >> (ci & 31)) & 1u;
+          if (G.vwords > 0) {
+            int nv = 0;
+            for (int w = 0; w < G.vwords; ++w) nv += __popc(viol[ci * G.vwords + w]);
+            hit = hit || nv > max_viol;                                            // fp.py:1113-1124
+          }
+          if (hit) {
+            cat = FOT_CAT_COLL;                                                    // fp.py:986-989
+          } else {
+            cat = FOT_CAT_OK;
+            if (stop_dist == stop_dist) {                                          // fp.py:307-324: v at the last kept sample
+              const int kl = keep - 1;
+              const double di = dg[ci];
+              const double l_rk = R(4, kl), l_isd = R(6, kl), l_sd = R(7, kl);
+              const double lQ0 = fma(-l_rk, R(8, kl), 1.0), lQ1 = -(l_rk * R(9, kl));
+              const double lP0 = R(10, kl) * l_isd, lP1 = R(11, kl) * l_isd;
+              const double qq = fma(di, lQ1, lQ0), dpr = fma(di, lP1, lP0);
+              const double v_last = sqrt((l_sd * l_sd) * fma(qq, qq, dpr * dpr));
+              const double s_span = R(5, kl) - R(5, 0);
+              if (!(v_last <= 0.15 && s_span <= stop_dist + 1e-6)) cat = FOT_CAT_STOP;
+            }
+          }
+        }
+        const int cand_idx = cand0 + ci;
+        if (O.cand_cat) O.cand_cat[(size_t)q * O.cand_stride + cand_idx] = (uint8_t)cat;
+        if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + cand_idx] = cost;
+        if (cat == FOT_CAT_OK && cost < INFINITY) argmin_merge(my_cost, my_idx, cost, cand_idx);
+      }
+      // histogram: lane k counts category k
+#pragma unroll 1
+      for (int kc = 0; kc < FOT_N_STATS; ++kc) {
+        const int cnt = __popc(__ballot_sync(full, cat == kc));
+        if (lane == kc) my_stat += cnt;
+      }
+    }
+    __syncwarp();                                          // the slice is free for the next pair
+  }  // pairs of this warp
+
+  if (staged && !dyn_ready) mbar_wait(&s_bar, 0u);         // the bulk copy must have landed before the CTA can exit
+  for (int off = 16; off > 0; off >>= 1) {
+    const double oc = __shfl_down_sync(full, my_cost, off);
+    const int oi = __shfl_down_sync(full, my_idx, off);
+    argmin_merge(my_cost, my_idx, oc, oi);
+  }
+  if (lane == 0) { s_cost[wid] = my_cost; s_idx[wid] = my_idx; }
+  if (lane < FOT_N_STATS && my_stat != 0) atomicAdd(&s_stats[lane], my_stat);
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < (bd >> 5); ++w) argmin_merge(my_cost, my_idx, s_cost[w], s_idx[w]);
+    O.part_cost[part] = my_cost;
+    O.part_idx[part] = (my_idx == 0x7fffffff) ? -1 : my_idx;
+  }
+  if (tid < FOT_N_STATS && s_stats[tid] != 0) atomicAdd(&O.stats[(size_t)q * FOT_N_STATS + tid], s_stats[tid]);
+}
+
+}  // namespace fot

@@ -40,9 +40,10 @@ def test_config4_batch_both_kernels():
     _, frenet, dyn = bench.make_queries(1000, 512)
     pl = _planner(scenarios.S1_KNOBS, scenarios.STRAIGHT_60)
     run = lambda: pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn[:, 0], want_candidates=True)
-    a, b, c = _run("warp", run), _run("items", run), _run("generic", run)
+    a, b, c, d = _run("warp", run), _run("items", run), _run("generic", run), _run("pairs", run)
     _assert_same(a, b)
     _assert_same(b, c)
+    _assert_same(b, d)
     assert (a.stats[:, 6] > 0).any() and (a.best_idx >= 0).any()
 
 
@@ -66,9 +67,10 @@ def test_curved_path_state_machine_knobs_both_kernels():
     pl = _planner(k, wp)
     run = lambda: pl.plan_batch(frenet, target, dynamic_obstacles=dyn, static_obstacles=wall, limits=limits,
                                 max_stop_distance=msd, want_candidates=True)
-    a, b, c = _run("warp", run), _run("items", run), _run("generic", run)
+    a, b, c, d = _run("warp", run), _run("items", run), _run("generic", run), _run("pairs", run)
     _assert_same(a, b)
     _assert_same(b, c)
+    _assert_same(b, d)
 
 
 def test_dense_grid_distribution_both_kernels():
@@ -82,8 +84,9 @@ def test_dense_grid_distribution_both_kernels():
     pl = _planner(knobs, wp)
     fs = np.array([[5.0, 5.0, 0.0, 0.0, 0.0, 0.0]])
     run = lambda: pl.plan_batch(fs, 6.2, distribution=dist[None], want_candidates=True)
-    a, b = _run("items", run), _run("generic", run)
+    a, b, d = _run("items", run), _run("generic", run), _run("pairs", run)
     _assert_same(a, b)
+    _assert_same(a, d)
     assert int(a.n_cand[0]) > 60000
 
 
@@ -105,6 +108,7 @@ def test_budgeted_distribution_and_footprint_both_kernels():
     from tests import runners
     pl = BatchFrenetPlanner(CubicSpline2D(*wp), footprint=runners.make_footprint((4.5, 2.0, 3)), **knobs)
     run = lambda: pl.plan_batch(frenet, 6.0, distribution=dist, want_candidates=True)
-    a, b, c = _run("warp", run), _run("items", run), _run("generic", run)      # 12 x 14 = 168 entries: inside the warp kernel's range
+    a, b, c, d = _run("warp", run), _run("items", run), _run("generic", run), _run("pairs", run)   # 12 x 14 = 168 entries: inside the warp kernel's range
     _assert_same(a, b)
     _assert_same(b, c)
+    _assert_same(b, d)
