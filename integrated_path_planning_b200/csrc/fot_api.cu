@@ -75,7 +75,6 @@ struct Options {
                                //                    DESIGN.md section 4c; fail if unsupported)
                                //                    4 "pairs" (fot_sweep_pairs: one longitudinal profile per warp, no block
                                //                    barriers; fail if unsupported)
-  int pair_warps = 0;          // FOT_PAIR_WARPS     warps per CTA of fot_sweep_pairs (0: kPairThreads / 32)
   int pair_cpq = 0;            // FOT_PAIR_CPQ       CTAs per query of fot_sweep_pairs (0: rule of pair_geometry)
   int host_chunks = 0;         // FOT_HOST_CHUNKS    equal chunks of the host-pointer call (0: rule)
   std::string chunk_waves;     // FOT_CHUNK_WAVES    chunk sizes in sweep waves, "1,2,3" (+ the rest)
@@ -96,7 +95,6 @@ struct Options {
     fused_box = geti("FOT_FUSED_BOX", 0) != 0;
     stage_dyn = geti("FOT_STAGE_DYN", 1) != 0;
     if (const char* e = getenv("FOT_SWEEP")) sweep = !strcmp(e, "generic") ? 2 : !strcmp(e, "items") ? 1 : !strcmp(e, "warp") ? 3 : !strcmp(e, "pairs") ? 4 : 0;
-    pair_warps = geti("FOT_PAIR_WARPS", 0);
     pair_cpq = geti("FOT_PAIR_CPQ", 0);
     host_chunks = geti("FOT_HOST_CHUNKS", 0);
     if (const char* e = getenv("FOT_CHUNK_WAVES")) chunk_waves = e;
@@ -522,71 +520,49 @@ static bool warp_geometry(const fot_handle* h, const fot_batch_t* b, WarpGeom* g
 
 // Geometry of the pair-per-warp kernel (fot_sweep_pairs): one CTA per query (several for small batches), every warp
 // with a private slice of shared memory for the pair it is working on.  False when the shape is outside its range
-// (long time grids, lateral grids whose per-warp tables do not fit): fot_sweep_items then runs.
+// (time grids beyond 64 samples, lateral grids beyond 96 targets, tables that do not fit): fot_sweep_items then runs.
 static bool pair_geometry(const fot_handle* h, const fot_batch_t* b, PairGeom* g, size_t* smem_bytes,
                           bool want_fused_box = false, int cpq_override = 0) {
   const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B, nx = h->plan.cfg.nx;
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const long long SPl = has_dyn ? (long long)b->S * b->P : 0;
-  if (NT > 128 || nd > 8192 || SPl > (1 << 20) || b->n_static > (1 << 20)) return false;   // 128: one NumPy pairwise block
-  if (SPl * std::max(1, b->T_obs) >= (1ll << 31)) return false;                            // list entries: 31-bit element offsets
+  if (NT > kPairNT || nd > kPairND || b->n_v_max > kPairNV || SPl > (1 << 20) || b->n_static > (1 << 20)) return false;
+  if (SPl * std::max(1, b->T_obs) >= (1ll << 27)) return false;                            // list entries: element offsets
   const int SP = (int)SPl;
   PairGeom G{};
   G.nw4 = (nd + 3) / 4;
   G.nwc = (nd + 31) / 32;
   const int max_viol = b->dyn_mode == FOT_DYN_DISTRIBUTION ? (int)std::floor(h->plan.cfg.chance_epsilon * (double)b->S) : 0;
   G.vwords = max_viol > 0 ? (b->S + 31) / 32 : 0;
+  G.viol_bytes = (nd * G.vwords * 4 + 15) / 16 * 16;
   G.spline_smem = nx <= 128 ? 1 : 0;
   const size_t dyn_bytes = (size_t)SP * b->T_obs * 16;
   const bool fuse = want_fused_box || h->opt.fused_box;
-  // the warp's slice
-  {
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
-    G.w_row = take((size_t)kRowW * NT * 8);
-    G.w_flags = take((size_t)G.nw4 * 4);
-    G.w_hit = take((size_t)G.nwc * 4);
-    G.w_viol = take((size_t)nd * G.vwords * 4);
-    G.n_zero = (int32_t)((off - (size_t)G.w_flags) / 4);
-    G.w_clean = take((size_t)G.nwc * 4);
-    G.w_list = take((size_t)kPairList * 4);
-    G.w_qoff = take((size_t)kPairQueue * 4);
-    G.w_qn = take((size_t)kPairQueue * 2);
-    G.w_slow = take((size_t)NT * 2);
-    G.wbytes = (int32_t)off;
-  }
-  const int max_warps = std::max(1, std::min(kPairThreads / 32, h->opt.pair_warps > 0 ? h->opt.pair_warps : kPairThreads / 32));
-  auto layout = [&](bool stage, int warps) {
-    size_t off = 0;
+  auto layout = [&](bool stage) {
+    size_t off = sizeof(PairShared);
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
     const bool box = has_dyn && ((stage && fuse) || (size_t)SP * 16 <= 8 * 1024);
-    G.o_qc = take((size_t)(12 + b->n_v_max) * 8);
-    G.o_dgrid = take((size_t)(nd + 1) * 8);
     G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);
     G.o_dyn = take(stage ? dyn_bytes : 0);
     G.o_box = take(box ? (size_t)SP * 16 : 0);
-    G.o_warp = take(0);
-    off += (size_t)warps * G.wbytes;
+    G.o_viol = take((size_t)kPairWarps * G.viol_bytes);
     G.stage_dyn = stage ? 1 : 0;
     G.fused_box = stage && fuse ? 1 : 0;
     G.box_smem = box ? 1 : 0;
-    G.warps = warps;
     return off;
   };
   // stage the query's obstacle block in shared memory when two CTAs per SM still fit
   bool stage = has_dyn && dyn_bytes > 0 && dyn_bytes <= 64 * 1024 && ((uintptr_t)b->dyn & 15) == 0;
   stage = stage && h->opt.stage_dyn;
-  int warps = max_warps;
-  size_t bytes = layout(stage, warps);
-  if (stage && bytes > 112 * 1024) { stage = false; bytes = layout(false, warps); }
-  while (bytes > (size_t)h->smem_optin && warps > 2) bytes = layout(stage, --warps);
+  size_t bytes = layout(stage);
+  if (stage && bytes > 113 * 1024 - 512) { stage = false; bytes = layout(false); }
   if (bytes > (size_t)h->smem_optin) return false;
   // CTAs per query: one once the batch alone fills the GPU several times over; for small batches the pairs of a
   // query are dealt to several CTAs (about one pair per warp for a single plan() call)
   {
     const int n_units = h->plan.cfg.n_T * b->n_v_max + nB;
     long long cpq = ((long long)h->sms * 2 * 4 + b->n_q - 1) / b->n_q;
-    cpq = std::max<long long>(1, std::min<long long>(cpq, (n_units + warps - 1) / warps));
+    cpq = std::max<long long>(1, std::min<long long>(cpq, (n_units + kPairWarps - 1) / kPairWarps));
     if (cpq_override > 0) cpq = std::max(1, std::min(cpq_override, n_units));
     if (h->opt.pair_cpq > 0) cpq = std::max(1, std::min(h->opt.pair_cpq, n_units));
     G.ctas_per_query = (int)cpq;
@@ -672,7 +648,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
     use_items = true;
     use_warp = false;
     ig.blocks_per_query = h->plan.cfg.n_T * b->n_v_max + h->plan.cfg.n_B;      // upper bound of ctas_per_query (scratch stride)
-    ig.ctas_per_query = pg.ctas_per_query; ig.threads = pg.warps * 32;
+    ig.ctas_per_query = pg.ctas_per_query; ig.threads = kPairThreads;
     ig.fused_box = pg.fused_box;
     if (gate.word) { pg.gate = gate.word; pg.gate_epoch = gate.epoch; pg.gate_per = gate.per; pg.gate_q0 = (int32_t)q_off; }
   }
@@ -779,8 +755,8 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
                                                                (const double2*)b->dyn, dyn_box, n_traj, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
-  if (use_pairs && pg.fused_box) fot_sweep_pairs<true><<<(unsigned)n_part, pg.warps * 32, psmem, st>>>(h->plan, B, O, pg);
-  else if (use_pairs) fot_sweep_pairs<false><<<(unsigned)n_part, pg.warps * 32, psmem, st>>>(h->plan, B, O, pg);
+  if (use_pairs && pg.fused_box) fot_sweep_pairs<true><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
+  else if (use_pairs) fot_sweep_pairs<false><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
   else if (use_warp && wg.fused_box) fot_sweep_warp<true><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
   else if (use_warp) fot_sweep_warp<false><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
   else if (use_items && ig.fused_box) fot_sweep_items<true><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);

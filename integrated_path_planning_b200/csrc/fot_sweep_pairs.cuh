@@ -25,6 +25,7 @@
 // Reference citations as in fot_sweep_items.cuh (fp.py = src/planning/frenet_planner.py, cs.py = cubic_spline.py,
 // cc.py = src/core/coordinate_converter.py).
 #pragma once
+#include <cstddef>
 #include <type_traits>
 #include "fot_sweep_items.cuh"
 
@@ -36,24 +37,48 @@ namespace fot {
 #ifndef FOT_PAIR_MIN_CTAS
 #define FOT_PAIR_MIN_CTAS 2
 #endif
-constexpr int kPairThreads = FOT_PAIR_THREADS;   // largest CTA of fot_sweep_pairs
+constexpr int kPairThreads = FOT_PAIR_THREADS;   // CTA size of fot_sweep_pairs
+constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kPairList = 64;                    // obstacle list entries per cull chunk (per warp)
 constexpr int kPairQueue = 64;                   // survivor queue entries (per warp): < 32 pending + <= 32 new
+constexpr int kPairNT = 64;                      // samples per profile this kernel covers (longer time grids: fot_sweep_items)
+constexpr int kPairND = 96;                      // lateral targets this kernel covers (wider grids: fot_sweep_items)
+constexpr int kPairNV = 52;                      // terminal speeds per query
+
+// One warp's private slice of shared memory, and behind the slices the CTA-wide tables whose size has a small bound.
+// The layout is a compile-time constant on purpose: every access is `base register + immediate`.  (With run-time
+// offsets the compiler rebuilt the addresses from the thread index at every use -- a fifth of the hot instructions of
+// the first version of this kernel, which is bound by instruction fetch.)
+struct __align__(16) PairSlice {
+  double row[kRowW][kPairNT];          // item rows of the current pair, field-major: rx ry cos sin | kappa s 1/s_dot s_dot | A0 B0 A1 B1
+                                       // (lane = sample reads and writes are conflict-free)
+  unsigned flags[kPairND / 4];         // validity flags, one byte per candidate
+  unsigned hitw[4];                    // decisive collision, one bit per candidate
+  unsigned cleanw[4];                  // kinematically clean
+  unsigned wl[kPairList];              // obstacle list: element offsets (bit 31: static)
+  unsigned q_off[kPairQueue];          // survivor queue: obstacle element offset
+  unsigned short q_n[kPairQueue];      //                 sample
+  unsigned short slowq[kPairNT];       // samples with a low-speed candidate
+};
+struct __align__(16) PairShared {
+  PairSlice w[kPairWarps];
+  double qc[12 + kPairNV];             // fs[6] | limits[4] | target | stop_dist | v_grid[n_v]
+  double dgrid[kPairND + 2];           // lateral targets, then the brake ladder's single target 0.0
+};
+
+static_assert(offsetof(PairSlice, hitw) == offsetof(PairSlice, flags) + kPairND && offsetof(PairSlice, cleanw) == offsetof(PairSlice, hitw) + 16 &&
+              kPairND / 4 + 8 == 32, "flags | hitw | cleanw are zeroed as 32 consecutive words");
 
 struct PairGeom {
-  int32_t warps;             // warps per CTA
   int32_t ctas_per_query;    // CTAs that share one query's pairs (1 in large batches)
   int32_t nw4, nwc, vwords;  // flag words (4 candidates each) / mask words (32 candidates each) / violation words per candidate
   int32_t stage_dyn;         // 1: the query's obstacle block is staged in shared memory by one bulk copy
   int32_t spline_smem;       // 1: spline tables copied to shared memory
   int32_t box_smem;          // 1: trajectory boxes in shared memory (copied from fot_prepass, or built here when fused_box)
   int32_t fused_box;         // 1: boxes built by the CTA from its staged block (gated host-pointer call)
-  int32_t n_zero;            // u32 words zeroed per pair, starting at w_flags (flags | hit words | violation bitmaps)
-  int32_t wbytes;            // bytes of one warp's private slice
-  // byte offsets into dynamic shared memory (CTA-wide)
-  int32_t o_qc, o_dgrid, o_spl, o_dyn, o_box, o_warp;
-  // byte offsets inside a warp's slice
-  int32_t w_row, w_flags, w_hit, w_viol, w_clean, w_list, w_qoff, w_qn, w_slow;
+  // byte offsets into dynamic shared memory of the run-time sized tables (behind PairShared)
+  int32_t o_spl, o_dyn, o_box, o_viol;
+  int32_t viol_bytes;        // per warp: [n_d][vwords] violation bitmaps (chance-constrained mode with a budget)
   // gated launch (see ItemGeom)
   int32_t gate_q0, gate_per;
   uint32_t gate_epoch;
@@ -64,22 +89,27 @@ template <bool kFused>
 __global__ void __launch_bounds__(kPairThreads, FOT_PAIR_MIN_CTAS)
 fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   extern __shared__ __align__(16) unsigned char smb[];
-  double* qc = reinterpret_cast<double*>(smb + G.o_qc);        // fs[6] | limits[4] | target | stop_dist | v_grid[n_v_max]
-  double* dgrid = reinterpret_cast<double*>(smb + G.o_dgrid);  // [n_d]
+  PairShared& S = *reinterpret_cast<PairShared*>(smb);
+  double* qc = S.qc;
+  double* dgrid = S.dgrid;
   double* spl = reinterpret_cast<double*>(smb + G.o_spl);      // [9][nx] when spline_smem
   const double2* dynst = reinterpret_cast<const double2*>(smb + G.o_dyn);   // [SP][T_obs] when stage_dyn
   float4* sbox = reinterpret_cast<float4*>(smb + G.o_box);     // [SP] trajectory boxes when box_smem
   __shared__ int s_next;                 // next pair of this CTA
   __shared__ int s_stats[FOT_N_STATS];
-  __shared__ double s_cost[kPairThreads / 32];
-  __shared__ int s_idx[kPairThreads / 32];
+  __shared__ double s_cost[kPairWarps];
+  __shared__ int s_idx[kPairWarps];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_abort;
 
   const int NT = P.n_t_max;
   const int q = blockIdx.x / G.ctas_per_query;
   const int cta = blockIdx.x - q * G.ctas_per_query;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, bd = blockDim.x;
+  const int tid = threadIdx.x, bd = blockDim.x;
+  int lane = tid & 31, wid = tid >> 5;
+  // opaque to the optimiser: held in registers instead of being rebuilt from %tid at every use
+  unsigned wofs = (unsigned)wid * (unsigned)sizeof(PairSlice);
+  asm volatile("" : "+r"(lane), "+r"(wofs));
   const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
   const double* fsg = B.frenet + 6 * (size_t)q;
   const int n_v = B.n_v[q];
@@ -97,18 +127,17 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
 
   // this warp's private slice
-  unsigned char* wb = smb + G.o_warp + (size_t)wid * G.wbytes;
-  double* row = reinterpret_cast<double*>(wb + G.w_row);            // [kRowW][NT] item rows of the current pair, field-major:
-                                                                    // lane = sample reads and writes are conflict-free
-  auto R = [&](int f, int n_) -> double& { return row[f * NT + n_]; };   // rx ry cos sin | kappa s 1/s_dot s_dot | A0 B0 A1 B1
-  unsigned* flags = reinterpret_cast<unsigned*>(wb + G.w_flags);    // [nw4]
-  unsigned* hitw = reinterpret_cast<unsigned*>(wb + G.w_hit);       // [nwc] decisive collision
-  unsigned* viol = reinterpret_cast<unsigned*>(wb + G.w_viol);      // [n_d][vwords]
-  unsigned* cleanw = reinterpret_cast<unsigned*>(wb + G.w_clean);   // [nwc] kinematically clean
-  unsigned* wl = reinterpret_cast<unsigned*>(wb + G.w_list);        // [kPairList] element offsets (bit 31: static)
-  unsigned* q_off = reinterpret_cast<unsigned*>(wb + G.w_qoff);     // [kPairQueue] survivor: obstacle element offset
-  unsigned short* q_n = reinterpret_cast<unsigned short*>(wb + G.w_qn);      // [kPairQueue] survivor: sample
-  unsigned short* slowq = reinterpret_cast<unsigned short*>(wb + G.w_slow);  // [NT] samples with a low-speed candidate
+  PairSlice& W = *reinterpret_cast<PairSlice*>(smb + wofs);
+  auto R = [&](int f, int n_) -> double& { return W.row[f][n_]; };
+  unsigned* flags = W.flags;
+  unsigned* hitw = W.hitw;
+  unsigned* cleanw = W.cleanw;
+  unsigned* wl = W.wl;
+  unsigned* q_off = W.q_off;
+  unsigned short* q_n = W.q_n;
+  unsigned short* slowq = W.slowq;
+  unsigned* viol = reinterpret_cast<unsigned*>(smb + G.o_viol + wid * G.viol_bytes);   // [n_d][vwords] (budget mode)
+  (void)NT;
 
   // ---- once per CTA ---------------------------------------------------------------------------------
   if (kFused && G.gate) {
@@ -283,8 +312,9 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
     const double* dg = dgrid + (brake ? n_d : 0);             // lateral targets of this pair (brake: the single 0.0 slot)
 
     // ---- phase A: the pair's private state -----------------------------------------------------------
-#pragma unroll 1
-    for (int i = lane; i < G.n_zero; i += 32) flags[i] = 0u;                   // flags | hit words | violation bitmaps
+    flags[lane] = 0u;                                       // flags | hit words | clean words (32 words in a row)
+    if (G.vwords > 0)
+      for (int i = lane; i < n_d * G.vwords; i += 32) viol[i] = 0u;
     __syncwarp();
 
     // ---- phases B + C, 32 samples at a time ---------------------------------------------------------
@@ -572,18 +602,17 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
         // test of every kept sample against the listed obstacles, lane = sample, survivors -> queue by ballot + prefix
         // count, (3) exact tests of 32 queued (sample, obstacle) entries, lane = entry, against every live clean candidate.
         int j0 = 0;                                        // next obstacle to list
-        int nl = 0, e = 0, c0 = keep;                      // current list, next entry, first sample of the current pass (>= keep: list done)
+        int nl = 0, n_st = 0, e = 0, c0 = keep;            // current list (static entries first), next entry, first sample of the current pass (>= keep: list done)
         int qn = 0;                                        // queued survivors
-        bool reload = true;
-        int cn_ = 0;
-        bool cv = false;
-        double c_cth = 0, c_sth = 0, ca = 0, cnn = 0, d_lo = 0, d_hi = 0;
-        const double2* obs_k = nullptr;
+        // 32-bit shared-space addresses for the two hot loops (a generic pointer costs the compiler a register pair, or a
+        // recomputation from the thread index, per access)
+        unsigned wl_a = smem_u32(wl), dg_a = smem_u32(dg), dyn_a = smem_u32(dynst);
+        asm volatile("" : "+r"(wl_a), "+r"(dg_a), "+r"(dyn_a));     // opaque: keep them in registers, do not recompute per use
 #pragma unroll 1
         for (;;) {
           if (c0 >= keep && j0 < n_obs) {
             // (1) obstacle list, lane = obstacle
-            nl = 0;
+            nl = 0; n_st = 0;
 #pragma unroll 1
             do {
               const int j = j0 + lane;
@@ -601,49 +630,69 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
               const unsigned m = __ballot_sync(full, in);
               if (in) wl[nl + __popc(m & lt_mask)] = ent;
               nl += __popc(m);
+              if (j0 < M) n_st += __popc(M - j0 >= 32 ? m : m & ((1u << (M - j0)) - 1u));   // statics come first
               j0 += 32;
             } while (j0 < n_obs && nl <= kPairList - 32);
             __syncwarp();
-            if (nl > 0) { c0 = 0; e = 0; reload = true; }
+            if (nl > 0) { c0 = 0; e = 0; }
             continue;
           }
-          // (2) window tests until a full drain is queued or the list is exhausted
+          if (c0 < keep) {
+            // (2) window tests of this pass's samples against list entries e.. until a full drain is queued:
+            // along = (o - ref).t within the collision radius, across = (o - ref).n within the radius of the
+            // lateral offsets the pair's clean candidates take at this sample
+            const int cn_ = c0 + lane;
+            const bool cv = cn_ < keep;
+            const int cs_ = cv ? cn_ : 0;
+            const double c_rx = R(0, cs_), c_ry = R(1, cs_), cA0 = R(8, cs_), cB0 = R(9, cs_);
+            const double c_cth = R(2, cs_), c_sth = R(3, cs_);
+            const double nca = -fma(c_rx, c_cth, c_ry * c_sth), ncn = -fma(c_ry, c_cth, -(c_rx * c_sth)), n_sth = -c_sth;
+            const double d_lo = cA0 + fmin(ga * cB0, gb * cB0) - 1e-9;
+            const double d_hi = cA0 + fmax(ga * cB0, gb * cB0) + 1e-9;
+            // a lane beyond the kept samples gets an empty window
+            const double w_lo = cv ? d_lo - rc_d : inf, w_hi = d_hi + rc_d;
+            const int kob = B.T_obs > 0 ? min(cn_, B.T_obs - 1) : 0;               // clip(round(t/dt)) = n (fp.py:1226-1227)
+            unsigned obs_a = dyn_a + 16u * (unsigned)kob;                          // this sample's time step (staged block)
+            asm volatile("" : "+r"(obs_a));
+            const double2* obs_g = dyn_q + kob;                                    // (resident tensor)
+            // kind 0: static entries [e, n_st) of the list; 1: dynamic entries, staged block; 2: dynamic entries, resident tensor
+            auto produce = [&](auto kind_tag, int e_end) {
+              constexpr int kKind = decltype(kind_tag)::value;
 #pragma unroll 1
-          while (qn < 32 && c0 < keep) {
-            if (reload) {
-              // this pass's samples: tangent-frame window -- along = (o - ref).t within the collision radius,
-              // across = (o - ref).n within the radius of the lateral offsets the pair's clean candidates take here
-              cn_ = c0 + lane;
-              cv = cn_ < keep;
-              const int cs_ = cv ? cn_ : 0;
-              const double c_rx = R(0, cs_), c_ry = R(1, cs_), cA0 = R(8, cs_), cB0 = R(9, cs_);
-              c_cth = R(2, cs_); c_sth = R(3, cs_);
-              ca = fma(c_rx, c_cth, c_ry * c_sth); cnn = fma(c_ry, c_cth, -(c_rx * c_sth));
-              d_lo = cA0 + fmin(ga * cB0, gb * cB0) - 1e-9;
-              d_hi = cA0 + fmax(ga * cB0, gb * cB0) + 1e-9;
-              const int kob = B.T_obs > 0 ? min(cn_, B.T_obs - 1) : 0;             // clip(round(t/dt)) = n (fp.py:1226-1227)
-              obs_k = (G.stage_dyn ? dynst : dyn_q) + kob;                         // this sample's time step
-              reload = false;
+              for (; e < e_end; ++e) {
+                unsigned off;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(wl_a + 4u * (unsigned)e) : "memory");
+                double2 o;
+                bool rel;
+                if (kKind == 0) {
+                  o = stat_q[off & 0x7fffffffu];
+                  const double al = fma(o.x, c_cth, fma(o.y, c_sth, nca));
+                  const double ac = fma(o.y, c_cth, fma(o.x, n_sth, ncn));
+                  rel = cv & (fabs(al) <= rc_s) & (ac >= d_lo - rc_s) & (ac <= d_hi + rc_s);
+                } else {
+                  if (kKind == 1) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o.x), "=d"(o.y) : "r"(obs_a + 16u * off) : "memory");
+                  else o = obs_g[off];
+                  const double al = fma(o.x, c_cth, fma(o.y, c_sth, nca));
+                  const double ac = fma(o.y, c_cth, fma(o.x, n_sth, ncn));
+                  rel = (fabs(al) <= rc_d) & (ac >= w_lo) & (ac <= w_hi);          // NaN -> false
+                }
+                const unsigned m = __ballot_sync(full, rel);
+                if (m) {
+                  if (rel) { const int slot = qn + __popc(m & lt_mask); q_off[slot] = off; q_n[slot] = (unsigned short)cn_; }
+                  qn += __popc(m);
+                  if (qn >= 32) { ++e; break; }
+                }
+              }
+            };
+            if (e < n_st) produce(std::integral_constant<int, 0>{}, n_st);
+            if (e >= n_st && qn < 32) {
+              if (G.stage_dyn) produce(std::integral_constant<int, 1>{}, nl); else produce(std::integral_constant<int, 2>{}, nl);
             }
-            const unsigned off = wl[e];
-            const bool is_st = off >> 31;
-            const double rc = is_st ? rc_s : rc_d;
-            bool rel = false;
-            if (cv) {
-              const double2 o = is_st ? stat_q[off & 0x7fffffffu] : obs_k[off];
-              const double al = fma(o.x, c_cth, fma(o.y, c_sth, -ca));
-              const double ac = fma(o.y, c_cth, fma(-o.x, c_sth, -cnn));
-              rel = (fabs(al) <= rc) & (ac >= d_lo - rc) & (ac <= d_hi + rc);      // NaN -> false
-            }
-            const unsigned m = __ballot_sync(full, rel);
-            if (m) {
-              if (rel) { const int slot = qn + __popc(m & lt_mask); q_off[slot] = off; q_n[slot] = (unsigned short)cn_; }
-              qn += __popc(m);
-            }
-            if (++e >= nl) { e = 0; c0 += 32; reload = true; }
+            if (e >= nl) { e = 0; c0 += 32; }
           }
           const bool finished = c0 >= keep && j0 >= n_obs;
-          if (qn >= 32 || (finished && qn > 0)) {
+          if (qn < 32 && !finished) continue;
+          if (qn > 0) {
             // (3) exact tests of the first min(qn, 32) queued entries: uniform loop over the live clean candidates,
             // one ballot per candidate
             __syncwarp();
@@ -656,9 +705,11 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
             double2 o = make_double2(0.0, 0.0);
             if (lv) {
               const unsigned ok_ = el + (unsigned)(B.T_obs > 0 ? min(en, B.T_obs - 1) : 0);
-              o = is_dyn ? (G.stage_dyn ? dynst[ok_] : dyn_q[ok_]) : stat_q[el];
+              if (!is_dyn) o = stat_q[el];
+              else if (G.stage_dyn) o = dynst[ok_];
+              else o = dyn_q[ok_];
             }
-            const double r2 = is_dyn ? r2_dyn : P.cfg.collide_r2;
+            const double r2 = !lv ? -1.0 : (is_dyn ? r2_dyn : P.cfg.collide_r2);   // idle lanes never hit
             const bool use_budget = budget && is_dyn;
             const double cth = R(2, en), sth = R(3, en), eA0 = R(8, en), eB0 = R(9, en);
             const double X0 = fma(-sth, eA0, R(0, en)) - o.x, X1 = -(sth * eB0);     // x - ox = X0 + d_i X1
@@ -668,33 +719,45 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
             for (int w = 0; w < G.nwc; ++w) {
               unsigned live = cleanw[w] & ~hitw[w];
               unsigned nh = 0u;
+              if (n_circ == 0 && !budget) {
+                // the common case (one circle, decisive hits): nothing but the distance test in the loop
 #pragma unroll 1
-              while (live) {
-                const int bit = __ffs(live) - 1;
-                live &= live - 1u;
-                const int i = w * 32 + bit;
-                const double di = dg[i];
-                bool hit = false;
-                if (n_circ == 0) {
+                while (live) {
+                  const int bit = __ffs(live) - 1;
+                  live &= live - 1u;
+                  double di;
+                  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(di) : "r"(dg_a + 8u * (unsigned)(w * 32 + bit)) : "memory");
                   const double dx = fma(di, X1, X0), dy = fma(di, Y1, Y0);
-                  hit = dx * dx + dy * dy <= r2;                                     // fp.py:1196-1198, :1231-1233
-                } else {                                                             // fp.py:1158-1167
-                  const double d = fma(di, eB0, eA0);
-                  const double dpr = fma(di, R(11, en), R(10, en)) * R(6, en);
-                  const double qq = fma(-R(4, en), d, 1.0);
-                  const double rh = 1.0 / sqrt(fma(qq, qq, dpr * dpr));
-                  const double hx = (cth * qq - sth * dpr) * rh, hy = (sth * qq + cth * dpr) * rh;   // (cos yaw, sin yaw)
-                  for (int ci = 0; ci < n_circ && !hit; ++ci) {
-                    const double dx = fma(di, X1, X0) + P.cfg.circle_offsets[ci] * hx, dy = fma(di, Y1, Y0) + P.cfg.circle_offsets[ci] * hy;
+                  if (__ballot_sync(full, dx * dx + dy * dy <= r2)) nh |= 1u << bit;   // fp.py:1196-1198, :1231-1233
+                }
+              } else {
+#pragma unroll 1
+                while (live) {
+                  const int bit = __ffs(live) - 1;
+                  live &= live - 1u;
+                  const int i = w * 32 + bit;
+                  const double di = dg[i];
+                  bool hit = false;
+                  if (n_circ == 0) {
+                    const double dx = fma(di, X1, X0), dy = fma(di, Y1, Y0);
                     hit = dx * dx + dy * dy <= r2;
+                  } else {                                                           // fp.py:1158-1167
+                    const double d = fma(di, eB0, eA0);
+                    const double dpr = fma(di, R(11, en), R(10, en)) * R(6, en);
+                    const double qq = fma(-R(4, en), d, 1.0);
+                    const double rh = 1.0 / sqrt(fma(qq, qq, dpr * dpr));
+                    const double hx = (cth * qq - sth * dpr) * rh, hy = (sth * qq + cth * dpr) * rh;   // (cos yaw, sin yaw)
+                    for (int ci = 0; ci < n_circ && !hit; ++ci) {
+                      const double dx = fma(di, X1, X0) + P.cfg.circle_offsets[ci] * hx, dy = fma(di, Y1, Y0) + P.cfg.circle_offsets[ci] * hy;
+                      hit = dx * dx + dy * dy <= r2;
+                    }
                   }
+                  if (use_budget) {
+                    if (hit) { const int sidx = (int)(el / (unsigned)B.T_obs) / B.P; atomicOr(&viol[i * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
+                    hit = false;
+                  }
+                  if (__ballot_sync(full, hit)) nh |= 1u << bit;
                 }
-                hit = hit && lv;
-                if (use_budget) {
-                  if (hit) { const int sidx = (int)(el / (unsigned)B.T_obs) / B.P; atomicOr(&viol[i * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
-                  hit = false;
-                }
-                if (__ballot_sync(full, hit)) nh |= 1u << bit;
               }
               if (nh && lane == 0) hitw[w] |= nh;
               alive |= (cleanw[w] & ~(hitw[w] | nh)) != 0u;
@@ -706,7 +769,6 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
             __syncwarp();
             if (lane < rest) { q_off[lane] = t_off; q_n[lane] = t_n; }
             qn = rest;
-            reload = true;
             __syncwarp();
             if (!alive && !budget) break;                  // every clean candidate has its decisive hit
           }
