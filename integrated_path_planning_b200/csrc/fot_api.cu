@@ -526,7 +526,7 @@ static bool pair_geometry(const fot_handle* h, const fot_batch_t* b, PairGeom* g
   const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B, nx = h->plan.cfg.nx;
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const long long SPl = has_dyn ? (long long)b->S * b->P : 0;
-  if (NT > kPairNT || nd > kPairND || b->n_v_max > kPairNV || SPl > (1 << 20) || b->n_static > (1 << 20)) return false;
+  if (NT > kPairNT || nd > kPairND || b->n_v_max > kPairNV || nx > kPairNX || SPl > (1 << 20) || b->n_static > (1 << 20)) return false;
   if (SPl * std::max(1, b->T_obs) >= (1ll << 27)) return false;                            // list entries: element offsets
   const int SP = (int)SPl;
   PairGeom G{};
@@ -535,14 +535,12 @@ static bool pair_geometry(const fot_handle* h, const fot_batch_t* b, PairGeom* g
   const int max_viol = b->dyn_mode == FOT_DYN_DISTRIBUTION ? (int)std::floor(h->plan.cfg.chance_epsilon * (double)b->S) : 0;
   G.vwords = max_viol > 0 ? (b->S + 31) / 32 : 0;
   G.viol_bytes = (nd * G.vwords * 4 + 15) / 16 * 16;
-  G.spline_smem = nx <= 128 ? 1 : 0;
   const size_t dyn_bytes = (size_t)SP * b->T_obs * 16;
   const bool fuse = want_fused_box || h->opt.fused_box;
   auto layout = [&](bool stage) {
     size_t off = sizeof(PairShared);
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 15) / 16 * 16; return (int32_t)o; };
     const bool box = has_dyn && ((stage && fuse) || (size_t)SP * 16 <= 8 * 1024);
-    G.o_spl = take(G.spline_smem ? (size_t)9 * nx * 8 : 0);
     G.o_dyn = take(stage ? dyn_bytes : 0);
     G.o_box = take(box ? (size_t)SP * 16 : 0);
     G.o_viol = take((size_t)kPairWarps * G.viol_bytes);

@@ -40,10 +40,14 @@ namespace fot {
 constexpr int kPairThreads = FOT_PAIR_THREADS;   // CTA size of fot_sweep_pairs
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kPairList = 64;                    // obstacle list entries per cull chunk (per warp)
-constexpr int kPairQueue = 64;                   // survivor queue entries (per warp): < 32 pending + <= 32 new
-constexpr int kPairNT = 64;                      // samples per profile this kernel covers (longer time grids: fot_sweep_items)
+constexpr int kPairQueue = 64;                   // survivor queue (per warp, a ring): < 32 waiting + <= 32 new
+#ifndef FOT_PAIR_NT
+#define FOT_PAIR_NT 56
+#endif
+constexpr int kPairNT = FOT_PAIR_NT;                      // samples per profile this kernel covers (longer time grids: fot_sweep_items)
 constexpr int kPairND = 96;                      // lateral targets this kernel covers (wider grids: fot_sweep_items)
 constexpr int kPairNV = 52;                      // terminal speeds per query
+constexpr int kPairNX = 48;                      // spline knots (longer reference lines: fot_sweep_items)
 
 // One warp's private slice of shared memory, and behind the slices the CTA-wide tables whose size has a small bound.
 // The layout is a compile-time constant on purpose: every access is `base register + immediate`.  (With run-time
@@ -55,15 +59,18 @@ struct __align__(16) PairSlice {
   unsigned flags[kPairND / 4];         // validity flags, one byte per candidate
   unsigned hitw[4];                    // decisive collision, one bit per candidate
   unsigned cleanw[4];                  // kinematically clean
-  unsigned wl[kPairList];              // obstacle list: element offsets (bit 31: static)
+  unsigned wl[kPairList];              // obstacle list: element offsets; dynamic entries from the front (padded to a multiple
+                                       // of four), static entries (bit 31 set) from the back
   unsigned q_off[kPairQueue];          // survivor queue: obstacle element offset
-  unsigned short q_n[kPairQueue];      //                 sample
+  unsigned char q_n[kPairQueue];       //                 sample
   unsigned short slowq[kPairNT];       // samples with a low-speed candidate
+  double pc[16];                       // the pair's polynomials: quartic a0..a4 | lateral basis c0..c5, b3..b5 | hold
 };
 struct __align__(16) PairShared {
   PairSlice w[kPairWarps];
   double qc[12 + kPairNV];             // fs[6] | limits[4] | target | stop_dist | v_grid[n_v]
   double dgrid[kPairND + 2];           // lateral targets, then the brake ladder's single target 0.0
+  double spl[9][kPairNX];              // spline tables: knots | x: a b c d | y: a b c d
 };
 
 static_assert(offsetof(PairSlice, hitw) == offsetof(PairSlice, flags) + kPairND && offsetof(PairSlice, cleanw) == offsetof(PairSlice, hitw) + 16 &&
@@ -73,17 +80,54 @@ struct PairGeom {
   int32_t ctas_per_query;    // CTAs that share one query's pairs (1 in large batches)
   int32_t nw4, nwc, vwords;  // flag words (4 candidates each) / mask words (32 candidates each) / violation words per candidate
   int32_t stage_dyn;         // 1: the query's obstacle block is staged in shared memory by one bulk copy
-  int32_t spline_smem;       // 1: spline tables copied to shared memory
   int32_t box_smem;          // 1: trajectory boxes in shared memory (copied from fot_prepass, or built here when fused_box)
   int32_t fused_box;         // 1: boxes built by the CTA from its staged block (gated host-pointer call)
   // byte offsets into dynamic shared memory of the run-time sized tables (behind PairShared)
-  int32_t o_spl, o_dyn, o_box, o_viol;
+  int32_t o_dyn, o_box, o_viol;
   int32_t viol_bytes;        // per warp: [n_d][vwords] violation bitmaps (chance-constrained mode with a budget)
   // gated launch (see ItemGeom)
   int32_t gate_q0, gate_per;
   uint32_t gate_epoch;
   unsigned* gate;
 };
+
+// spline_ref_fast (fot_sweep_items.cuh) over the shared-memory tables of PairShared: compile-time strides.
+__device__ __forceinline__ RefFast spline_ref_smem(const double (*T)[kPairNX], int nx, double s) {
+  RefFast o;
+  if (!(s >= T[0][0] && s <= T[0][nx - 1])) {            // cs.py:62
+    o.rx = o.ry = o.cth = o.sth = o.rk = o.rdk = qnan();
+    return o;
+  }
+  int lo = 0, hi = nx;                                   // searchsorted(side='right') (cs.py:162)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (T[0][mid] <= s) lo = mid + 1; else hi = mid;
+  }
+  int seg = lo - 1;
+  seg = seg < 0 ? 0 : (seg > nx - 2 ? nx - 2 : seg);     // cs.py:165
+  const double dx = s - T[0][seg];
+  const double dx2 = dx * dx, dx3 = dx2 * dx;
+  const double xa = T[1][seg], xb = T[2][seg], xc = T[3][seg], xd = T[4][seg];
+  const double ya = T[5][seg], yb = T[6][seg], yc = T[7][seg], yd = T[8][seg];
+  o.rx = xa + xb * dx + xc * dx2 + xd * dx3;             // cs.py:73-74
+  o.ry = ya + yb * dx + yc * dx2 + yd * dx3;
+  const double x1 = xb + 2.0 * xc * dx + 3.0 * xd * dx2; // cs.py:100
+  const double y1 = yb + 2.0 * yc * dx + 3.0 * yd * dx2;
+  const double x2 = 2.0 * xc + 6.0 * xd * dx;            // cs.py:125
+  const double y2 = 2.0 * yc + 6.0 * yd * dx;
+  const double x3 = 6.0 * xd, y3 = 6.0 * yd;             // cs.py:149
+  const double D = x1 * x1 + y1 * y1;
+  const double rD = rsqrt_nr(D);
+  o.cth = x1 * rD;
+  o.sth = y1 * rD;
+  const double iD15 = rD * rD * rD;                      // D ** -1.5
+  o.rk = (y2 * x1 - x2 * y1) * iD15;                     // cs.py:246
+  const double a = x1 * y2 - y1 * x2;
+  const double b = x1 * y3 - y1 * x3;
+  const double c = x1 * x2 + y1 * y2;
+  o.rdk = b * iD15 - 3.0 * a * c * (iD15 * rD * rD);     // cs.py:273
+  return o;
+}
 
 template <bool kFused>
 __global__ void __launch_bounds__(kPairThreads, FOT_PAIR_MIN_CTAS)
@@ -92,7 +136,6 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   PairShared& S = *reinterpret_cast<PairShared*>(smb);
   double* qc = S.qc;
   double* dgrid = S.dgrid;
-  double* spl = reinterpret_cast<double*>(smb + G.o_spl);      // [9][nx] when spline_smem
   const double2* dynst = reinterpret_cast<const double2*>(smb + G.o_dyn);   // [SP][T_obs] when stage_dyn
   float4* sbox = reinterpret_cast<float4*>(smb + G.o_box);     // [SP] trajectory boxes when box_smem
   __shared__ int s_next;                 // next pair of this CTA
@@ -134,7 +177,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   unsigned* cleanw = W.cleanw;
   unsigned* wl = W.wl;
   unsigned* q_off = W.q_off;
-  unsigned short* q_n = W.q_n;
+  unsigned char* q_n = W.q_n;
   unsigned short* slowq = W.slowq;
   unsigned* viol = reinterpret_cast<unsigned*>(smb + G.o_viol + wid * G.viol_bytes);   // [n_d][vwords] (budget mode)
   (void)NT;
@@ -180,15 +223,15 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   else if (tid == 10) qc[10] = B.target[q];
   else if (tid == 11) qc[11] = B.stop_dist[q];
   for (int i = tid; i < n_v; i += bd) qc[12 + i] = B.v_grid[(size_t)q * B.n_v_max + i];
-  if (G.spline_smem) {
+  {
     const int nx = P.cfg.nx;
     for (int i = tid; i < nx; i += bd) {
-      spl[i] = P.knots[i];
-      spl[nx + i] = P.xa[i];      spl[3 * nx + i] = P.xc[i];
-      spl[5 * nx + i] = P.ya[i];  spl[7 * nx + i] = P.yc[i];
+      S.spl[0][i] = P.knots[i];
+      S.spl[1][i] = P.xa[i];  S.spl[3][i] = P.xc[i];
+      S.spl[5][i] = P.ya[i];  S.spl[7][i] = P.yc[i];
       if (i < nx - 1) {
-        spl[2 * nx + i] = P.xb[i]; spl[4 * nx + i] = P.xd[i];
-        spl[6 * nx + i] = P.yb[i]; spl[8 * nx + i] = P.yd[i];
+        S.spl[2][i] = P.xb[i]; S.spl[4][i] = P.xd[i];
+        S.spl[6][i] = P.yb[i]; S.spl[8][i] = P.yd[i];
       }
     }
   }
@@ -271,16 +314,6 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   const double fast2 = 0.25;                                                   // v > 0.5 (fp.py:1019)
   const double stop_dist = qc[11];
   const double kTan01Sq = 0.010067046422495888;                                // tan(0.1)^2
-  SplineView V;
-  V.nx = P.cfg.nx;
-  if (G.spline_smem) {
-    const int nx = V.nx;
-    V.knots = spl; V.xa = spl + nx; V.xb = spl + 2 * nx; V.xc = spl + 3 * nx; V.xd = spl + 4 * nx;
-    V.ya = spl + 5 * nx; V.yb = spl + 6 * nx; V.yc = spl + 7 * nx; V.yd = spl + 8 * nx;
-  } else {
-    V.knots = P.knots; V.xa = P.xa; V.xb = P.xb; V.xc = P.xc; V.xd = P.xd;
-    V.ya = P.ya; V.yb = P.yb; V.yc = P.yc; V.yd = P.yd;
-  }
   const float4* boxes = G.box_smem ? sbox : B.dyn_box + (size_t)q * SP;
 
   double my_cost = INFINITY;             // running arg-min over every pair this lane has seen
@@ -311,10 +344,38 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
     const int cand0 = brake ? n_grid * n_d + kk : (jT * n_v + kk) * n_d;      // generation order (fp.py:398-449)
     const double* dg = dgrid + (brake ? n_d : 0);             // lateral targets of this pair (brake: the single 0.0 slot)
 
-    // ---- phase A: the pair's private state -----------------------------------------------------------
+    // ---- phase A: the pair's private state, its polynomials --------------------------------------------
     flags[lane] = 0u;                                       // flags | hit words | clean words (32 words in a row)
     if (G.vwords > 0)
       for (int i = lane; i < n_d * G.vwords; i += 32) viol[i] = 0u;
+    {
+      // quartic solve of the pair (fp.py:619-647) and the lateral basis: d_i(t) = A(t) + d_i * B(t) -- the quintic's
+      // right-hand side is linear in the target (fp.py:676-683).  Once per pair; the passes reload the sixteen numbers.
+      Lon L;
+      double c0, c1, c2, c3, c4, c5, b3, b4, b5;
+      if (!brake) {
+        const double T = P.T[jT];
+        L = lon_solve(fs, qc[12 + kk], T, P.inv4 + 4 * jT, n_v == 1, N - 1);
+        const double* Ai = P.inv5 + 9 * jT;
+        c0 = fs[3]; c1 = fs[4]; c2 = fs[5] / 2.0;
+        const double r0 = -c0 - c1 * T - c2 * T * T, r1 = -c1 - 2.0 * c2 * T, r2 = -2.0 * c2;
+        c3 = fma(r2, Ai[2], fma(r1, Ai[1], r0 * Ai[0]));
+        c4 = fma(r2, Ai[5], fma(r1, Ai[4], r0 * Ai[3]));
+        c5 = fma(r2, Ai[8], fma(r1, Ai[7], r0 * Ai[6]));
+        b3 = Ai[0]; b4 = Ai[3]; b5 = Ai[6];
+      } else {                                                                     // one lateral profile per brake horizon (fp.py:480-482)
+        L = lon_solve(fs, 0.0, P.Tb[kk], P.inv4b + 4 * kk, true, P.n_steps_b[kk]);
+        const Lat Lb = lat_solve(fs, fs[3], P.Tb[kk], P.inv5b + 9 * kk, true, P.n_steps_b[kk]);
+        c0 = Lb.a0; c1 = Lb.a1; c2 = Lb.a2; c3 = Lb.a3; c4 = Lb.a4; c5 = Lb.a5;
+        b3 = b4 = b5 = 0.0;
+      }
+      if (lane == 0) {
+        double* pc = W.pc;
+        pc[0] = L.a0; pc[1] = L.a1; pc[2] = L.a2; pc[3] = L.a3; pc[4] = L.a4;
+        pc[5] = c0; pc[6] = c1; pc[7] = c2; pc[8] = c3; pc[9] = c4; pc[10] = c5; pc[11] = b3; pc[12] = b4; pc[13] = b5;
+        pc[14] = __longlong_as_double((long long)L.hold);
+      }
+    }
     __syncwarp();
 
     // ---- phases B + C, 32 samples at a time ---------------------------------------------------------
@@ -322,44 +383,25 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
     int nslow = 0;
     unsigned bxlo = 0xffffffffu, bxhi = 0u, bylo = 0xffffffffu, byhi = 0u;    // box of the reference points (ordered-uint floats)
     for (int n0 = 0; n0 < N; n0 += 32) {
-      const int n = n0 + lane;
-      const bool active = n < N;
-      double i_rx = 0, i_ry = 0, i_cth = 0, i_sth = 0, i_rk = 0, i_rdk = 0, i_sd = 0, i_sdd = 0, i_isd = 0;
-      double A0 = 0, B0 = 0, A1 = 0, B1 = 0, A2 = 0, B2 = 0;
-      if (active) {
-        // quartic solve of the pair (fp.py:619-647) -- a dozen flops per lane, all lanes alike
-        Lon L;
-        if (!brake)
-          L = lon_solve(fs, qc[12 + kk], P.T[jT], P.inv4 + 4 * jT, n_v == 1, N - 1);
-        else
-          L = lon_solve(fs, 0.0, P.Tb[kk], P.inv4b + 4 * kk, true, P.n_steps_b[kk]);
-        const bool held = n > L.hold;                                              // fp.py:487-499 brake padding
-        const TPow tp = tpow(held ? L.hold : n, dt);
-        const double s = L.a0 + L.a1 * tp.t + L.a2 * tp.t2 + L.a3 * tp.t3 + L.a4 * tp.t4;             // fp.py:644
-        i_sd = held ? 0.0 : L.a1 + 2.0 * L.a2 * tp.t + 3.0 * L.a3 * tp.t2 + 4.0 * L.a4 * tp.t3;      // fp.py:645
-        i_sdd = held ? 0.0 : 2.0 * L.a2 + 6.0 * L.a3 * tp.t + 12.0 * L.a4 * tp.t2;                    // fp.py:646
-        const RefFast rp = spline_ref_fast(V, s);
+      const int n = min(n0 + lane, N - 1);                   // lanes beyond the last sample repeat it (nothing of theirs is used)
+      const bool active = n0 + lane < N;
+      double i_rx, i_ry, i_cth, i_sth, i_rk, i_rdk, i_sd, i_sdd, i_isd;
+      double A0, B0, A1, B1, A2, B2;
+      {
+        const double* pc = W.pc;
+        const int hold = (int)__double_as_longlong(pc[14]);
+        const bool held = n > hold;                                                // fp.py:487-499 brake padding
+        const TPow tp = tpow(held ? hold : n, dt);
+        const double s = pc[0] + pc[1] * tp.t + pc[2] * tp.t2 + pc[3] * tp.t3 + pc[4] * tp.t4;             // fp.py:644
+        i_sd = held ? 0.0 : pc[1] + 2.0 * pc[2] * tp.t + 3.0 * pc[3] * tp.t2 + 4.0 * pc[4] * tp.t3;       // fp.py:645
+        i_sdd = held ? 0.0 : 2.0 * pc[2] + 6.0 * pc[3] * tp.t + 12.0 * pc[4] * tp.t2;                      // fp.py:646
+        const RefFast rp = spline_ref_smem(S.spl, P.cfg.nx, s);
         i_rx = rp.rx; i_ry = rp.ry; i_cth = rp.cth; i_sth = rp.sth; i_rk = rp.rk; i_rdk = rp.rdk;
         i_isd = fabs(i_sd) > 1e-3 ? rcp_nr(i_sd) : 0.0;                            // fp.py:792 EPS_S_DOT
-        // lateral basis at this sample: d_i(t) = A(t) + d_i * B(t) (the quintic's right-hand side is linear
-        // in the target, fp.py:676-683); Horner with running derivatives
-        double c0, c1, c2, c3, c4, c5, b3, b4, b5;
-        if (!brake) {
-          const double T = P.T[jT];
-          const double* Ai = P.inv5 + 9 * jT;
-          c0 = fs[3]; c1 = fs[4]; c2 = fs[5] / 2.0;
-          const double r0 = -c0 - c1 * T - c2 * T * T, r1 = -c1 - 2.0 * c2 * T, r2 = -2.0 * c2;
-          c3 = fma(r2, Ai[2], fma(r1, Ai[1], r0 * Ai[0]));
-          c4 = fma(r2, Ai[5], fma(r1, Ai[4], r0 * Ai[3]));
-          c5 = fma(r2, Ai[8], fma(r1, Ai[7], r0 * Ai[6]));
-          b3 = Ai[0]; b4 = Ai[3]; b5 = Ai[6];
-        } else {                                                                   // one lateral profile per brake horizon (fp.py:480-482)
-          const Lat Lb = lat_solve(fs, fs[3], P.Tb[kk], P.inv5b + 9 * kk, true, P.n_steps_b[kk]);
-          c0 = Lb.a0; c1 = Lb.a1; c2 = Lb.a2; c3 = Lb.a3; c4 = Lb.a4; c5 = Lb.a5;
-          b3 = b4 = b5 = 0.0;
-        }
         {
+          // Horner with running derivatives
           const double t = tp.t;
+          const double c0 = pc[5], c1 = pc[6], c2 = pc[7], c3 = pc[8], c4 = pc[9], c5 = pc[10], b3 = pc[11], b4 = pc[12], b5 = pc[13];
           double pA = fma(c5, t, c4), dA = c5, ddA;
           ddA = dA;               dA = fma(dA, t, pA);  pA = fma(pA, t, c3);
           ddA = fma(ddA, t, dA);  dA = fma(dA, t, pA);  pA = fma(pA, t, c2);
@@ -397,7 +439,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
       const bool chk = valid && n >= 1;                                            // limits skip index 0 (fp.py:964-983)
       const unsigned keep4 = chk ? 0xffffffffu : F_DROP * 0x01010101u;             // n = 0: only the drop guards apply
       // per-item affine coefficients in d_i
-      const int np_ = chk ? n - 1 : (active ? n : 0);                             // the previous sample (itself at n = 0)
+      const int np_ = chk ? n - 1 : n;                                            // the previous sample (itself at n = 0)
       const double p_rx = R(0, np_), p_ry = R(1, np_), p_cth = R(2, np_), p_sth = R(3, np_), p_A0 = R(8, np_), p_B0 = R(9, np_);
       const double sd2 = i_sd * i_sd, isd2 = i_isd * i_isd;
       const double Q0 = fma(-i_rk, A0, 1.0), Q1 = -(i_rk * B0);                    // q = 1 - kappa_r d
@@ -486,8 +528,19 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
         flag_gt(acc, lat_lhs, lat_rhs, F_LAT << sh);                               // fp.py:975  v^2 |kappa| > a_lat
       };
       auto sweep_targets = [&](auto lite_tag) {
+        constexpr bool kLiteLoop = decltype(lite_tag)::value;
 #pragma unroll 1
         for (int i0 = 0; i0 < n_dl; i0 += 4) {
+          const int left = n_dl - i0;
+          const unsigned tailm = left >= 4 ? 0xffffffffu : (1u << (8 * left)) - 1u;
+          if (n0 > 0) {
+            // a quad whose candidates all carry, from the earlier samples, a flag that outranks everything this loop
+            // can still add (fp.py:964-991: drop > speed > acceleration > the rest) is settled
+            constexpr unsigned kTop = (kLiteLoop ? (F_DROP | F_SPEED | F_ACCEL) : F_DROP) * 0x01010101u;
+            const unsigned t = flags[i0 >> 2] & kTop;
+            const unsigned nz = (((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;      // bit 7 of every non-zero byte
+            if (((nz | ~tailm) & 0x80808080u) == 0x80808080u) continue;
+          }
           unsigned acc = 0u;
           if (valid) {
             // the last quad repeats the last target (its bytes are masked off below): one code path for every grid size
@@ -495,8 +548,6 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
             const double g0 = dg[i0], g1 = dg[min(i0 + 1, l)], g2 = dg[min(i0 + 2, l)], g3 = dg[min(i0 + 3, l)];
             sample(lite_tag, g0, acc, 0u); sample(lite_tag, g1, acc, 8u); sample(lite_tag, g2, acc, 16u); sample(lite_tag, g3, acc, 24u);
           }
-          const int left = n_dl - i0;
-          const unsigned tailm = left >= 4 ? 0xffffffffu : (1u << (8 * left)) - 1u;
           const unsigned red = __reduce_or_sync(full, acc & keep4 & tailm);
           if (lane == 0 && red) flags[i0 >> 2] |= red;           // the warp owns the pair: a plain read-modify-write
         }
@@ -602,43 +653,68 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
         // test of every kept sample against the listed obstacles, lane = sample, survivors -> queue by ballot + prefix
         // count, (3) exact tests of 32 queued (sample, obstacle) entries, lane = entry, against every live clean candidate.
         int j0 = 0;                                        // next obstacle to list
-        int nl = 0, n_st = 0, e = 0, c0 = keep;            // current list (static entries first), next entry, first sample of the current pass (>= keep: list done)
-        int qn = 0;                                        // queued survivors
+        int nl = 0, n_st = 0;                              // current list: dynamic entries wl[0, nl), static entries wl[kPairList - n_st, kPairList)
+        int c0 = keep;                                     // first sample of the next window pass (>= keep: the list is done)
+        unsigned rel_lo = 0u, rel_hi = 0u;                 // this lane's survivors of the last window pass not queued yet: bit e <-> wl[e]
+        int pn = 0;                                        // ... and the lane's sample in that pass
+        unsigned qh = 0u;                                  // survivor ring: head and
+        int qn = 0;                                        //                number of queued entries
+        bool finished = false;                             // every obstacle listed, every pass done
         // 32-bit shared-space addresses for the two hot loops (a generic pointer costs the compiler a register pair, or a
         // recomputation from the thread index, per access)
         unsigned wl_a = smem_u32(wl), dg_a = smem_u32(dg), dyn_a = smem_u32(dynst);
         asm volatile("" : "+r"(wl_a), "+r"(dg_a), "+r"(dyn_a));     // opaque: keep them in registers, do not recompute per use
 #pragma unroll 1
         for (;;) {
-          if (c0 >= keep && j0 < n_obs) {
-            // (1) obstacle list, lane = obstacle
-            nl = 0; n_st = 0;
+          const unsigned pend = __ballot_sync(full, (rel_lo | rel_hi) != 0u);
+          if (pend) {
+            // (2b) one survivor of every lane that has any -> queue (ballot + prefix count)
+            if (rel_lo | rel_hi) {
+              int e;
+              if (rel_lo) { e = __ffs(rel_lo) - 1; rel_lo &= rel_lo - 1u; }
+              else { e = 32 + __ffs(rel_hi) - 1; rel_hi &= rel_hi - 1u; }
+              const unsigned slot = (qh + (unsigned)qn + __popc(pend & lt_mask)) & (kPairQueue - 1);
+              q_off[slot] = wl[e];
+              q_n[slot] = (unsigned char)pn;
+            }
+            qn += __popc(pend);
+            if (qn < 32) continue;
+          } else if (!finished) {
+            if (c0 >= keep) {
+              if (j0 >= n_obs) { finished = true; continue; }
+              // (1) obstacle list, lane = obstacle
+              nl = 0; n_st = 0;
 #pragma unroll 1
-            do {
-              const int j = j0 + lane;
-              bool in = false;
-              unsigned ent = 0u;
-              if (j < M) {
-                const double2 o = stat_q[j];
-                in = o.x >= (double)bx0 && o.x <= (double)bx1 && o.y >= (double)by0 && o.y <= (double)by1;
-                ent = 0x80000000u | (unsigned)j;
-              } else if (j < n_obs) {
-                const float4 ob = boxes[j - M];                   // xmin xmax ymin ymax
-                in = ob.x <= bx1 && ob.y >= bx0 && ob.z <= by1 && ob.w >= by0;
-                ent = (unsigned)((j - M) * B.T_obs);
-              }
-              const unsigned m = __ballot_sync(full, in);
-              if (in) wl[nl + __popc(m & lt_mask)] = ent;
-              nl += __popc(m);
-              if (j0 < M) n_st += __popc(M - j0 >= 32 ? m : m & ((1u << (M - j0)) - 1u));   // statics come first
-              j0 += 32;
-            } while (j0 < n_obs && nl <= kPairList - 32);
-            __syncwarp();
-            if (nl > 0) { c0 = 0; e = 0; }
-            continue;
-          }
-          if (c0 < keep) {
-            // (2) window tests of this pass's samples against list entries e.. until a full drain is queued:
+              do {
+                const int j = j0 + lane;
+                bool in = false;
+                unsigned ent = 0u;
+                if (j < M) {
+                  const double2 o = stat_q[j];
+                  in = o.x >= (double)bx0 && o.x <= (double)bx1 && o.y >= (double)by0 && o.y <= (double)by1;
+                  ent = 0x80000000u | (unsigned)j;
+                } else if (j < n_obs) {
+                  const float4 ob = boxes[j - M];                   // xmin xmax ymin ymax
+                  in = ob.x <= bx1 && ob.y >= bx0 && ob.z <= by1 && ob.w >= by0;
+                  ent = (unsigned)((j - M) * B.T_obs);
+                }
+                const unsigned m = __ballot_sync(full, in);
+                const unsigned ms = j0 >= M ? 0u : (M - j0 >= 32 ? m : m & ((1u << (M - j0)) - 1u));   // the static lanes of this chunk
+                if (in) {
+                  if (j < M) wl[kPairList - 1 - n_st - __popc(ms & lt_mask)] = ent;
+                  else wl[nl + __popc((m & ~ms) & lt_mask)] = ent;
+                }
+                n_st += __popc(ms);
+                nl += __popc(m & ~ms);
+                j0 += 32;
+              } while (j0 < n_obs && nl + n_st <= kPairList - 32 - 3);
+              __syncwarp();
+              if (nl > 0 && lane < ((4 - nl) & 3)) wl[nl + lane] = wl[nl - 1];   // pad to a multiple of four (the copies' bits are masked)
+              __syncwarp();
+              if (nl + n_st > 0) c0 = 0;
+              continue;
+            }
+            // (2a) window test of this pass's samples against the whole list, lane = sample, no votes: a bit per entry.
             // along = (o - ref).t within the collision radius, across = (o - ref).n within the radius of the
             // lateral offsets the pair's clean candidates take at this sample
             const int cn_ = c0 + lane;
@@ -652,54 +728,64 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
             // a lane beyond the kept samples gets an empty window
             const double w_lo = cv ? d_lo - rc_d : inf, w_hi = d_hi + rc_d;
             const int kob = B.T_obs > 0 ? min(cn_, B.T_obs - 1) : 0;               // clip(round(t/dt)) = n (fp.py:1226-1227)
-            unsigned obs_a = dyn_a + 16u * (unsigned)kob;                          // this sample's time step (staged block)
-            asm volatile("" : "+r"(obs_a));
-            const double2* obs_g = dyn_q + kob;                                    // (resident tensor)
-            // kind 0: static entries [e, n_st) of the list; 1: dynamic entries, staged block; 2: dynamic entries, resident tensor
-            auto produce = [&](auto kind_tag, int e_end) {
-              constexpr int kKind = decltype(kind_tag)::value;
-#pragma unroll 1
-              for (; e < e_end; ++e) {
-                unsigned off;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(wl_a + 4u * (unsigned)e) : "memory");
-                double2 o;
-                bool rel;
-                if (kKind == 0) {
-                  o = stat_q[off & 0x7fffffffu];
-                  const double al = fma(o.x, c_cth, fma(o.y, c_sth, nca));
-                  const double ac = fma(o.y, c_cth, fma(o.x, n_sth, ncn));
-                  rel = cv & (fabs(al) <= rc_s) & (ac >= d_lo - rc_s) & (ac <= d_hi + rc_s);
-                } else {
-                  if (kKind == 1) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o.x), "=d"(o.y) : "r"(obs_a + 16u * off) : "memory");
-                  else o = obs_g[off];
-                  const double al = fma(o.x, c_cth, fma(o.y, c_sth, nca));
-                  const double ac = fma(o.y, c_cth, fma(o.x, n_sth, ncn));
-                  rel = (fabs(al) <= rc_d) & (ac >= w_lo) & (ac <= w_hi);          // NaN -> false
-                }
-                const unsigned m = __ballot_sync(full, rel);
-                if (m) {
-                  if (rel) { const int slot = qn + __popc(m & lt_mask); q_off[slot] = off; q_n[slot] = (unsigned short)cn_; }
-                  qn += __popc(m);
-                  if (qn >= 32) { ++e; break; }
-                }
-              }
+            auto window = [&](const double2 o) {
+              const double al = fma(o.x, c_cth, fma(o.y, c_sth, nca));
+              const double ac = fma(o.y, c_cth, fma(o.x, n_sth, ncn));
+              return (fabs(al) <= rc_d) & (ac >= w_lo) & (ac <= w_hi);             // NaN -> false
             };
-            if (e < n_st) produce(std::integral_constant<int, 0>{}, n_st);
-            if (e >= n_st && qn < 32) {
-              if (G.stage_dyn) produce(std::integral_constant<int, 1>{}, nl); else produce(std::integral_constant<int, 2>{}, nl);
+            unsigned lo = 0u, hi = 0u;
+            if (G.stage_dyn) {
+              // staged block: four entries per iteration
+              unsigned obs_a = dyn_a + 16u * (unsigned)kob;                        // this sample's time step
+              asm volatile("" : "+r"(obs_a));
+#pragma unroll 1
+              for (int e = 0; e < nl; e += 4) {
+                unsigned f0, f1, f2, f3;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f0), "=r"(f1), "=r"(f2), "=r"(f3) : "r"(wl_a + 4u * (unsigned)e) : "memory");
+                double2 o0, o1, o2, o3;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o0.x), "=d"(o0.y) : "r"(obs_a + 16u * f0) : "memory");
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o1.x), "=d"(o1.y) : "r"(obs_a + 16u * f1) : "memory");
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o2.x), "=d"(o2.y) : "r"(obs_a + 16u * f2) : "memory");
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o3.x), "=d"(o3.y) : "r"(obs_a + 16u * f3) : "memory");
+                unsigned nib = 0u;
+                if (window(o0)) nib |= 1u;
+                if (window(o1)) nib |= 2u;
+                if (window(o2)) nib |= 4u;
+                if (window(o3)) nib |= 8u;
+                if (e < 32) lo |= nib << e; else hi |= nib << (e - 32);
+              }
+            } else {
+              // resident tensor
+              const double2* obs_g = dyn_q + kob;
+#pragma unroll 1
+              for (int e = 0; e < nl; ++e)
+                if (window(obs_g[wl[e]])) { if (e < 32) lo |= 1u << e; else hi |= 1u << (e - 32); }
             }
-            if (e >= nl) { e = 0; c0 += 32; }
+            lo &= nl >= 32 ? 0xffffffffu : (1u << nl) - 1u;                        // the padding's bits
+            hi &= nl <= 32 ? 0u : (1u << (nl - 32)) - 1u;
+#pragma unroll 1
+            for (int k = 0; k < n_st; ++k) {                                       // static entries, from the back of the list
+              const int e = kPairList - 1 - k;
+              const double2 o = stat_q[wl[e] & 0x7fffffffu];
+              const double al = fma(o.x, c_cth, fma(o.y, c_sth, nca));
+              const double ac = fma(o.y, c_cth, fma(o.x, n_sth, ncn));
+              if (cv & (fabs(al) <= rc_s) & (ac >= d_lo - rc_s) & (ac <= d_hi + rc_s)) { if (e < 32) lo |= 1u << e; else hi |= 1u << (e - 32); }
+            }
+            rel_lo = lo; rel_hi = hi; pn = cn_;
+            c0 += 32;
+            continue;
+          } else if (qn == 0) {
+            break;
           }
-          const bool finished = c0 >= keep && j0 >= n_obs;
-          if (qn < 32 && !finished) continue;
-          if (qn > 0) {
+          {
             // (3) exact tests of the first min(qn, 32) queued entries: uniform loop over the live clean candidates,
             // one ballot per candidate
             __syncwarp();
             const int cnt = min(qn, 32);
             const bool lv = lane < cnt;
-            const unsigned off = lv ? q_off[lane] : 0u;
-            const int en = lv ? (int)q_n[lane] : 0;
+            const unsigned qslot = (qh + (unsigned)lane) & (kPairQueue - 1);
+            const unsigned off = lv ? q_off[qslot] : 0u;
+            const int en = lv ? (int)q_n[qslot] : 0;
             const bool is_dyn = !(off >> 31);
             const unsigned el = off & 0x7fffffffu;
             double2 o = make_double2(0.0, 0.0);
@@ -762,17 +848,11 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
               if (nh && lane == 0) hitw[w] |= nh;
               alive |= (cleanw[w] & ~(hitw[w] | nh)) != 0u;
             }
-            // the entries behind the drained ones move to the front
-            const int rest = qn - cnt;
-            const unsigned t_off = lane < rest ? q_off[32 + lane] : 0u;
-            const unsigned short t_n = lane < rest ? q_n[32 + lane] : (unsigned short)0;
-            __syncwarp();
-            if (lane < rest) { q_off[lane] = t_off; q_n[lane] = t_n; }
-            qn = rest;
+            qh += (unsigned)cnt;
+            qn -= cnt;
             __syncwarp();
             if (!alive && !budget) break;                  // every clean candidate has its decisive hit
           }
-          if (finished && qn == 0) break;
         }
       }
     }
