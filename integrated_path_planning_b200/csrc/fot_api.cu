@@ -69,7 +69,7 @@ struct Options {
   int qcap = 1024;             // FOT_QCAP           collision queue entries (tests force the queue-full path)
   int fused_box = 0;           // FOT_FUSED_BOX      1: trajectory boxes in the sweep even for a resident tensor
   int stage_dyn = 1;           // FOT_STAGE_DYN      0: never stage the obstacle block in shared memory
-  int sweep = 0;               // FOT_SWEEP          0 auto (fot_sweep_items, else the candidate-major kernel), 1 "items" (fail if
+  int sweep = 0;               // FOT_SWEEP          0 auto (fot_sweep_pairs, else fot_sweep_items, else the candidate-major kernel), 1 "items" (fail if
                                //                    unsupported), 2 "generic" (candidate-major kernel), 3 "warp" (fot_sweep_warp: two
                                //                    barriers per block + barrier-free collision queue; measured equal to "items",
                                //                    DESIGN.md section 4c; fail if unsupported)
@@ -635,10 +635,10 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
     ig.blocks_per_query = wg.blocks_per_query; ig.ctas_per_query = wg.ctas_per_query; ig.threads = wg.threads;
     ig.fused_box = wg.fused_box;
   }
-  // the pair-per-warp kernel on request (FOT_SWEEP=pairs)
+  // the pair-per-warp kernel: the default wherever its shape limits allow (FOT_SWEEP=pairs insists on it)
   PairGeom pg{};
   size_t psmem = 0;
-  bool use_pairs = h->opt.sweep == 4 && pair_geometry(h, b, &pg, &psmem, gate.word != nullptr);
+  bool use_pairs = (h->opt.sweep == 0 || h->opt.sweep == 4) && use_items && pair_geometry(h, b, &pg, &psmem, gate.word != nullptr);
   if (use_pairs && gate.word && !pg.fused_box) use_pairs = false;
   if (h->opt.sweep == 4 && !use_pairs && !gate.word) return fail(FOT_ERR_ARG, "FOT_SWEEP=pairs: shape not supported by fot_sweep_pairs");
   if (use_pairs) {

@@ -142,7 +142,7 @@ def test_config5_rollout_500_steps():
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("kernel", ["items", "generic"])
+@pytest.mark.parametrize("kernel", ["pairs", "items", "generic"])
 def test_config3_dense_grid_against_the_reference(variant, kernel):
     """Campaign D = BASELINE config 3 at its stated size, BOTH sweep kernels against one recorded reference run
     (59.8 s of NumPy): per-candidate categories, costs, winner."""

@@ -94,15 +94,19 @@ def test_full_collision_queue_degrades_to_in_place_tests():
     base = run()
     with _env(FOT_SWEEP="warp"):                           # the two-barrier kernel (73 entries per query)
         warp = run()
-    with _env(FOT_QCAP=4):
+    with _env(FOT_SWEEP="items"):                          # the sample-major kernel (the default is fot_sweep_pairs)
+        items = run()
+    with _env(FOT_SWEEP="items", FOT_QCAP=4):
         capped = run()
-    with _env(FOT_STAGE_DYN=0, FOT_BPC=1):
+    with _env(FOT_SWEEP="items", FOT_STAGE_DYN=0, FOT_BPC=1):
         unstaged = run()
+    with _env(FOT_STAGE_DYN=0, FOT_PAIR_CPQ=8):
+        unstaged_pairs = run()
     with _env(FOT_SWEEP="warp", FOT_STAGE_DYN=0, FOT_BPC=1):
         unstaged_warp = run()
     with _env(FOT_SWEEP="generic"):
         generic = run()
-    for other in (warp, capped, unstaged, unstaged_warp, generic):
+    for other in (warp, items, capped, unstaged, unstaged_pairs, unstaged_warp, generic):
         assert np.array_equal(base.cand_cat, other.cand_cat)
         assert np.array_equal(base.best_idx, other.best_idx) and np.array_equal(base.stats, other.stats)
         assert np.array_equal(base.best_cost.view(np.uint64), other.best_cost.view(np.uint64))
@@ -171,7 +175,7 @@ def test_gated_upload_pipeline_matches_the_single_launch():
         ref = run()
         ref = {k: getattr(ref, k).copy() for k in keys}
     assert len(set(ref["best_idx"].tolist())) > 20
-    variants = [dict(), dict(FOT_SWEEP="warp"), dict(FOT_SWEEP="warp", FOT_GATED=0), dict(FOT_GATED=0), dict(FOT_GATED=0, FOT_HOST_STREAMS=1), dict(FOT_GATE_UPLOADS=7),
+    variants = [dict(), dict(FOT_SWEEP="items"), dict(FOT_SWEEP="items", FOT_GATED=0), dict(FOT_SWEEP="warp"), dict(FOT_SWEEP="warp", FOT_GATED=0), dict(FOT_GATED=0), dict(FOT_GATED=0, FOT_HOST_STREAMS=1), dict(FOT_GATE_UPLOADS=7),
                 dict(FOT_GATE_UPLOADS=64, FOT_GATE_COPY_STREAMS=2), dict(FOT_GATE_MEMCPY=1, FOT_CHUNK_WAVES="1,1"),
                 dict(FOT_GATE_TAIL_BPC=1), dict(FOT_GATE_FLAG_STREAM=1), dict(FOT_STAGE_DYN=0), dict(FOT_STAGE_DYN=0, FOT_HOST_STREAMS=1), dict(FOT_GATED=0, FOT_HOST_CHUNKS=1, FOT_FUSED_BOX=1),
                 dict(FOT_SWEEP="warp", FOT_GATED=0, FOT_HOST_CHUNKS=1, FOT_FUSED_BOX=1)]
