@@ -237,7 +237,7 @@ def _ncu_traffic():
     """DRAM bytes per query of the sweep kernel from the newest committed ncu --set full summary (profiles/)."""
     import glob
     import re
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "sweep_items_ncu_full_summary.txt")), reverse=True):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "sweep_pairs_ncu_full_summary.txt")), reverse=True):
         txt = open(path).read()
         rd = re.search(r"dram__bytes_read\.sum\s+([\d.]+)\s*(\w*)", txt)
         wr = re.search(r"dram__bytes_write\.sum\s+([\d.]+)\s*(\w*)", txt)
@@ -602,7 +602,8 @@ def main():
                 "frac": achieved_tf / peak.value,
                 "traffic": per_q * Q if per_q else None,
                 "traffic_source": f"constant from {src} (ncu --set full, dram read + write bytes per query x queries); not measured in this run" if src else None,
-                "kernel": "fot_sweep_items", "kernel_ms": sweep_ms,
+                "kernel": {4: "fot_sweep_pairs", 1: "fot_sweep_items", 3: "fot_sweep_warp", 2: "fot_sweep"}.get(
+                    int(eng.lib.fot_last_sweep_kind(eng._h)), "?"), "kernel_ms": sweep_ms,
                 "stage_ms": {"prepass": float(stage[:, 0].mean()), "sweep": sweep_ms, "winner": float(stage[:, 2].mean())},
                 "peak_source": "fot_probe_fma_tflops on this GPU (dependent-chain DFMA, 2 FLOP/FMA); "
                                "MEASURED_PEAKS.json has no FP64 figure",

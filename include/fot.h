@@ -27,9 +27,10 @@
 extern "C" {
 #endif
 
-#define FOT_ABI_VERSION 5   /* 2: + prediction post-processing and safety metrics; 3: + fot_plan_batch_device_to_host;
+#define FOT_ABI_VERSION 6   /* 2: + prediction post-processing and safety metrics; 3: + fot_plan_batch_device_to_host;
                                4: + fot_result_t.winner_samples, fot_fetch_winners, fot_reload_options;
-                               5: + fot_set_result_mirror, fot_peer_* (gather of a sharded sweep over peer memory) */
+                               5: + fot_set_result_mirror, fot_peer_* (gather of a sharded sweep over peer memory);
+                               6: + fot_last_sweep_kind (fot_sweep_pairs is the default sweep kernel) */
 #define FOT_MAX_CIRCLES 8
 #define FOT_N_STATS 8    /* ok, max_speed, max_accel, max_curvature, max_lat_accel, road_bound, collision, stop_distance */
 #define FOT_N_SERIES 15  /* t s s_d s_dd s_ddd d d_d d_dd d_ddd x y yaw c v a  (data_structures.py:149-181) */
@@ -206,6 +207,11 @@ int fot_reload_options(fot_handle_t* h);
 /* Device-side time of the kernels of the last fot_plan_batch_* call on this handle, in ms (CUDA events; for a call that
  * was cut into chunks / ranges: from the first chunk's start to the last kernel of any chunk); negative if unavailable. */
 float fot_last_kernel_ms(const fot_handle_t* h);
+
+/* Which sweep kernel the last launch on this handle used: 4 fot_sweep_pairs (one longitudinal profile per warp; the
+ * default), 1 fot_sweep_items (sample-major with block barriers; shapes beyond the limits of fot_sweep_pairs), 3
+ * fot_sweep_warp (FOT_SWEEP=warp), 2 fot_sweep (candidate-major; very long time grids), 0 none yet. */
+int fot_last_sweep_kind(const fot_handle_t* h);
 
 /* Device time of the three stages of the `back`-th most recent launch on this handle (0 = the
  * last one; the handle keeps the last 256), in ms, from CUDA events on the launching stream:

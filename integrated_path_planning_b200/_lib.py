@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfot.so")
 
-FOT_ABI_VERSION = 5
+FOT_ABI_VERSION = 6
 FOT_MAX_CIRCLES = 8
 FOT_N_STATS = 8
 FOT_N_SERIES = 15
@@ -87,6 +87,7 @@ SYMBOLS = (
     ("fot_fetch_winners", C.c_int, (C.c_void_p, C.c_int, C.c_int, C.c_void_p)),
     ("fot_reload_options", C.c_int, (C.c_void_p,)),
     ("fot_last_kernel_ms", C.c_float, (C.c_void_p,)),
+    ("fot_last_sweep_kind", C.c_int, (C.c_void_p,)),
     ("fot_launch_stage_ms", C.c_int, (C.c_void_p, C.c_int, C.POINTER(C.c_float * 3))),
     ("fot_probe_fma_tflops", C.c_int, (C.c_int, C.c_int, c_double_p)),
     ("fot_predict_cv_device", C.c_int, (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

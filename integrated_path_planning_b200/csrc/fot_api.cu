@@ -76,6 +76,7 @@ struct Options {
                                //                    4 "pairs" (fot_sweep_pairs: one longitudinal profile per warp, no block
                                //                    barriers; fail if unsupported)
   int pair_cpq = 0;            // FOT_PAIR_CPQ       CTAs per query of fot_sweep_pairs (0: rule of pair_geometry)
+  int pair_simple = 1;         // FOT_PAIR_SIMPLE    0: never the campaign-shape instantiation of fot_sweep_pairs (tests)
   int host_chunks = 0;         // FOT_HOST_CHUNKS    equal chunks of the host-pointer call (0: rule)
   std::string chunk_waves;     // FOT_CHUNK_WAVES    chunk sizes in sweep waves, "1,2,3" (+ the rest)
   int host_streams = 2;        // FOT_HOST_STREAMS   1: chunks on one compute stream
@@ -96,6 +97,7 @@ struct Options {
     stage_dyn = geti("FOT_STAGE_DYN", 1) != 0;
     if (const char* e = getenv("FOT_SWEEP")) sweep = !strcmp(e, "generic") ? 2 : !strcmp(e, "items") ? 1 : !strcmp(e, "warp") ? 3 : !strcmp(e, "pairs") ? 4 : 0;
     pair_cpq = geti("FOT_PAIR_CPQ", 0);
+    pair_simple = geti("FOT_PAIR_SIMPLE", 1) != 0;
     host_chunks = geti("FOT_HOST_CHUNKS", 0);
     if (const char* e = getenv("FOT_CHUNK_WAVES")) chunk_waves = e;
     host_streams = geti("FOT_HOST_STREAMS", 2);
@@ -135,7 +137,7 @@ struct fot_handle {
   int smem_optin = 0;
   int sms = 148;                     // SM count of the device (block-per-CTA grouping, host chunk sizes)
   Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_box, cost_tab;   // device scratch
-  int last_sweep_kind = 0;           // 1: fot_sweep_items, 2: fot_sweep (generic)
+  int last_sweep_kind = 0;           // 4: fot_sweep_pairs, 1: fot_sweep_items, 3: fot_sweep_warp, 2: fot_sweep (generic)
   fot_result_t mirror{};             // fot_set_result_mirror: second destination of the winner block (all null: none)
   unsigned* mirror_flag = nullptr;   // word published behind each mirrored launch (fot_set_result_mirror), or null
   unsigned mirror_seq = 0;
@@ -238,8 +240,10 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   CK(cudaFuncSetAttribute(fot_sweep_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-  CK(cudaFuncSetAttribute(fot_sweep_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-  CK(cudaFuncSetAttribute(fot_sweep_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_pairs<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_pairs<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_pairs<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  CK(cudaFuncSetAttribute(fot_sweep_pairs<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   { std::lock_guard<std::mutex> lk(g_live_mu); g_live.insert(h); }
   guard.h = nullptr;
   *out = h;
@@ -753,8 +757,14 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
                                                                (const double2*)b->dyn, dyn_box, n_traj, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
-  if (use_pairs && pg.fused_box) fot_sweep_pairs<true><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
-  else if (use_pairs) fot_sweep_pairs<false><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
+  // the campaign shape (no static obstacles, one circle, no violation budget, staged block, no per-candidate outputs)
+  // runs the instantiation with everything else compiled out
+  const bool simple = use_pairs && h->opt.pair_simple && b->n_static == 0 && h->plan.cfg.n_circles == 0 && pg.vwords == 0 &&
+                      pg.stage_dyn && pg.box_smem && h->plan.d_sorted && !r->cand_cat && !r->cand_cost;
+  if (use_pairs && pg.fused_box && simple) fot_sweep_pairs<true, true><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
+  else if (use_pairs && pg.fused_box) fot_sweep_pairs<true, false><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
+  else if (use_pairs && simple) fot_sweep_pairs<false, true><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
+  else if (use_pairs) fot_sweep_pairs<false, false><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
   else if (use_warp && wg.fused_box) fot_sweep_warp<true><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
   else if (use_warp) fot_sweep_warp<false><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
   else if (use_items && ig.fused_box) fot_sweep_items<true><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
@@ -1292,6 +1302,8 @@ extern "C" float fot_last_kernel_ms(const fot_handle_t* h) {
   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
   return ms;
 }
+
+extern "C" int fot_last_sweep_kind(const fot_handle_t* h) { return h ? h->last_sweep_kind : 0; }
 
 extern "C" int fot_launch_stage_ms(const fot_handle_t* h, int back, float ms[3]) {
   if (!h || !ms || back < 0 || back >= fot_handle::kRing || back >= h->n_launch)

@@ -129,9 +129,16 @@ __device__ __forceinline__ RefFast spline_ref_smem(const double (*T)[kPairNX], i
   return o;
 }
 
-template <bool kFused>
+// kFused: the variant of the gated host-pointer call (waits for its query's upload slice, boxes the trajectories itself).
+// kSimple: the batch has no static obstacles, one collision circle, no violation budget, a sorted lateral grid, a staged
+// obstacle block and no per-candidate outputs -- the shape of a planning campaign.  The kernel is bound by instruction
+// fetch, so the code of the other modes is compiled out of this instantiation instead of being
+// branched over.
+template <bool kFused, bool kSimple>
 __global__ void __launch_bounds__(kPairThreads, FOT_PAIR_MIN_CTAS)
-fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
+fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
+  Out O = O_;
+  if (kSimple) { O.cand_cat = nullptr; O.cand_cost = nullptr; }
   extern __shared__ __align__(16) unsigned char smb[];
   PairShared& S = *reinterpret_cast<PairShared*>(smb);
   double* qc = S.qc;
@@ -165,7 +172,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
 
   const bool has_dyn = B.dyn_raw != nullptr;
   const int SP = has_dyn ? B.S * B.P : 0;
-  const int M = B.static_raw ? B.n_static : 0;
+  const int M = kSimple ? 0 : (B.static_raw ? B.n_static : 0);
   const double2* dyn_q = has_dyn ? reinterpret_cast<const double2*>(B.dyn_raw) + (size_t)q * SP * B.T_obs : nullptr;
   const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
 
@@ -205,7 +212,9 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
     __syncthreads();
     if (s_abort) return;
   }
-  const bool staged = G.stage_dyn && state_ok;
+  const bool stage_dyn = kSimple || G.stage_dyn, box_smem = kSimple || G.box_smem, d_sorted = kSimple || P.d_sorted;
+  const int vwords = kSimple ? 0 : G.vwords;
+  const bool staged = stage_dyn && state_ok;
   if (tid == 0) {
     if (staged) {
       mbar_init(&s_bar, 1);
@@ -235,7 +244,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
       }
     }
   }
-  if (G.box_smem && !G.fused_box && state_ok)
+  if (box_smem && !G.fused_box && state_ok)
     for (int j = tid; j < SP; j += bd) sbox[j] = B.dyn_box[(size_t)q * SP + j];
   __syncthreads();
   if (kFused && G.fused_box && staged) {
@@ -285,7 +294,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   }
 
   // ---- per-CTA constants of the validity chain and the collision tests -----------------------------
-  const int n_circ = P.cfg.n_circles;
+  const int n_circ = kSimple ? 0 : P.cfg.n_circles;
   double max_off = 0.0;                                  // footprint circles sit within max|offset| of the path point
   for (int i = 0; i < n_circ; ++i) max_off = fmax(max_off, fabs(P.cfg.circle_offsets[i]));
   const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
@@ -295,7 +304,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   const double wroad = fmax(P.cfg.max_road_width + 1e-9, fabs(fs[3]));
   const float pad = __double2float_ru(wroad + fmax(rc_s, rc_d));
   const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
-  const bool budget = dist_mode && max_viol > 0;
+  const bool budget = !kSimple && dist_mode && max_viol > 0;
   const double inf = INFINITY;
   // squared limits; a negative limit rejects every checked sample, as `x > negative` does in the reference
   // (warp-uniform: pushed through redux so that they live in uniform registers)
@@ -314,12 +323,12 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
   const double fast2 = 0.25;                                                   // v > 0.5 (fp.py:1019)
   const double stop_dist = qc[11];
   const double kTan01Sq = 0.010067046422495888;                                // tan(0.1)^2
-  const float4* boxes = G.box_smem ? sbox : B.dyn_box + (size_t)q * SP;
+  const float4* boxes = box_smem ? sbox : B.dyn_box + (size_t)q * SP;
 
   double my_cost = INFINITY;             // running arg-min over every pair this lane has seen
   int my_idx = 0x7fffffff;
   int my_stat = 0;                       // lane k < FOT_N_STATS: candidates of category k
-  bool dyn_ready = !(G.stage_dyn && SP > 0) || (kFused && G.fused_box);
+  bool dyn_ready = !(stage_dyn && SP > 0) || (kFused && G.fused_box);
 
   for (;;) {
     // ---- next pair of this CTA: longest horizons first, the brake ladder last ----------------------
@@ -346,8 +355,8 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
 
     // ---- phase A: the pair's private state, its polynomials --------------------------------------------
     flags[lane] = 0u;                                       // flags | hit words | clean words (32 words in a row)
-    if (G.vwords > 0)
-      for (int i = lane; i < n_d * G.vwords; i += 32) viol[i] = 0u;
+    if (vwords > 0)
+      for (int i = lane; i < n_d * vwords; i += 32) viol[i] = 0u;
     {
       // quartic solve of the pair (fp.py:619-647) and the lateral basis: d_i(t) = A(t) + d_i * B(t) -- the quintic's
       // right-hand side is linear in the target (fp.py:676-683).  Once per pair; the passes reload the sixteen numbers.
@@ -648,7 +657,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
         // of a clean candidate; a NaN box (fp.py:1211-1222) fails every comparison
         const float bx0 = __fsub_rd(ord2f(bxlo), pad), bx1 = __fadd_ru(ord2f(bxhi), pad);
         const float by0 = __fsub_rd(ord2f(bylo), pad), by1 = __fadd_ru(ord2f(byhi), pad);
-        const double ga = P.d_sorted ? dg[i_lo] : (brake ? 0.0 : P.d_min), gb = P.d_sorted ? dg[i_hi] : (brake ? 0.0 : P.d_max);
+        const double ga = d_sorted ? dg[i_lo] : (brake ? 0.0 : P.d_min), gb = d_sorted ? dg[i_hi] : (brake ? 0.0 : P.d_max);
         // One loop, three jobs, whichever is due: (1) list the next obstacles whose box meets the pair's, (2) window
         // test of every kept sample against the listed obstacles, lane = sample, survivors -> queue by ballot + prefix
         // count, (3) exact tests of 32 queued (sample, obstacle) entries, lane = entry, against every live clean candidate.
@@ -734,7 +743,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
               return (fabs(al) <= rc_d) & (ac >= w_lo) & (ac <= w_hi);             // NaN -> false
             };
             unsigned lo = 0u, hi = 0u;
-            if (G.stage_dyn) {
+            if (stage_dyn) {
               // staged block: four entries per iteration
               unsigned obs_a = dyn_a + 16u * (unsigned)kob;                        // this sample's time step
               asm volatile("" : "+r"(obs_a));
@@ -792,7 +801,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
             if (lv) {
               const unsigned ok_ = el + (unsigned)(B.T_obs > 0 ? min(en, B.T_obs - 1) : 0);
               if (!is_dyn) o = stat_q[el];
-              else if (G.stage_dyn) o = dynst[ok_];
+              else if (stage_dyn) o = dynst[ok_];
               else o = dyn_q[ok_];
             }
             const double r2 = !lv ? -1.0 : (is_dyn ? r2_dyn : P.cfg.collide_r2);   // idle lanes never hit
@@ -839,7 +848,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
                     }
                   }
                   if (use_budget) {
-                    if (hit) { const int sidx = (int)(el / (unsigned)B.T_obs) / B.P; atomicOr(&viol[i * G.vwords + (sidx >> 5)], 1u << (sidx & 31)); }
+                    if (hit) { const int sidx = (int)(el / (unsigned)B.T_obs) / B.P; atomicOr(&viol[i * vwords + (sidx >> 5)], 1u << (sidx & 31)); }
                     hit = false;
                   }
                   if (__ballot_sync(full, hit)) nh |= 1u << bit;
@@ -882,9 +891,9 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O, const PairGeom G) {
         else if (byte & F_ROAD) cat = FOT_CAT_ROAD;
         else {
           bool hit = (hitw[ci >> 5] >> (ci & 31)) & 1u;
-          if (G.vwords > 0) {
+          if (vwords > 0) {
             int nv = 0;
-            for (int w = 0; w < G.vwords; ++w) nv += __popc(viol[ci * G.vwords + w]);
+            for (int w = 0; w < vwords; ++w) nv += __popc(viol[ci * vwords + w]);
             hit = hit || nv > max_viol;                                            // fp.py:1113-1124
           }
           if (hit) {

@@ -112,3 +112,51 @@ def test_budgeted_distribution_and_footprint_both_kernels():
     _assert_same(a, b)
     _assert_same(b, c)
     _assert_same(b, d)
+
+
+def test_campaign_shape_instantiations_of_the_pair_kernel():
+    """fot_sweep_pairs compiles the planning-campaign shape (no static obstacles, one circle, no violation budget, no
+    per-candidate outputs) into instantiations of its own, resident and gated.  Winners, costs, histograms and the
+    returned series must be those of the general instantiation and of fot_sweep_items, bit for bit."""
+    import torch
+    import bench
+    from integrated_path_planning_b200 import _lib
+    from integrated_path_planning_b200.batch import DeviceBatch
+    from tests import runners
+    _, frenet, dyn = bench.make_queries(2000, 384)
+    pl = _planner(scenarios.S1_KNOBS, scenarios.STRAIGHT_60)
+    keys = ("best_idx", "best_cost", "stats", "winner_len", "winner")
+
+    def resident():
+        db = DeviceBatch(pl, frenet, 6.0, dyn, _lib.FOT_DYN_SINGLE)
+        db.launch()
+        torch.cuda.synchronize()
+        kind = int(pl.engine.lib.fot_last_sweep_kind(pl.engine._h))
+        return {k: db.out[k].cpu().numpy().copy() for k in keys}, kind
+
+    def host():
+        r = pl.plan_batch(frenet, 6.0, dynamic_obstacles=dyn[:, 0])
+        return {k: np.array(getattr(r, k)) for k in keys}
+
+    def same(a, b):
+        for k in ("best_idx", "stats", "winner_len"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a["best_cost"].view(np.uint64), b["best_cost"].view(np.uint64))
+        n_t = a["winner"].shape[-1]
+        live = (np.arange(n_t)[None, None, :] < a["winner_len"].reshape(-1, 1, 1)) & (a["best_idx"].reshape(-1, 1, 1) >= 0)
+        wa, wb = a["winner"].reshape(len(a["best_idx"]), -1, n_t), b["winner"].reshape(len(b["best_idx"]), -1, n_t)
+        assert np.array_equal(np.where(live, wa, 0.0).view(np.uint64), np.where(live, wb, 0.0).view(np.uint64))
+
+    pl.engine
+    with runners.fot_env(FOT_SWEEP="items"):
+        ref, kind = resident()
+        assert kind == 1
+        ref_host = host()
+    same(ref, ref_host)
+    for env in (dict(), dict(FOT_PAIR_SIMPLE=0)):
+        with runners.fot_env(**env):
+            got, kind = resident()
+            assert kind == 4
+            same(ref, got)
+            same(ref, host())
+    assert (ref["best_idx"] >= 0).sum() > 100
