@@ -186,7 +186,7 @@ def cpu_model():
 class ClockSampler(threading.Thread):
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index: int, period=0.01):
+    def __init__(self, index: int, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.power, self.reasons, self.max_mhz = [], [], set(), None
@@ -211,13 +211,20 @@ class ClockSampler(threading.Thread):
             return
         while not self._stop_evt.is_set():
             if self._armed.is_set():
+                # one query per try: a box whose NVML refuses the power reading must still report clocks and reasons
                 try:
                     self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                    self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                     for bit, name in self.REASONS.items():
                         if mask & bit:
                             self.reasons.add(name)
+                except Exception:
+                    pass
+                try:
+                    self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 except Exception:
                     pass
             time.sleep(self.period)
@@ -234,7 +241,8 @@ class ClockSampler(threading.Thread):
 
 
 def _ncu_traffic():
-    """DRAM bytes per query of the sweep kernel from the newest committed ncu --set full summary (profiles/)."""
+    """DRAM bytes per query of the sweep kernel and its FP64-pipe utilisation from the newest committed ncu --set full
+    summary (profiles/): (bytes per query, pipe fraction, file)."""
     import glob
     import re
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "sweep_pairs_ncu_full_summary.txt")), reverse=True):
@@ -242,11 +250,12 @@ def _ncu_traffic():
         rd = re.search(r"dram__bytes_read\.sum\s+([\d.]+)\s*(\w*)", txt)
         wr = re.search(r"dram__bytes_write\.sum\s+([\d.]+)\s*(\w*)", txt)
         nq = re.search(r"launch__grid_size\s+(\d+)", txt)     # one CTA per query in the captured launch
+        pipe = re.search(r"sm__inst_executed_pipe_fp64\.avg\.pct_of_peak_sustained_active\s+([\d.]+)", txt)
         if rd and wr and nq:
             scale = {"": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tot = float(rd.group(1)) * scale.get(rd.group(2), 1.0) + float(wr.group(1)) * scale.get(wr.group(2), 1.0)
-            return tot / int(nq.group(1)), os.path.relpath(path, ROOT)
-    return None, None
+            return tot / int(nq.group(1)), (float(pipe.group(1)) / 100.0 if pipe else None), os.path.relpath(path, ROOT)
+    return None, None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -597,11 +606,15 @@ def main():
     peak = C.c_double()
     _lib.check(eng.lib.fot_probe_fma_tflops(local_rank, 0, C.byref(peak)), "probe")
     achieved_tf = FLOP_PER_EVAL * evals_local / (sweep_ms * 1e-3) / 1e12
-    per_q, src = _ncu_traffic()
+    per_q, pipe_util, src = _ncu_traffic()
     roofline = {"bound": "fp64_pipe", "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak.value,
                 "traffic": per_q * Q if per_q else None,
                 "traffic_source": f"constant from {src} (ncu --set full, dram read + write bytes per query x queries); not measured in this run" if src else None,
+                "pipe_util_ncu": pipe_util,
+                "pipe_util_note": f"sm__inst_executed_pipe_fp64 of the same kernel and workload, constant from {src}: the FP64 pipe's own busy "
+                                  "fraction, next to the dense-credit `frac` (which counts every candidate x obstacle x step test, "
+                                  "most of which the kernel culls -- it can exceed 1)" if src else None,
                 "kernel": {4: "fot_sweep_pairs", 1: "fot_sweep_items", 3: "fot_sweep_warp", 2: "fot_sweep"}.get(
                     int(eng.lib.fot_last_sweep_kind(eng._h)), "?"), "kernel_ms": sweep_ms,
                 "stage_ms": {"prepass": float(stage[:, 0].mean()), "sweep": sweep_ms, "winner": float(stage[:, 2].mean())},
