@@ -1066,27 +1066,35 @@ __device__ __forceinline__ void aabb_prepass_body(const double2* __restrict__ dy
   const int lane = threadIdx.x & 31;
   if (warp >= n_traj) return;
   const double2* src = dyn + (size_t)warp * T_obs;
-  double xlo = INFINITY, xhi = -INFINITY, ylo = INFINITY, yhi = -INFINITY;
-  bool bad = false;
-  for (int k = lane; k < T_obs; k += 32) {
+  // both loads of a <= 64-step trajectory are in flight before the first comparison
+  const bool h0 = lane < T_obs, h1 = lane + 32 < T_obs;
+  const double2 o0 = h0 ? src[lane] : make_double2(INFINITY, INFINITY);
+  const double2 o1 = h1 ? src[lane + 32] : o0;
+  bool bad = (h0 && ((o0.x != o0.x) || (o0.y != o0.y))) || (h1 && ((o1.x != o1.x) || (o1.y != o1.y)));
+  double xlo = h0 ? fmin(o0.x, o1.x) : INFINITY, xhi = h0 ? fmax(o0.x, o1.x) : -INFINITY;
+  double ylo = h0 ? fmin(o0.y, o1.y) : INFINITY, yhi = h0 ? fmax(o0.y, o1.y) : -INFINITY;
+  for (int k = lane + 64; k < T_obs; k += 32) {
     const double2 o = src[k];
     bad |= (o.x != o.x) || (o.y != o.y);
     xlo = fmin(xlo, o.x); xhi = fmax(xhi, o.x); ylo = fmin(ylo, o.y); yhi = fmax(yhi, o.y);
   }
-  for (int off = 16; off > 0; off >>= 1) {
-    xlo = fmin(xlo, __shfl_xor_sync(0xffffffffu, xlo, off)); xhi = fmax(xhi, __shfl_xor_sync(0xffffffffu, xhi, off));
-    ylo = fmin(ylo, __shfl_xor_sync(0xffffffffu, ylo, off)); yhi = fmax(yhi, __shfl_xor_sync(0xffffffffu, yhi, off));
-  }
+  // outward rounding to fp32 is monotone, so it commutes with min / max: round first, then reduce the ordered-uint
+  // images with one redux each (four instructions instead of forty shuffles and as many fp64 comparisons)
+  const unsigned rxlo = __reduce_min_sync(0xffffffffu, f2ord(__double2float_rd(xlo)));
+  const unsigned rxhi = __reduce_max_sync(0xffffffffu, f2ord(__double2float_ru(xhi)));
+  const unsigned rylo = __reduce_min_sync(0xffffffffu, f2ord(__double2float_rd(ylo)));
+  const unsigned ryhi = __reduce_max_sync(0xffffffffu, f2ord(__double2float_ru(yhi)));
   bad = __any_sync(0xffffffffu, bad);
   if (lane == 0) {
     const float nanf_ = __int_as_float(0x7fc00000);
-    box[warp] = bad ? make_float4(nanf_, nanf_, nanf_, nanf_)
-                    : make_float4(__double2float_rd(xlo), __double2float_ru(xhi), __double2float_rd(ylo), __double2float_ru(yhi));
+    box[warp] = bad ? make_float4(nanf_, nanf_, nanf_, nanf_) : make_float4(ord2f(rxlo), ord2f(rxhi), ord2f(rylo), ord2f(ryhi));
   }
 }
 
 // One launch for both prepasses (they are independent and each too small to fill the GPU for long):
-// blocks [0, n_cost_blocks) build the cost tables, the rest box the predicted trajectories.
+// blocks [0, n_cost_blocks) build the cost tables, the rest box the predicted trajectories.  (Spreading the two kinds
+// evenly over the grid, so that every SM runs FP64-bound and memory-bound blocks together, measured slower: 0.142 against
+// 0.133 ms.)
 __global__ void __launch_bounds__(256)
 fot_prepass(const Plan P, const Batch B, double* __restrict__ cost_tab, unsigned n_cost_blocks,
             const double2* __restrict__ dyn, float4* __restrict__ box, long long n_traj, int T_obs) {
