@@ -166,9 +166,6 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
   const int n_d = P.cfg.n_d;
   const double dt = P.cfg.dt;
   const size_t part = (size_t)q * G.ctas_per_query + cta;
-  // A non-finite Frenet state makes every sample of every candidate non-finite: the reference drops
-  // them all silently (empty / non-finite guards fp.py:933-946).
-  const bool state_ok = fabs(fsg[0]) + fabs(fsg[1]) + fabs(fsg[2]) + fabs(fsg[3]) + fabs(fsg[4]) + fabs(fsg[5]) < INFINITY;
 
   const bool has_dyn = B.dyn_raw != nullptr;
   const int SP = has_dyn ? B.S * B.P : 0;
@@ -214,7 +211,10 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
   }
   const bool stage_dyn = kSimple || G.stage_dyn, box_smem = kSimple || G.box_smem, d_sorted = kSimple || P.d_sorted;
   const int vwords = kSimple ? 0 : G.vwords;
-  const bool staged = stage_dyn && state_ok;
+  // Nothing below depends on a global load before the barrier: the CTA's first round trip to memory (Frenet state,
+  // limits, speed grid, lateral grid, spline tables, trajectory boxes) is ONE, issued by all threads at once, and the bulk
+  // copy of the obstacle block is in flight beside it.
+  const bool staged = stage_dyn && SP > 0;
   if (tid == 0) {
     if (staged) {
       mbar_init(&s_bar, 1);
@@ -231,7 +231,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
   else if (tid < 10) qc[tid] = B.limits[4 * (size_t)q + tid - 6];
   else if (tid == 10) qc[10] = B.target[q];
   else if (tid == 11) qc[11] = B.stop_dist[q];
-  for (int i = tid; i < n_v; i += bd) qc[12 + i] = B.v_grid[(size_t)q * B.n_v_max + i];
+  for (int i = tid; i < B.n_v_max; i += bd) qc[12 + i] = B.v_grid[(size_t)q * B.n_v_max + i];
   {
     const int nx = P.cfg.nx;
     for (int i = tid; i < nx; i += bd) {
@@ -244,9 +244,12 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
       }
     }
   }
-  if (box_smem && !G.fused_box && state_ok)
+  if (box_smem && !G.fused_box)
     for (int j = tid; j < SP; j += bd) sbox[j] = B.dyn_box[(size_t)q * SP + j];
   __syncthreads();
+  // A non-finite Frenet state makes every sample of every candidate non-finite: the reference drops
+  // them all silently (empty / non-finite guards fp.py:933-946).
+  const bool state_ok = fabs(qc[0]) + fabs(qc[1]) + fabs(qc[2]) + fabs(qc[3]) + fabs(qc[4]) + fabs(qc[5]) < INFINITY;
   if (kFused && G.fused_box && staged) {
     // box every predicted trajectory of the staged obstacle block (what fot_prepass does for a resident tensor):
     // one warp per trajectory, fp32 rounded outward, NaN trajectory -> NaN box
@@ -290,6 +293,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
       }
     }
     if (tid == 0) { O.part_cost[part] = INFINITY; O.part_idx[part] = -1; }
+    if (staged) mbar_wait(&s_bar, 0u);                     // the bulk copy must have landed before the CTA can exit
     return;
   }
 
@@ -328,7 +332,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
   double my_cost = INFINITY;             // running arg-min over every pair this lane has seen
   int my_idx = 0x7fffffff;
   int my_stat = 0;                       // lane k < FOT_N_STATS: candidates of category k
-  bool dyn_ready = !(stage_dyn && SP > 0) || (kFused && G.fused_box);
+  bool dyn_ready = !staged || (kFused && G.fused_box);
 
   for (;;) {
     // ---- next pair of this CTA: longest horizons first, the brake ladder last ----------------------
