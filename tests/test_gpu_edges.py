@@ -267,3 +267,26 @@ def test_compact_winner_read_back_and_fetch():
                     assert _same("winner", got, want["winner"][q0:q0 + n], lens), (env, k)
                     series = res.series(int(np.argmax(want["best_idx"] >= 0))) if (want["best_idx"] >= 0).any() else None
                     assert series is None or len(series["x"]) <= k
+
+
+def test_pair_kernel_shape_limits_and_fallback():
+    """fot_sweep_pairs has compile-time shape limits (56 samples per profile, 96 lateral targets, 48 spline knots): at the
+    limits it runs, one step beyond them fot_sweep_items takes over -- and either way every candidate's category is the
+    oracle's."""
+    rng = np.random.default_rng(23)
+    k = scenarios.S1_KNOBS
+    dyn = scenarios.pedestrian_field(rng, 12, n_steps=60)
+    fs = np.array([[4.0, 5.0, 0.2, 0.3, 0.05, 0.0], [6.0, 2.0, -0.5, -0.8, 0.0, 0.02]])
+    cases = [
+        (dict(k, max_t=5.5, min_t=5.0), scenarios.STRAIGHT_60, 4),                      # 56 samples: the last shape the pair kernel takes
+        (dict(k, max_t=5.6, min_t=5.2), scenarios.STRAIGHT_60, 1),                      # 57 samples
+        (dict(k, d_road_w=2.7 / 47.5, min_t=4.8), scenarios.STRAIGHT_60, 4),            # 95 lateral targets
+        (dict(k, d_road_w=2.7 / 48.5, min_t=4.8), scenarios.STRAIGHT_60, 1),            # 97 lateral targets
+        (dict(k, min_t=4.8), scenarios.arc_waypoints(n=48), 4),                         # 48 spline knots
+        (dict(k, min_t=4.8), scenarios.arc_waypoints(n=49), 1),                         # 49
+    ]
+    for knobs, wp, kind in cases:
+        pl, orc = _planner(knobs, wp), _oracle(knobs, wp)
+        res = pl.plan_batch(fs, 6.0, dynamic_obstacles=np.stack([dyn] * 2), want_candidates=True)
+        assert int(pl.engine.lib.fot_last_sweep_kind(pl.engine._h)) == kind, (knobs, kind)
+        _check(res, [orc.plan_frenet(tuple(s), np.empty((0, 2)), dyn, 6.0) for s in fs])
