@@ -751,7 +751,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
     const long long n_prof = (long long)h->plan.cfg.n_T * (b->n_v_max + h->plan.cfg.n_d) + 2 * h->plan.cfg.n_B;
     const long long cblocks = ((long long)b->n_q * n_prof + 255) / 256;
     const long long n_traj = need_box ? (long long)b->n_q * SP : 0;
-    const long long ablocks = (n_traj * 32 + 255) / 256;
+    const long long ablocks = ((n_traj + kBoxPerWarp - 1) / kBoxPerWarp * 32 + 255) / 256;
     if (cblocks + ablocks > 0x7fffffffll) return fail(FOT_ERR_ARG, "batch too large for one launch");
     fot_prepass<<<(unsigned)(cblocks + ablocks), 256, 0, st>>>(h->plan, B, cost_tab, (unsigned)cblocks,
                                                                (const double2*)b->dyn, dyn_box, n_traj, b->T_obs);

@@ -1060,34 +1060,45 @@ __device__ __forceinline__ void cost_prepass_body(const Plan& P, const Batch& B,
 // (xmin, xmax, ymin, ymax) over all its steps rounded outward to fp32.  A NaN anywhere makes the
 // whole box NaN, which fails every overlap test: exactly the reference's prefilter, whose np.min /
 // np.max propagate the NaN and thereby remove that pedestrian from the test (fp.py:1211-1222).
+constexpr int kBoxPerWarp = 4;   // trajectories boxed per warp of fot_prepass: their loads are all in flight together
 __device__ __forceinline__ void aabb_prepass_body(const double2* __restrict__ dyn, float4* __restrict__ box, long long n_traj, int T_obs,
                                                   unsigned block) {
   const long long warp = ((long long)block * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= n_traj) return;
-  const double2* src = dyn + (size_t)warp * T_obs;
-  // both loads of a <= 64-step trajectory are in flight before the first comparison
+  const long long t0 = warp * kBoxPerWarp;
+  if (t0 >= n_traj) return;
+  // both loads of each of the warp's <= 64-step trajectories are issued before the first comparison
   const bool h0 = lane < T_obs, h1 = lane + 32 < T_obs;
-  const double2 o0 = h0 ? src[lane] : make_double2(INFINITY, INFINITY);
-  const double2 o1 = h1 ? src[lane + 32] : o0;
-  bool bad = (h0 && ((o0.x != o0.x) || (o0.y != o0.y))) || (h1 && ((o1.x != o1.x) || (o1.y != o1.y)));
-  double xlo = h0 ? fmin(o0.x, o1.x) : INFINITY, xhi = h0 ? fmax(o0.x, o1.x) : -INFINITY;
-  double ylo = h0 ? fmin(o0.y, o1.y) : INFINITY, yhi = h0 ? fmax(o0.y, o1.y) : -INFINITY;
-  for (int k = lane + 64; k < T_obs; k += 32) {
-    const double2 o = src[k];
-    bad |= (o.x != o.x) || (o.y != o.y);
-    xlo = fmin(xlo, o.x); xhi = fmax(xhi, o.x); ylo = fmin(ylo, o.y); yhi = fmax(yhi, o.y);
+  double2 o0[kBoxPerWarp], o1[kBoxPerWarp];
+#pragma unroll
+  for (int u = 0; u < kBoxPerWarp; ++u) {
+    const double2* src = dyn + (size_t)min(t0 + u, n_traj - 1) * T_obs;
+    o0[u] = h0 ? src[lane] : make_double2(INFINITY, INFINITY);
+    o1[u] = h1 ? src[lane + 32] : o0[u];
   }
-  // outward rounding to fp32 is monotone, so it commutes with min / max: round first, then reduce the ordered-uint
-  // images with one redux each (four instructions instead of forty shuffles and as many fp64 comparisons)
-  const unsigned rxlo = __reduce_min_sync(0xffffffffu, f2ord(__double2float_rd(xlo)));
-  const unsigned rxhi = __reduce_max_sync(0xffffffffu, f2ord(__double2float_ru(xhi)));
-  const unsigned rylo = __reduce_min_sync(0xffffffffu, f2ord(__double2float_rd(ylo)));
-  const unsigned ryhi = __reduce_max_sync(0xffffffffu, f2ord(__double2float_ru(yhi)));
-  bad = __any_sync(0xffffffffu, bad);
-  if (lane == 0) {
-    const float nanf_ = __int_as_float(0x7fc00000);
-    box[warp] = bad ? make_float4(nanf_, nanf_, nanf_, nanf_) : make_float4(ord2f(rxlo), ord2f(rxhi), ord2f(rylo), ord2f(ryhi));
+#pragma unroll
+  for (int u = 0; u < kBoxPerWarp; ++u) {
+    if (t0 + u >= n_traj) break;
+    const double2* src = dyn + (size_t)(t0 + u) * T_obs;
+    bool bad = (h0 && ((o0[u].x != o0[u].x) || (o0[u].y != o0[u].y))) || (h1 && ((o1[u].x != o1[u].x) || (o1[u].y != o1[u].y)));
+    double xlo = h0 ? fmin(o0[u].x, o1[u].x) : INFINITY, xhi = h0 ? fmax(o0[u].x, o1[u].x) : -INFINITY;
+    double ylo = h0 ? fmin(o0[u].y, o1[u].y) : INFINITY, yhi = h0 ? fmax(o0[u].y, o1[u].y) : -INFINITY;
+    for (int k = lane + 64; k < T_obs; k += 32) {
+      const double2 o = src[k];
+      bad |= (o.x != o.x) || (o.y != o.y);
+      xlo = fmin(xlo, o.x); xhi = fmax(xhi, o.x); ylo = fmin(ylo, o.y); yhi = fmax(yhi, o.y);
+    }
+    // outward rounding to fp32 is monotone, so it commutes with min / max: round first, then reduce the ordered-uint
+    // images with one redux each (four instructions instead of forty shuffles and as many fp64 comparisons)
+    const unsigned rxlo = __reduce_min_sync(0xffffffffu, f2ord(__double2float_rd(xlo)));
+    const unsigned rxhi = __reduce_max_sync(0xffffffffu, f2ord(__double2float_ru(xhi)));
+    const unsigned rylo = __reduce_min_sync(0xffffffffu, f2ord(__double2float_rd(ylo)));
+    const unsigned ryhi = __reduce_max_sync(0xffffffffu, f2ord(__double2float_ru(yhi)));
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      const float nanf_ = __int_as_float(0x7fc00000);
+      box[t0 + u] = bad ? make_float4(nanf_, nanf_, nanf_, nanf_) : make_float4(ord2f(rxlo), ord2f(rxhi), ord2f(rylo), ord2f(ryhi));
+    }
   }
 }
 
