@@ -240,6 +240,29 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
 
 
+def _pinned_write_combined(arr):
+    """A copy of `arr` in write-combined page-locked host memory (cudaHostAlloc, flag 0x04): uploads from it do not snoop
+    the CPU caches.  Never freed (bench process)."""
+    import ctypes as C
+    rt = None
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            rt = C.CDLL(name)
+            break
+        except OSError:
+            pass
+    if rt is None:
+        raise RuntimeError("libcudart not found")
+    ptr = C.c_void_p()
+    rc = rt.cudaHostAlloc(C.byref(ptr), C.c_size_t(arr.nbytes), C.c_uint(0x04))
+    if rc != 0:
+        raise RuntimeError(f"cudaHostAlloc failed: {rc}")
+    buf = (C.c_char * arr.nbytes).from_address(ptr.value)
+    out = np.frombuffer(buf, dtype=arr.dtype).reshape(arr.shape)
+    out[...] = arr
+    return out
+
+
 def _ncu_traffic():
     """DRAM bytes per query of the sweep kernel and its FP64-pipe utilisation from the newest committed ncu --set full
     summary (profiles/): (bytes per query, pipe fraction, file)."""
@@ -275,6 +298,7 @@ def main():
                          "falls back to nccl when CUDA IPC is unavailable), or one all_gather_into_tensor of the packed block")
     ap.add_argument("--gather-priority", type=int, default=0, help="tuning: CUDA priority of the gather stream (0 default, -1 high)")
     ap.add_argument("--brief", action="store_true", help="resident + e2e legs only (scaling experiments)")
+    ap.add_argument("--wc-input", action="store_true", help="experiment: e2e input in write-combined pinned memory (cudaHostAllocWriteCombined)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -536,8 +560,11 @@ def main():
         del leg_o
 
     # e2e leg: host-pointer C-ABI call, pinned inputs, H2D + kernels + D2H inside the timed region
-    dyn_pinned = torch.from_numpy(dyn).pin_memory()
-    dyn_host = dyn_pinned.numpy()
+    if args.wc_input:
+        dyn_host = _pinned_write_combined(dyn)                # experiment: write-combined page-locked input (no snooping on the upload)
+    else:
+        dyn_pinned = torch.from_numpy(dyn).pin_memory()
+        dyn_host = dyn_pinned.numpy()
     for _ in range(args.warmup):
         res = planner.plan_batch(frenet, TARGET_SPEED, dynamic_obstacles=dyn_host[:, 0])
     e2e_steps = args.steps
