@@ -22,6 +22,13 @@
 // atomics, the clean masks and decisive-hit words are plain words, the survivor queue is filled by ballot +
 // prefix count, and the exact tests run a uniform loop over the live candidates with one ballot each.
 //
+// What that bought and what it cost is in DESIGN.md section 4d: the barrier stall went from 3.1 to 0.4 cycles per issued
+// instruction, and the first version was slower for it -- twenty warps that each walk their own way through 30-40 KB of
+// mostly straight-line code do not share instruction fetches the way ten warps in lock-step do.  From then on the kernel's
+// time followed the size of its hot code (profiles/r2/sweep_pairs_icache_history.txt), which is why the slice layout is a
+// compile-time constant, why there is one code site per job in the collision loop, and why the batch shape of a planning
+// campaign has an instantiation of its own (kSimple) with every other mode compiled out.
+//
 // Reference citations as in fot_sweep_items.cuh (fp.py = src/planning/frenet_planner.py, cs.py = cubic_spline.py,
 // cc.py = src/core/coordinate_converter.py).
 #pragma once
@@ -39,12 +46,12 @@ namespace fot {
 #endif
 constexpr int kPairThreads = FOT_PAIR_THREADS;   // CTA size of fot_sweep_pairs
 constexpr int kPairWarps = kPairThreads / 32;
-constexpr int kPairList = 64;                    // obstacle list entries per cull chunk (per warp)
+constexpr int kPairList = 64;                    // obstacle list entries per chunk (per warp): dynamic from the front, static from the back
 constexpr int kPairQueue = 64;                   // survivor queue (per warp, a ring): < 32 waiting + <= 32 new
 #ifndef FOT_PAIR_NT
 #define FOT_PAIR_NT 56
 #endif
-constexpr int kPairNT = FOT_PAIR_NT;                      // samples per profile this kernel covers (longer time grids: fot_sweep_items)
+constexpr int kPairNT = FOT_PAIR_NT;             // samples per profile this kernel covers (longer time grids: fot_sweep_items)
 constexpr int kPairND = 96;                      // lateral targets this kernel covers (wider grids: fot_sweep_items)
 constexpr int kPairNV = 52;                      // terminal speeds per query
 constexpr int kPairNX = 48;                      // spline knots (longer reference lines: fot_sweep_items)
