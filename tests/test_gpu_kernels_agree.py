@@ -160,3 +160,62 @@ def test_campaign_shape_instantiations_of_the_pair_kernel():
             same(ref, got)
             same(ref, host())
     assert (ref["best_idx"] >= 0).sum() > 100
+
+
+def test_random_shapes_pair_kernel_against_item_kernel():
+    """Shape fuzz for the pair kernel's compile-time layout, clamped quads and tail masks: time grids from 8 to 56
+    samples (one pass, exactly 32 / 33 samples, two passes), 1 to 95 lateral targets (quads with 1-3 live candidates), one
+    to many terminal speeds, brake ladder on and off, obstacle horizons shorter and longer than the time grid, static
+    obstacles across chunk borders, single-sample and distribution mode with and without a violation budget, with and
+    without a footprint -- every candidate's category and cost, winners and histograms bit for bit against
+    fot_sweep_items, and the winners once more through the instantiation without per-candidate outputs."""
+    from integrated_path_planning_b200 import BatchFrenetPlanner, CubicSpline2D
+    from tests import runners
+    rng = np.random.default_rng(77)
+    paths = (scenarios.STRAIGHT_60, scenarios.s_curve_waypoints(), scenarios.arc_waypoints())
+    seen_kinds = set()
+    for case in range(28):
+        dt = float(rng.choice([0.1, 0.2, 0.25]))
+        n_max = int(rng.choice([8, 17, 31, 32, 33, 40, 47, 56]))
+        max_t = round((n_max - 1) * dt, 6)
+        min_t = round(max(dt * 4, max_t - dt * int(rng.integers(0, 6))), 6)
+        n_side = int(rng.choice([0, 1, 2, 5, 9, 16, 31, 47]))
+        road = 2.7
+        knobs = dict(scenarios.S1_KNOBS, dt=dt, min_t=min_t, max_t=max_t, max_road_width=road,
+                     d_road_w=(road / (n_side + 0.5) if n_side > 0 else 2 * road + 1.0),
+                     d_t_s=float(rng.choice([0.5, 5.0 / 3.6, 3.0, 20.0])))
+        if case % 4 == 3:
+            knobs["chance_epsilon"] = float(rng.choice([0.0, 0.2, 0.34]))
+        footprint = runners.make_footprint((4.5, 2.0, 3)) if case % 5 == 4 else None
+        pl = BatchFrenetPlanner(CubicSpline2D(*paths[case % 3]), footprint=footprint, **knobs)
+        n = 12
+        frenet = np.stack([rng.uniform(2, 20, n), rng.uniform(0, 8, n), rng.uniform(-1, 1, n), rng.uniform(-1.5, 1.5, n),
+                           rng.normal(0, 0.3, n), rng.normal(0, 0.05, n)], axis=1)
+        frenet[::5, 1] = rng.uniform(0.0, 0.1, len(frenet[::5]))                   # too slow for the brake ladder
+        target = rng.choice([0.0, 2.0, 6.0, 8.5], n)
+        t_obs = int(rng.choice([1, 5, n_max - 3, n_max, n_max + 9]))
+        t_obs = max(1, t_obs)
+        n_ped = int(rng.choice([1, 7, 31, 33, 70]))
+        kw = {}
+        if case % 4 == 3:
+            S = int(rng.choice([3, 6]))
+            base = np.stack([scenarios.pedestrian_field(rng, min(n_ped, 12), n_steps=t_obs, dt=dt, x_range=(0.0, 40.0), y_range=(-6.0, 6.0)) for _ in range(n)])
+            kw["distribution"] = np.stack([scenarios.sample_distribution(rng, base[i], S, sigma=0.08) for i in range(n)])
+        else:
+            kw["dynamic_obstacles"] = np.stack([scenarios.pedestrian_field(rng, n_ped, n_steps=t_obs, dt=dt, x_range=(0.0, 40.0), y_range=(-6.0, 6.0))
+                                                for _ in range(n)])
+        if case % 3 == 1:
+            m = int(rng.choice([1, 30, 40, 75]))
+            kw["static_obstacles"] = np.stack([rng.uniform(5.0, 45.0, m), rng.uniform(-5.0, 5.0, m)], axis=1)
+        msd = np.where(target == 0.0, 6.0, np.nan)
+        run = lambda cands: pl.plan_batch(frenet, target, max_stop_distance=msd, want_candidates=cands, **kw)
+        pl.engine
+        with runners.fot_env(FOT_SWEEP="items"):
+            ref = run(True)
+        got = run(True)
+        seen_kinds.add(int(pl.engine.lib.fot_last_sweep_kind(pl.engine._h)))
+        _assert_same(ref, got)
+        lean = run(False)
+        assert np.array_equal(ref.best_idx, lean.best_idx) and np.array_equal(ref.stats, lean.stats), case
+        assert np.array_equal(ref.best_cost.view(np.uint64), lean.best_cost.view(np.uint64)), case
+    assert 4 in seen_kinds
