@@ -338,7 +338,6 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
 
   double my_cost = INFINITY;             // running arg-min over every pair this lane has seen
   int my_idx = 0x7fffffff;
-  int my_stat = 0;                       // lane k < FOT_N_STATS: candidates of category k
   bool dyn_ready = !staged || (kFused && G.fused_box);
 
   for (;;) {
@@ -929,11 +928,10 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
         if (O.cand_cost) O.cand_cost[(size_t)q * O.cand_stride + cand_idx] = cost;
         if (cat == FOT_CAT_OK && cost < INFINITY) argmin_merge(my_cost, my_idx, cost, cand_idx);
       }
-      // histogram: lane k counts category k
-#pragma unroll 1
-      for (int kc = 0; kc < FOT_N_STATS; ++kc) {
-        const int cnt = __popc(__ballot_sync(full, cat == kc));
-        if (lane == kc) my_stat += cnt;
+      // histogram: the lanes of one category elect a leader, which adds their number to the CTA's counter
+      {
+        const unsigned peers = __match_any_sync(full, cat);
+        if (cat >= 0 && cat < FOT_N_STATS && lane == __ffs(peers) - 1) atomicAdd(&s_stats[cat], __popc(peers));
       }
     }
     __syncwarp();                                          // the slice is free for the next pair
@@ -946,7 +944,6 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
     argmin_merge(my_cost, my_idx, oc, oi);
   }
   if (lane == 0) { s_cost[wid] = my_cost; s_idx[wid] = my_idx; }
-  if (lane < FOT_N_STATS && my_stat != 0) atomicAdd(&s_stats[lane], my_stat);
   __syncthreads();
   if (tid == 0) {
     for (int w = 1; w < (bd >> 5); ++w) argmin_merge(my_cost, my_idx, s_cost[w], s_idx[w]);
