@@ -530,7 +530,7 @@ static bool pair_geometry(const fot_handle* h, const fot_batch_t* b, PairGeom* g
   const int NT = h->plan.n_t_max, nd = h->plan.cfg.n_d, nB = h->plan.cfg.n_B, nx = h->plan.cfg.nx;
   const bool has_dyn = b->dyn_mode != FOT_DYN_NONE;
   const long long SPl = has_dyn ? (long long)b->S * b->P : 0;
-  if (NT > kPairNT || nd > kPairND || b->n_v_max > kPairNV || nx > kPairNX || SPl > (1 << 20) || b->n_static > (1 << 20)) return false;
+  if (NT > kPairNT || nd > kPairND || b->n_v_max > kPairNV || nx > kPairNX || h->plan.cfg.n_T > kPairNH || SPl > (1 << 20) || b->n_static > (1 << 20)) return false;
   if (SPl * std::max(1, b->T_obs) >= (1ll << 27)) return false;                            // list entries: element offsets
   const int SP = (int)SPl;
   PairGeom G{};

@@ -55,6 +55,7 @@ constexpr int kPairNT = FOT_PAIR_NT;             // samples per profile this ker
 constexpr int kPairND = 96;                      // lateral targets this kernel covers (wider grids: fot_sweep_items)
 constexpr int kPairNV = 52;                      // terminal speeds per query
 constexpr int kPairNX = 48;                      // spline knots (longer reference lines: fot_sweep_items)
+constexpr int kPairNH = 64;                      // horizons
 
 // One warp's private slice of shared memory, and behind the slices the CTA-wide tables whose size has a small bound.
 // The layout is a compile-time constant on purpose: every access is `base register + immediate`.  (With run-time
@@ -78,6 +79,7 @@ struct __align__(16) PairShared {
   double qc[12 + kPairNV];             // fs[6] | limits[4] | target | stop_dist | v_grid[n_v]
   double dgrid[kPairND + 2];           // lateral targets, then the brake ladder's single target 0.0
   double spl[9][kPairNX];              // spline tables: knots | x: a b c d | y: a b c d
+  int n_steps[kPairNH];                // samples - 1 of every horizon
 };
 
 static_assert(offsetof(PairSlice, hitw) == offsetof(PairSlice, flags) + kPairND && offsetof(PairSlice, cleanw) == offsetof(PairSlice, hitw) + 16 &&
@@ -233,6 +235,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
     s_next = 0;
   }
   if (tid < FOT_N_STATS) s_stats[tid] = 0;
+  for (int i = tid; i < P.cfg.n_T; i += bd) S.n_steps[i] = P.n_steps[i];
   for (int i = tid; i <= n_d; i += bd) dgrid[i] = i < n_d ? P.d_grid[i] : 0.0;   // [n_d]: the brake ladder's single target
   if (tid < 6) qc[tid] = fsg[tid];
   else if (tid < 10) qc[tid] = B.limits[4 * (size_t)q + tid - 6];
@@ -353,7 +356,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
       const int u = n_grid - 1 - ord;
       jT = __float2int_rz(((float)u + 0.5f) * rcp_nv);      // u / n_v (exact: u < 2^20)
       kk = u - jT * n_v;
-      N = P.n_steps[jT] + 1;
+      N = S.n_steps[jT] + 1;
       n_dl = n_d;
     } else {
       kk = ord - n_grid;
