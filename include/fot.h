@@ -30,7 +30,7 @@ extern "C" {
 #define FOT_ABI_VERSION 6   /* 2: + prediction post-processing and safety metrics; 3: + fot_plan_batch_device_to_host;
                                4: + fot_result_t.winner_samples, fot_fetch_winners, fot_reload_options;
                                5: + fot_set_result_mirror, fot_peer_* (gather of a sharded sweep over peer memory);
-                               6: + fot_last_sweep_kind (fot_sweep_pairs is the default sweep kernel) */
+                               6: + fot_last_sweep_kind, fot_last_pair_features (fot_sweep_pairs is the default sweep kernel) */
 #define FOT_MAX_CIRCLES 8
 #define FOT_N_STATS 8    /* ok, max_speed, max_accel, max_curvature, max_lat_accel, road_bound, collision, stop_distance */
 #define FOT_N_SERIES 15  /* t s s_d s_dd s_ddd d d_d d_dd d_ddd x y yaw c v a  (data_structures.py:149-181) */
@@ -212,6 +212,11 @@ float fot_last_kernel_ms(const fot_handle_t* h);
  * default), 1 fot_sweep_items (sample-major with block barriers; shapes beyond the limits of fot_sweep_pairs), 3
  * fot_sweep_warp (FOT_SWEEP=warp), 2 fot_sweep (candidate-major; very long time grids), 0 none yet. */
 int fot_last_sweep_kind(const fot_handle_t* h);
+
+/* fot_sweep_pairs is compiled per set of optional modes (1 static obstacles, 2 footprint circles, 4 violation budget,
+ * 8 per-candidate outputs, 16 unstaged obstacle block / unsorted lateral grid) and the smallest
+ * instantiated superset of what a batch needs runs: the set of the last launch, or -1 if another kernel ran. */
+int fot_last_pair_features(const fot_handle_t* h);
 
 /* Device time of the three stages of the `back`-th most recent launch on this handle (0 = the
  * last one; the handle keeps the last 256), in ms, from CUDA events on the launching stream:

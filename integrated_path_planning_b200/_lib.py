@@ -88,6 +88,7 @@ SYMBOLS = (
     ("fot_reload_options", C.c_int, (C.c_void_p,)),
     ("fot_last_kernel_ms", C.c_float, (C.c_void_p,)),
     ("fot_last_sweep_kind", C.c_int, (C.c_void_p,)),
+    ("fot_last_pair_features", C.c_int, (C.c_void_p,)),
     ("fot_launch_stage_ms", C.c_int, (C.c_void_p, C.c_int, C.POINTER(C.c_float * 3))),
     ("fot_probe_fma_tflops", C.c_int, (C.c_int, C.c_int, c_double_p)),
     ("fot_predict_cv_device", C.c_int, (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

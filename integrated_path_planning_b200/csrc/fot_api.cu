@@ -76,7 +76,8 @@ struct Options {
                                //                    4 "pairs" (fot_sweep_pairs: one longitudinal profile per warp, no block
                                //                    barriers; fail if unsupported)
   int pair_cpq = 0;            // FOT_PAIR_CPQ       CTAs per query of fot_sweep_pairs (0: rule of pair_geometry)
-  int pair_simple = 1;         // FOT_PAIR_SIMPLE    0: never the campaign-shape instantiation of fot_sweep_pairs (tests)
+  int pair_simple = 1;         // FOT_PAIR_SIMPLE    0: always the instantiation of fot_sweep_pairs with every mode compiled in (tests)
+  int pair_feat = 0;           // FOT_PAIR_FEAT      mode bits (PAIR_*) added to what the batch needs (tests, tuning)
   int host_chunks = 0;         // FOT_HOST_CHUNKS    equal chunks of the host-pointer call (0: rule)
   std::string chunk_waves;     // FOT_CHUNK_WAVES    chunk sizes in sweep waves, "1,2,3" (+ the rest)
   int host_streams = 2;        // FOT_HOST_STREAMS   1: chunks on one compute stream
@@ -98,6 +99,7 @@ struct Options {
     if (const char* e = getenv("FOT_SWEEP")) sweep = !strcmp(e, "generic") ? 2 : !strcmp(e, "items") ? 1 : !strcmp(e, "warp") ? 3 : !strcmp(e, "pairs") ? 4 : 0;
     pair_cpq = geti("FOT_PAIR_CPQ", 0);
     pair_simple = geti("FOT_PAIR_SIMPLE", 1) != 0;
+    pair_feat = geti("FOT_PAIR_FEAT", 0) & 31;
     host_chunks = geti("FOT_HOST_CHUNKS", 0);
     if (const char* e = getenv("FOT_CHUNK_WAVES")) chunk_waves = e;
     host_streams = geti("FOT_HOST_STREAMS", 2);
@@ -115,6 +117,21 @@ std::mutex g_live_mu;
 std::set<fot_handle*> g_live;     // handles alive in this process (fot_reload_options(NULL) walks them)
 
 }  // namespace
+
+// The instantiations of fot_sweep_pairs that exist (mode sets, PAIR_*), smallest first: the campaign shape, + static
+// obstacles, + per-candidate outputs, + both, everything.
+static const int kPairInstances[] = {0, PAIR_STATIC, PAIR_OUTPUTS, PAIR_STATIC | PAIR_OUTPUTS, PAIR_ALL};
+static const int kPairInstanceCount = 5;
+typedef void (*PairKernel)(const Plan, const Batch, const Out, const PairGeom);
+static PairKernel pair_kernel(bool fused, int feat) {
+  switch (feat) {
+    case 0: return fused ? fot_sweep_pairs<true, 0> : fot_sweep_pairs<false, 0>;
+    case PAIR_STATIC: return fused ? fot_sweep_pairs<true, PAIR_STATIC> : fot_sweep_pairs<false, PAIR_STATIC>;
+    case PAIR_OUTPUTS: return fused ? fot_sweep_pairs<true, PAIR_OUTPUTS> : fot_sweep_pairs<false, PAIR_OUTPUTS>;
+    case PAIR_STATIC | PAIR_OUTPUTS: return fused ? fot_sweep_pairs<true, PAIR_STATIC | PAIR_OUTPUTS> : fot_sweep_pairs<false, PAIR_STATIC | PAIR_OUTPUTS>;
+    default: return fused ? fot_sweep_pairs<true, PAIR_ALL> : fot_sweep_pairs<false, PAIR_ALL>;
+  }
+}
 
 struct fot_handle {
   Options opt;
@@ -137,6 +154,7 @@ struct fot_handle {
   int smem_optin = 0;
   int sms = 148;                     // SM count of the device (block-per-CTA grouping, host chunk sizes)
   Buf obs_tm, obs_max2, stat_tm, stat_max2, part_cost, part_idx, dyn_box, cost_tab;   // device scratch
+  int last_pair_feat = -1;           // mode set (PAIR_*) of the fot_sweep_pairs instantiation of the last launch
   int last_sweep_kind = 0;           // 4: fot_sweep_pairs, 1: fot_sweep_items, 3: fot_sweep_warp, 2: fot_sweep (generic)
   fot_result_t mirror{};             // fot_set_result_mirror: second destination of the winner block (all null: none)
   unsigned* mirror_flag = nullptr;   // word published behind each mirrored launch (fot_set_result_mirror), or null
@@ -240,10 +258,9 @@ extern "C" int fot_create(const fot_config_t* cfg, const fot_tables_t* tb, int d
   CK(cudaFuncSetAttribute(fot_sweep_items<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   CK(cudaFuncSetAttribute(fot_sweep_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-  CK(cudaFuncSetAttribute(fot_sweep_pairs<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-  CK(cudaFuncSetAttribute(fot_sweep_pairs<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-  CK(cudaFuncSetAttribute(fot_sweep_pairs<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
-  CK(cudaFuncSetAttribute(fot_sweep_pairs<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
+  for (int i = 0; i < kPairInstanceCount; ++i)
+    for (int f = 0; f < 2; ++f)
+      CK(cudaFuncSetAttribute(pair_kernel(f != 0, kPairInstances[i]), cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_optin));
   { std::lock_guard<std::mutex> lk(g_live_mu); g_live.insert(h); }
   guard.h = nullptr;
   *out = h;
@@ -757,14 +774,23 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
                                                                (const double2*)b->dyn, dyn_box, n_traj, b->T_obs);
   }
   CK(cudaEventRecord(ring[1], st));
-  // the campaign shape (no static obstacles, one circle, no violation budget, staged block, no per-candidate outputs)
-  // runs the instantiation with everything else compiled out
-  const bool simple = use_pairs && h->opt.pair_simple && b->n_static == 0 && h->plan.cfg.n_circles == 0 && pg.vwords == 0 &&
-                      pg.stage_dyn && pg.box_smem && h->plan.d_sorted && !r->cand_cat && !r->cand_cost;
-  if (use_pairs && pg.fused_box && simple) fot_sweep_pairs<true, true><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
-  else if (use_pairs && pg.fused_box) fot_sweep_pairs<true, false><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
-  else if (use_pairs && simple) fot_sweep_pairs<false, true><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
-  else if (use_pairs) fot_sweep_pairs<false, false><<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
+  if (use_pairs) {
+    // the modes this batch needs; the smallest instantiated superset runs (everything else is compiled out of it)
+    int need = 0;
+    if (b->n_static > 0) need |= PAIR_STATIC;
+    if (h->plan.cfg.n_circles > 0) need |= PAIR_FOOTPRINT;
+    if (pg.vwords > 0) need |= PAIR_BUDGET;
+    if (r->cand_cat || r->cand_cost) need |= PAIR_OUTPUTS;
+    if (has_dyn && !(pg.stage_dyn && pg.box_smem)) need |= PAIR_LOOSE;
+    if (!h->plan.d_sorted) need |= PAIR_LOOSE;
+    need |= h->opt.pair_feat;
+    if (!h->opt.pair_simple) need = PAIR_ALL;
+    int feat = PAIR_ALL;
+    for (int i = 0; i < kPairInstanceCount; ++i)
+      if ((kPairInstances[i] & need) == need) { feat = kPairInstances[i]; break; }
+    pair_kernel(pg.fused_box != 0, feat)<<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
+    h->last_pair_feat = feat;
+  }
   else if (use_warp && wg.fused_box) fot_sweep_warp<true><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
   else if (use_warp) fot_sweep_warp<false><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
   else if (use_items && ig.fused_box) fot_sweep_items<true><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
@@ -1304,6 +1330,7 @@ extern "C" float fot_last_kernel_ms(const fot_handle_t* h) {
 }
 
 extern "C" int fot_last_sweep_kind(const fot_handle_t* h) { return h ? h->last_sweep_kind : 0; }
+extern "C" int fot_last_pair_features(const fot_handle_t* h) { return h && h->last_sweep_kind == 4 ? h->last_pair_feat : -1; }
 
 extern "C" int fot_launch_stage_ms(const fot_handle_t* h, int back, float ms[3]) {
   if (!h || !ms || back < 0 || back >= fot_handle::kRing || back >= h->n_launch)

@@ -27,7 +27,7 @@
 // mostly straight-line code do not share instruction fetches the way ten warps in lock-step do.  From then on the kernel's
 // time followed the size of its hot code (profiles/r2/sweep_pairs_icache_history.txt), which is why the slice layout is a
 // compile-time constant, why there is one code site per job in the collision loop, and why the batch shape of a planning
-// campaign has an instantiation of its own (kSimple) with every other mode compiled out.
+// campaign has an instantiation of its own (kFeat = 0) with every other mode compiled out.
 //
 // Reference citations as in fot_sweep_items.cuh (fp.py = src/planning/frenet_planner.py, cs.py = cubic_spline.py,
 // cc.py = src/core/coordinate_converter.py).
@@ -139,15 +139,17 @@ __device__ __forceinline__ RefFast spline_ref_smem(const double (*T)[kPairNX], i
 }
 
 // kFused: the variant of the gated host-pointer call (waits for its query's upload slice, boxes the trajectories itself).
-// kSimple: the batch has no static obstacles, one collision circle, no violation budget, a sorted lateral grid, a staged
-// obstacle block and no per-candidate outputs -- the shape of a planning campaign.  The kernel is bound by instruction
-// fetch, so the code of the other modes is compiled out of this instantiation instead of being
-// branched over.
-template <bool kFused, bool kSimple>
+// kFeat: which optional modes this instantiation carries (PAIR_*).  The kernel is bound by instruction fetch (DESIGN.md
+// section 4d), so the code of a mode the batch does not use is compiled out of the instantiation it runs instead of
+// being branched over: 0 is the shape of a planning campaign (no static obstacles, one collision circle, no violation
+// budget, sorted lateral grid, staged obstacle block, no per-candidate outputs); the host picks the smallest
+// instantiated superset of what the batch needs (fot_api.cu, kPairInstances).
+enum : int { PAIR_STATIC = 1, PAIR_FOOTPRINT = 2, PAIR_BUDGET = 4, PAIR_OUTPUTS = 8, PAIR_LOOSE = 16, PAIR_ALL = 31 };
+template <bool kFused, int kFeat>
 __global__ void __launch_bounds__(kPairThreads, FOT_PAIR_MIN_CTAS)
 fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
   Out O = O_;
-  if (kSimple) { O.cand_cat = nullptr; O.cand_cost = nullptr; }
+  if (!(kFeat & PAIR_OUTPUTS)) { O.cand_cat = nullptr; O.cand_cost = nullptr; }
   extern __shared__ __align__(16) unsigned char smb[];
   PairShared& S = *reinterpret_cast<PairShared*>(smb);
   double* qc = S.qc;
@@ -178,7 +180,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
 
   const bool has_dyn = B.dyn_raw != nullptr;
   const int SP = has_dyn ? B.S * B.P : 0;
-  const int M = kSimple ? 0 : (B.static_raw ? B.n_static : 0);
+  const int M = (kFeat & PAIR_STATIC) ? (B.static_raw ? B.n_static : 0) : 0;
   const double2* dyn_q = has_dyn ? reinterpret_cast<const double2*>(B.dyn_raw) + (size_t)q * SP * B.T_obs : nullptr;
   const double2* stat_q = M > 0 ? reinterpret_cast<const double2*>(B.static_raw) + (size_t)(B.static_per_query ? q : 0) * M : nullptr;
 
@@ -218,8 +220,9 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
     __syncthreads();
     if (s_abort) return;
   }
-  const bool stage_dyn = kSimple || G.stage_dyn, box_smem = kSimple || G.box_smem, d_sorted = kSimple || P.d_sorted;
-  const int vwords = kSimple ? 0 : G.vwords;
+  // PAIR_LOOSE: obstacle block read from global memory, boxes from global memory, or an unsorted lateral grid
+  const bool stage_dyn = !(kFeat & PAIR_LOOSE) || G.stage_dyn, box_smem = !(kFeat & PAIR_LOOSE) || G.box_smem, d_sorted = !(kFeat & PAIR_LOOSE) || P.d_sorted;
+  const int vwords = (kFeat & PAIR_BUDGET) ? G.vwords : 0;
   // Nothing below depends on a global load before the barrier: the CTA's first round trip to memory (Frenet state,
   // limits, speed grid, lateral grid, spline tables, trajectory boxes) is ONE, issued by all threads at once, and the bulk
   // copy of the obstacle block is in flight beside it.
@@ -308,7 +311,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
   }
 
   // ---- per-CTA constants of the validity chain and the collision tests -----------------------------
-  const int n_circ = kSimple ? 0 : P.cfg.n_circles;
+  const int n_circ = (kFeat & PAIR_FOOTPRINT) ? P.cfg.n_circles : 0;
   double max_off = 0.0;                                  // footprint circles sit within max|offset| of the path point
   for (int i = 0; i < n_circ; ++i) max_off = fmax(max_off, fabs(P.cfg.circle_offsets[i]));
   const bool dist_mode = (B.dyn_mode == FOT_DYN_DISTRIBUTION);
@@ -318,7 +321,7 @@ fot_sweep_pairs(const Plan P, const Batch B, const Out O_, const PairGeom G) {
   const double wroad = fmax(P.cfg.max_road_width + 1e-9, fabs(fs[3]));
   const float pad = __double2float_ru(wroad + fmax(rc_s, rc_d));
   const int max_viol = dist_mode ? (int)floor(P.cfg.chance_epsilon * (double)B.S) : 0;   // fp.py:1114
-  const bool budget = !kSimple && dist_mode && max_viol > 0;
+  const bool budget = (kFeat & PAIR_BUDGET) && dist_mode && max_viol > 0;
   const double inf = INFINITY;
   // squared limits; a negative limit rejects every checked sample, as `x > negative` does in the reference
   // (warp-uniform: pushed through redux so that they live in uniform registers)

@@ -173,7 +173,7 @@ def test_random_shapes_pair_kernel_against_item_kernel():
     from tests import runners
     rng = np.random.default_rng(77)
     paths = (scenarios.STRAIGHT_60, scenarios.s_curve_waypoints(), scenarios.arc_waypoints())
-    seen_kinds = set()
+    seen_kinds, seen_feats = set(), set()
     for case in range(28):
         dt = float(rng.choice([0.1, 0.2, 0.25]))
         n_max = int(rng.choice([8, 17, 31, 32, 33, 40, 47, 56]))
@@ -214,8 +214,16 @@ def test_random_shapes_pair_kernel_against_item_kernel():
             ref = run(True)
         got = run(True)
         seen_kinds.add(int(pl.engine.lib.fot_last_sweep_kind(pl.engine._h)))
+        seen_feats.add(int(pl.engine.lib.fot_last_pair_features(pl.engine._h)))
         _assert_same(ref, got)
         lean = run(False)
+        seen_feats.add(int(pl.engine.lib.fot_last_pair_features(pl.engine._h)))
         assert np.array_equal(ref.best_idx, lean.best_idx) and np.array_equal(ref.stats, lean.stats), case
         assert np.array_equal(ref.best_cost.view(np.uint64), lean.best_cost.view(np.uint64)), case
+        if case % 2 == 0:
+            with runners.fot_env(FOT_PAIR_SIMPLE=0):                               # the instantiation with every mode compiled in
+                _assert_same(ref, run(True))
+                assert int(pl.engine.lib.fot_last_pair_features(pl.engine._h)) in (31, -1)
     assert 4 in seen_kinds
+    # the kernel is compiled per mode set: campaign shape, + statics, + outputs, + both, everything -- all of them ran
+    assert {0, 1, 8, 9, 31} <= seen_feats, seen_feats
