@@ -790,8 +790,7 @@ static int launch_all(fot_handle* h, const fot_batch_t* b, const fot_result_t* r
       if ((kPairInstances[i] & need) == need) { feat = kPairInstances[i]; break; }
     pair_kernel(pg.fused_box != 0, feat)<<<(unsigned)n_part, kPairThreads, psmem, st>>>(h->plan, B, O, pg);
     h->last_pair_feat = feat;
-  }
-  else if (use_warp && wg.fused_box) fot_sweep_warp<true><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
+  } else if (use_warp && wg.fused_box) fot_sweep_warp<true><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
   else if (use_warp) fot_sweep_warp<false><<<(unsigned)n_part, wg.threads, wsmem, st>>>(h->plan, B, O, wg);
   else if (use_items && ig.fused_box) fot_sweep_items<true><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
   else if (use_items) fot_sweep_items<false><<<(unsigned)n_part, ig.threads, ismem, st>>>(h->plan, B, O, ig);
