@@ -119,16 +119,18 @@ std::set<fot_handle*> g_live;     // handles alive in this process (fot_reload_o
 }  // namespace
 
 // The instantiations of fot_sweep_pairs that exist (mode sets, PAIR_*), smallest first: the campaign shape, + static
-// obstacles, + per-candidate outputs, + both, everything.
-static const int kPairInstances[] = {0, PAIR_STATIC, PAIR_OUTPUTS, PAIR_STATIC | PAIR_OUTPUTS, PAIR_ALL};
-static const int kPairInstanceCount = 5;
+// obstacles, + per-candidate outputs, + both, the unstaged obstacle block (large sample sets), the violation budget
+// (chance-constrained planning), static obstacles + footprint (the corridor scenarios), everything.
+#define FOT_PAIR_INSTANCES(X) X(0) X(PAIR_STATIC) X(PAIR_OUTPUTS) X(PAIR_STATIC | PAIR_OUTPUTS) X(PAIR_LOOSE) X(PAIR_BUDGET) \
+  X(PAIR_STATIC | PAIR_FOOTPRINT) X(PAIR_ALL)
+#define FOT_PAIR_LIST(f) (f),
+static const int kPairInstances[] = {FOT_PAIR_INSTANCES(FOT_PAIR_LIST)};
+static const int kPairInstanceCount = (int)(sizeof(kPairInstances) / sizeof(kPairInstances[0]));
 typedef void (*PairKernel)(const Plan, const Batch, const Out, const PairGeom);
 static PairKernel pair_kernel(bool fused, int feat) {
   switch (feat) {
-    case 0: return fused ? fot_sweep_pairs<true, 0> : fot_sweep_pairs<false, 0>;
-    case PAIR_STATIC: return fused ? fot_sweep_pairs<true, PAIR_STATIC> : fot_sweep_pairs<false, PAIR_STATIC>;
-    case PAIR_OUTPUTS: return fused ? fot_sweep_pairs<true, PAIR_OUTPUTS> : fot_sweep_pairs<false, PAIR_OUTPUTS>;
-    case PAIR_STATIC | PAIR_OUTPUTS: return fused ? fot_sweep_pairs<true, PAIR_STATIC | PAIR_OUTPUTS> : fot_sweep_pairs<false, PAIR_STATIC | PAIR_OUTPUTS>;
+#define FOT_PAIR_CASE(f) case (f): return fused ? fot_sweep_pairs<true, (f)> : fot_sweep_pairs<false, (f)>;
+    FOT_PAIR_INSTANCES(FOT_PAIR_CASE)
     default: return fused ? fot_sweep_pairs<true, PAIR_ALL> : fot_sweep_pairs<false, PAIR_ALL>;
   }
 }

@@ -225,5 +225,6 @@ def test_random_shapes_pair_kernel_against_item_kernel():
                 _assert_same(ref, run(True))
                 assert int(pl.engine.lib.fot_last_pair_features(pl.engine._h)) in (31, -1)
     assert 4 in seen_kinds
-    # the kernel is compiled per mode set: campaign shape, + statics, + outputs, + both, everything -- all of them ran
+    # the kernel is compiled per mode set (campaign shape, + statics, + outputs, + both, budget, statics + footprint,
+    # everything; the unstaged set runs in the config-3 tests): these ran here
     assert {0, 1, 8, 9, 31} <= seen_feats, seen_feats
