@@ -105,16 +105,19 @@ class DeviceBatch:
             return
         self.engine.run_device(self.batch, self.result, stream)
 
-    def launch_to_host(self, host_out: dict, stream: Optional[int] = None) -> None:
+    def launch_to_host(self, host_out: dict, stream: Optional[int] = None, winner_samples: int = 0) -> None:
         """fot_plan_batch_device_to_host: sweep the (device-resident) batch and deliver the winners into the host
         arrays of `host_out` (keys of `self.out`; torch CPU tensors or NumPy arrays, ideally page-locked): the
         queries run in ranges and each range's winners are copied back while the next range is swept.  `stream`:
-        the raw cudaStream_t on which the batch's inputs become ready (None: they are ready)."""
+        the raw cudaStream_t on which the batch's inputs become ready (None: they are ready).  `winner_samples = k > 0`:
+        only the first k samples of every winner series come back (`host_out["winner"]` is [n_q, 15, k]) -- what a
+        closed-loop caller consumes (integrated_simulator.py:663), 240 B instead of 6.1 KB per query at k = 2."""
         import ctypes as C
         ptr = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
         r = _lib.FotResult()
         r.best_idx, r.best_cost, r.stats = ptr(host_out["best_idx"]), ptr(host_out["best_cost"]), ptr(host_out["stats"])
         r.winner_len, r.winner = ptr(host_out["winner_len"]), ptr(host_out["winner"])
+        r.winner_samples = int(winner_samples)
         _lib.check(self.engine.lib.fot_plan_batch_device_to_host(self.engine._h, C.byref(self.batch), C.byref(r),
                                                                  C.c_void_p(stream) if stream else None),
                    "fot_plan_batch_device_to_host")
