@@ -192,3 +192,27 @@ def test_full_size_batch_properties():
     first = inv.reshape(reps, -1)[0]
     for j, i in enumerate(sample):
         assert int(res.best_idx[first[i]]) == refs[j].best_index
+
+
+def test_device_batch_to_host_compact_read_back():
+    """DeviceBatch.launch_to_host(winner_samples=k): the first k samples of every winner series, equal to the head of the
+    full read-back; indices, costs and histograms unchanged."""
+    from integrated_path_planning_b200 import _lib
+    from integrated_path_planning_b200.batch import DeviceBatch
+    rng = np.random.default_rng(41)
+    n = 300
+    frenet = _random_frenet(rng, n)
+    dyn = np.stack([scenarios.pedestrian_field(rng, 20) for _ in range(n)])[:, None]
+    pl = _planner()
+    db = DeviceBatch(pl, frenet, 6.0, dyn, _lib.FOT_DYN_SINGLE)
+    full = {k: np.zeros(tuple(v.shape), dtype=v.cpu().numpy().dtype) for k, v in db.out.items()}
+    db.launch_to_host(full)
+    k_head = 2
+    head = {k: (np.zeros((n, v.shape[1], k_head)) if k == "winner" else np.zeros_like(v)) for k, v in full.items()}
+    db.launch_to_host(head, winner_samples=k_head)
+    for key in ("best_idx", "stats", "winner_len"):
+        assert np.array_equal(full[key], head[key]), key
+    assert np.array_equal(full["best_cost"].view(np.uint64), head["best_cost"].view(np.uint64))
+    has = full["best_idx"] >= 0
+    assert has.sum() > 20
+    assert np.array_equal(head["winner"][has].view(np.uint64), full["winner"][has][:, :, :k_head].view(np.uint64))
